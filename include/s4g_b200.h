@@ -1,0 +1,127 @@
+/*
+ * s4g_b200 — C ABI of the B200-native PointNet++ hot path of S4G.
+ *
+ * This is the drop-in boundary: every entry point replaces one function of the reference's
+ * `pn2_ext` torch extension (yzqin/s4g-release,
+ * inference/grasp_proposal/network_models/models/pointnet2_utils/csrc/main.cpp:7-13) or one fused
+ * stage of the module stack above it.  Plain pointers and sizes only; no torch types.
+ *
+ * Conventions
+ *   - all pointers are DEVICE pointers on the current CUDA device unless a name ends in `_host`;
+ *   - tensors use the reference's interface layout: fp32, channel-first (B, C, N), contiguous;
+ *     indices are int64 (the `_i32` variants feed the fused path);
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream); all work is
+ *     enqueued on it and nothing synchronises the host;
+ *   - return value: 0 on success, otherwise a negative S4G_E_* code (argument errors, mirroring
+ *     the reference's CHECK_* macros) or a positive cudaError_t; s4g_last_error() gives the text
+ *     (thread-local).  Inputs are never modified; outputs are written completely (no need to
+ *     pre-zero them).
+ */
+#ifndef S4G_B200_H_
+#define S4G_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define S4G_OK 0
+#define S4G_E_ARG (-1)         /* a CHECK_* precondition of the reference failed            */
+#define S4G_E_UNSUPPORTED (-2) /* valid for the reference, not (yet) supported by this build */
+
+/* ABI version of this header (bumped on any signature change). */
+int s4g_version(void);
+/* Text of the last error raised on the calling thread ("" if none). */
+const char* s4g_last_error(void);
+
+/* ---- pn2_ext replacements --------------------------------------------------------------- */
+
+/* farthest_point_sample — csrc/sampling.h:7-9, sampling_kernel.cu:128-172.
+ * points (B,3,N) -> index (B,M) int64.  index[:,0] = 0; reproduces the reference's tie-breaking
+ * (block tree reduction, sampling_kernel.cu:100-113) exactly.  Requires N >= M > 0. */
+int s4g_farthest_point_sample_f32(const float* points, int B, int N, int M, int64_t* index, void* stream);
+int s4g_farthest_point_sample_f32_i32(const float* points, int B, int N, int M, int32_t* index, void* stream);
+
+/* gather_points — pointnet2_utils/functions.py:10-25.  out[b,c,m] = points[b,c,index[b,m]]. */
+int s4g_gather_points_f32(const float* points, const int64_t* index, int B, int C, int N, int M, float* out,
+                          void* stream);
+
+/* ball_query — csrc/ball_query.h:7-11, ball_query_kernel.cu:89-133.
+ * points (B,3,N), centroids (B,3,M) -> index (B,M,K) int64, count (B,M) int64 (count may be NULL).
+ * First K points in index order with d2 < radius*radius (strict, fp32); the first hit pads every
+ * unused slot; no hit -> zeros and count 0. */
+int s4g_ball_query_f32(const float* points, const float* centroids, int B, int N, int M, float radius, int K,
+                       int64_t* index, int64_t* count, void* stream);
+int s4g_ball_query_f32_i32(const float* points, const float* centroids, int B, int N, int M, float radius, int K,
+                           int32_t* index, int32_t* count, void* stream);
+
+/* group_points_forward / backward — csrc/grouping.h:7-14, grouping_kernel.cu:32-54,106-152.
+ * fwd: input (B,C,N), index (B,M,K) -> out (B,C,M,K).   bwd: grad_out (B,C,M,K) -> grad_in (B,C,N). */
+int s4g_group_points_forward_f32(const float* input, const int64_t* index, int B, int C, int N, int M, int K,
+                                 float* out, void* stream);
+int s4g_group_points_backward_f32(const float* grad_out, const int64_t* index, int B, int C, int N, int M, int K,
+                                  float* grad_in, void* stream);
+
+/* point_search (3-NN) — csrc/interpolate.h:8-11, interpolate_kernel.cu:92-132.
+ * query (B,3,Nq), key (B,3,Nk) -> index (B,Nq,3) int64, distance (B,Nq,3) = SQUARED distances,
+ * ascending, earlier key wins ties.  num_neighbours must be 3 and Nk >= 3. */
+int s4g_point_search_f32(const float* query, const float* key, int B, int Nq, int Nk, int num_neighbours,
+                         int64_t* index, float* distance, void* stream);
+
+/* interpolate_forward / backward — csrc/interpolate.h:13-22, interpolate_kernel.cu:191-236,296-341.
+ * fwd: input (B,C,Nk), index (B,Nq,3), weight (B,Nq,3) -> out (B,C,Nq);  bwd scatters grad*w. */
+int s4g_interpolate_forward_f32(const float* input, const int64_t* index, const float* weight, int B, int C, int Nk,
+                                int Nq, float* out, void* stream);
+int s4g_interpolate_backward_f32(const float* grad_out, const int64_t* index, const float* weight, int B, int C,
+                                 int Nk, int Nq, float* grad_in, void* stream);
+
+/* ---- fused inference path (channel-last bf16 features, int32 indices) ---------------------- */
+
+/* PointSearch (interpolate_kernel.cu:33-81) fused with the inverse-squared-distance weights of
+ * FeatureInterpolator.forward (pointnet2_utils/modules.py:115-120).  index (B,Nq,3) int32,
+ * weight (B,Nq,3) fp32 (normalised). */
+int s4g_three_nn_weights_f32_i32(const float* query, const float* key, int B, int Nq, int Nk, int* index,
+                                 float* weight, void* stream);
+
+/* InterpolateForward (interpolate_kernel.cu:139-181) + channel concat (modules.py:124-127).
+ * sparse [B*Nk][C2] bf16, dense [B*Nq][C1] bf16 (NULL when C1 == 0) -> out [B*Nq][C2+C1] bf16. */
+int s4g_interp_concat_bf16(const void* sparse, const int* index, const float* weight, const void* dense, int B, int Nk,
+                           int Nq, int C2, int C1, void* out, void* stream);
+
+/* gather_points for xyz with int32 indices (functions.py:10-25): (B,3,N),(B,M) -> (B,3,M). */
+int s4g_gather_xyz_f32_i32(const float* xyz, const int* index, int B, int N, int M, float* out, void* stream);
+
+/* Fused shared-MLP chain on tcgen05 tensor cores (csrc/mlp_chain.cu): replaces
+ * SharedMLP / Conv1d / Conv2d (nn_utils/mlp.py:95-106, nn_utils/conv.py:30-36,70-76) with eval-mode
+ * BatchNorm folded in, and around it the grouping + max-pool of PointNetSAModule.forward
+ * (pointnet2_utils/modules.py:208-244) or the final biased 1x1 conv (+sigmoid) of the heads
+ * (models/PointNet2_tcls.py:126-148).
+ *   in_mode : 0 = bf16 rows [P][stride];  1 = gathered set-abstraction input (feat_c feature channels
+ *             + relative xyz; reference channel order [xyz | feat] is handled by the weight packer)
+ *   out_mode: 2 = bf16 rows [P][out_c];  3 = max-pool over groups of `group` rows -> bf16 [P/group][out_c];
+ *             4 = fp32 logits, channel-first (P/n_points, out_c, n_points), bias, optional sigmoid
+ * Layer l computes relu?(W_l x + bias_l) with W_l (cout x cin, fp32, BN-folded) packed to bf16 by
+ * s4g_chain_pack_weights into a host buffer of s4g_chain_weight_bytes(); copy it to the device and
+ * register it together with the per-layer fp32 shift vectors (length s4g_chain_cout_pad, zero padded). */
+typedef struct s4g_chain s4g_chain;
+s4g_chain* s4g_chain_create(int n_layers, const int* cin, const int* cout, const int* relu, int in_mode, int feat_c,
+                            int out_mode, int out_c, int group, int sigmoid);
+void s4g_chain_destroy(s4g_chain* chain);
+size_t s4g_chain_weight_bytes(const s4g_chain* chain);
+int s4g_chain_cout_pad(const s4g_chain* chain, int layer);
+int s4g_chain_info(const s4g_chain* chain, int* n_phases, int* act_c, int* stages, int* tmem_cols, int* smem_bytes,
+                   int* ctas_per_sm);
+int s4g_chain_pack_weights(const s4g_chain* chain, int layer, const float* w_host, int cout_real, int cin_real,
+                           void* packed_host);
+int s4g_chain_set_params(s4g_chain* chain, const void* weights_dev, const float* const* bias_dev);
+int s4g_chain_run_rows(const s4g_chain* chain, const void* in_rows, int in_stride, long long P, void* out,
+                       int n_points, void* stream);
+int s4g_chain_run_gather(const s4g_chain* chain, const void* feat, const float* xyz, const float* ctr, const int* nbr,
+                         int B, int N, int M, int K, void* out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* S4G_B200_H_ */

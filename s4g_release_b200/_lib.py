@@ -1,0 +1,76 @@
+"""ctypes binding of the C ABI declared in include/s4g_b200.h.
+
+There is NO fallback: if ``libs4g_b200.so`` is missing the import fails loudly, and every entry point
+refuses CPU tensors (like the reference's CHECK_CUDA).  The oracle under oracle/ is never used here.
+"""
+import ctypes
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libs4g_b200.so")
+
+if not os.path.exists(LIB_PATH):
+    raise ImportError(
+        "s4g_release_b200: %s is missing — build the CUDA library first "
+        "(python -c 'import __graft_entry__ as g; g.build()' or python s4g_release_b200/build.py). "
+        "There is no CPU fallback." % LIB_PATH)
+
+lib = ctypes.CDLL(LIB_PATH)
+
+_vp = ctypes.c_void_p
+_i = ctypes.c_int
+_f = ctypes.c_float
+_ip = ctypes.POINTER(ctypes.c_int)
+
+_SIGNATURES = {
+    "s4g_version": ([], _i),
+    "s4g_last_error": ([], ctypes.c_char_p),
+    "s4g_farthest_point_sample_f32": ([_vp, _i, _i, _i, _vp, _vp], _i),
+    "s4g_farthest_point_sample_f32_i32": ([_vp, _i, _i, _i, _vp, _vp], _i),
+    "s4g_gather_points_f32": ([_vp, _vp, _i, _i, _i, _i, _vp, _vp], _i),
+    "s4g_ball_query_f32": ([_vp, _vp, _i, _i, _i, _f, _i, _vp, _vp, _vp], _i),
+    "s4g_ball_query_f32_i32": ([_vp, _vp, _i, _i, _i, _f, _i, _vp, _vp, _vp], _i),
+    "s4g_group_points_forward_f32": ([_vp, _vp, _i, _i, _i, _i, _i, _vp, _vp], _i),
+    "s4g_group_points_backward_f32": ([_vp, _vp, _i, _i, _i, _i, _i, _vp, _vp], _i),
+    "s4g_point_search_f32": ([_vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp], _i),
+    "s4g_interpolate_forward_f32": ([_vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp], _i),
+    "s4g_interpolate_backward_f32": ([_vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp], _i),
+    "s4g_three_nn_weights_f32_i32": ([_vp, _vp, _i, _i, _i, _vp, _vp, _vp], _i),
+    "s4g_interp_concat_bf16": ([_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp], _i),
+    "s4g_gather_xyz_f32_i32": ([_vp, _vp, _i, _i, _i, _vp, _vp], _i),
+    "s4g_chain_create": ([_i, _ip, _ip, _ip, _i, _i, _i, _i, _i, _i], _vp),
+    "s4g_chain_destroy": ([_vp], None),
+    "s4g_chain_weight_bytes": ([_vp], ctypes.c_size_t),
+    "s4g_chain_cout_pad": ([_vp, _i], _i),
+    "s4g_chain_info": ([_vp, _ip, _ip, _ip, _ip, _ip, _ip], _i),
+    "s4g_chain_pack_weights": ([_vp, _i, _vp, _i, _i, _vp], _i),
+    "s4g_chain_set_params": ([_vp, _vp, _vp], _i),
+    "s4g_chain_run_rows": ([_vp, _vp, _i, ctypes.c_longlong, _vp, _i, _vp], _i),
+    "s4g_chain_run_gather": ([_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp], _i),
+}
+
+for _name, (_args, _res) in _SIGNATURES.items():
+    _fn = getattr(lib, _name)
+    _fn.argtypes = _args
+    _fn.restype = _res
+
+
+def exported_symbols():
+    return sorted(_SIGNATURES)
+
+
+def check(status, what):
+    """Non-zero status -> RuntimeError, as the reference's TORCH_CHECK macros raise."""
+    if status != 0:
+        msg = lib.s4g_last_error().decode("utf-8", "replace")
+        raise RuntimeError("%s failed (status %d): %s" % (what, status, msg))
+
+
+def stream_ptr(device):
+    return ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def ptr(t):
+    return ctypes.c_void_p(t.data_ptr())

@@ -1,0 +1,84 @@
+"""Host handle of one fused tcgen05 MLP chain (csrc/mlp_chain.cu) — plans the chain through the C ABI,
+packs the BN-folded weights to the kernel's bf16 chunk stream and keeps the device buffers alive."""
+import ctypes
+
+import numpy as np
+import torch
+
+from ._lib import check, lib, ptr, stream_ptr
+
+IN_ROWS, IN_GATHER = 0, 1
+OUT_ROWS, OUT_MAXPOOL, OUT_LOGITS = 2, 3, 4
+
+
+def _int_array(values):
+    return (ctypes.c_int * len(values))(*[int(v) for v in values])
+
+
+class MlpChain:
+    """layers: list of (W fp32 [cout, cin] BN-folded, shift fp32 [cout], relu: bool)."""
+
+    def __init__(self, layers, device, in_mode=IN_ROWS, feat_c=0, out_mode=OUT_ROWS, group=1, sigmoid=False):
+        self.device = torch.device(device)
+        self.n_layers = len(layers)
+        self.cin = [int(w.shape[1]) for w, _, _ in layers]
+        self.cout = [int(w.shape[0]) for w, _, _ in layers]
+        self.in_mode, self.out_mode, self.group = in_mode, out_mode, group
+        self.out_c = self.cout[-1]
+        relu = [1 if r else 0 for _, _, r in layers]
+        self._h = lib.s4g_chain_create(self.n_layers, _int_array(self.cin), _int_array(self.cout), _int_array(relu),
+                                       in_mode, feat_c, out_mode, self.out_c, group, 1 if sigmoid else 0)
+        if not self._h:
+            raise RuntimeError("s4g_chain_create failed: " + lib.s4g_last_error().decode())
+        nbytes = lib.s4g_chain_weight_bytes(self._h)
+        packed = np.zeros(nbytes, dtype=np.uint8)
+        for l, (w, _, _) in enumerate(layers):
+            w32 = np.ascontiguousarray(w.detach().float().cpu().numpy())
+            check(lib.s4g_chain_pack_weights(self._h, l, w32.ctypes.data_as(ctypes.c_void_p), w32.shape[0],
+                                             w32.shape[1], packed.ctypes.data_as(ctypes.c_void_p)), "chain_pack_weights")
+        self.weights = torch.from_numpy(packed).to(self.device)
+        self.bias = []
+        for l, (_, b, _) in enumerate(layers):
+            pad = lib.s4g_chain_cout_pad(self._h, l)
+            t = torch.zeros(pad, dtype=torch.float32, device=self.device)
+            t[: b.numel()] = b.detach().float().to(self.device)
+            self.bias.append(t)
+        self._bias_ptrs = (ctypes.c_void_p * self.n_layers)(*[t.data_ptr() for t in self.bias])
+        check(lib.s4g_chain_set_params(self._h, ptr(self.weights), ctypes.cast(self._bias_ptrs, ctypes.c_void_p)),
+              "chain_set_params")
+
+    def info(self):
+        vals = [ctypes.c_int() for _ in range(6)]
+        check(lib.s4g_chain_info(self._h, *[ctypes.byref(v) for v in vals]), "chain_info")
+        keys = ("n_phases", "act_c", "stages", "tmem_cols", "smem_bytes", "ctas_per_sm")
+        return {k: v.value for k, v in zip(keys, vals)}
+
+    def flops(self, rows):
+        return 2.0 * rows * sum(ci * co for ci, co in zip(self.cin, self.cout))
+
+    def run_rows(self, x, n_points=0):
+        """x: bf16 [P, stride] channel-last (stride >= cin).  Returns bf16 [P, out_c] or fp32 (B, out_c, n_points)."""
+        assert x.is_cuda and x.dtype == torch.bfloat16 and x.dim() == 2 and x.stride(1) == 1
+        P = x.shape[0]
+        if self.out_mode == OUT_LOGITS:
+            out = torch.empty((P // n_points, self.out_c, n_points), dtype=torch.float32, device=x.device)
+        else:
+            out = torch.empty((P, self.out_c), dtype=torch.bfloat16, device=x.device)
+        check(lib.s4g_chain_run_rows(self._h, ptr(x), x.stride(0), P, ptr(out), n_points, stream_ptr(x.device)),
+              "chain_run_rows")
+        return out
+
+    def run_gather(self, feat, xyz, ctr, nbr):
+        """feat: bf16 [B*N, C] or None; xyz (B,3,N) fp32; ctr (B,3,M) fp32; nbr (B,M,K) int32."""
+        B, _, N = xyz.shape
+        M, K = nbr.shape[1], nbr.shape[2]
+        rows = B * M if self.out_mode == OUT_MAXPOOL else B * M * K
+        out = torch.empty((rows, self.out_c), dtype=torch.bfloat16, device=xyz.device)
+        check(lib.s4g_chain_run_gather(self._h, ptr(feat) if feat is not None else None, ptr(xyz), ptr(ctr), ptr(nbr),
+                                       B, N, M, K, ptr(out), stream_ptr(xyz.device)), "chain_run_gather")
+        return out
+
+    def __del__(self):
+        h, self._h = getattr(self, "_h", None), None
+        if h:
+            lib.s4g_chain_destroy(h)

@@ -1,0 +1,25 @@
+// Error plumbing and version of the C ABI (include/s4g_b200.h).
+#include <stdarg.h>
+#include <string.h>
+
+#include "common.cuh"
+
+namespace s4g {
+
+char* error_buffer() {
+  static thread_local char buf[512] = {0};
+  return buf;
+}
+
+int set_error(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(error_buffer(), 512, fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+}  // namespace s4g
+
+extern "C" int s4g_version(void) { return 1; }
+extern "C" const char* s4g_last_error(void) { return s4g::error_buffer(); }

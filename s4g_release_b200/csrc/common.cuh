@@ -1,0 +1,51 @@
+// Shared helpers for the sm_100a kernels behind include/s4g_b200.h.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/s4g_b200.h"
+
+namespace s4g {
+
+// thread-local error text, returned by s4g_last_error()
+char* error_buffer();
+int set_error(int code, const char* fmt, ...);
+
+#define S4G_CHECK_ARG(cond, ...)                               \
+  do {                                                         \
+    if (!(cond)) return s4g::set_error(S4G_E_ARG, __VA_ARGS__); \
+  } while (0)
+
+#define S4G_CUDA(expr)                                                                          \
+  do {                                                                                          \
+    cudaError_t _e = (expr);                                                                    \
+    if (_e != cudaSuccess) return s4g::set_error((int)_e, "%s: %s", #expr, cudaGetErrorString(_e)); \
+  } while (0)
+
+#define S4G_LAUNCH_CHECK(name)                                                                 \
+  do {                                                                                         \
+    cudaError_t _e = cudaGetLastError();                                                       \
+    if (_e != cudaSuccess) return s4g::set_error((int)_e, "%s launch: %s", name, cudaGetErrorString(_e)); \
+  } while (0)
+
+// Squared distance with exactly the rounding sequence nvcc emits for the reference expression
+// (x2-x1)*(x2-x1)+(y2-y1)*(y2-y1)+(z2-z1)*(z2-z1) under -fmad=true (checked in the SASS of the
+// reference objects, oracle/_ref):  FMUL dy*dy ; FFMA dx*dx + . ; FFMA dz*dz + .
+// The _rn intrinsics are never re-contracted by the compiler.
+__device__ __forceinline__ float sqdist(float dx, float dy, float dz) {
+  return __fmaf_rn(dz, dz, __fmaf_rn(dx, dx, __fmul_rn(dy, dy)));
+}
+
+inline int num_sms() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+  }
+  return n;
+}
+
+}  // namespace s4g

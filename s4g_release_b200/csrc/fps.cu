@@ -1,0 +1,223 @@
+// Farthest point sampling for sm_100a — replaces FarthestPointSample / FarthestPointSampleKernel
+// (reference: pointnet2_utils/csrc/sampling_kernel.cu:49-119,128-172).
+//
+// Design (B200-first, not a port of the reference's global-memory loop):
+//   * one thread-block CLUSTER per cloud (1, 2, 4 or 8 CTAs of 512 threads, chosen so that
+//     B x CLUSTER fills the 148 SMs and the cloud fits on chip);
+//   * every point lives in REGISTERS for the whole kernel (x, y, z and its running min-distance,
+//     P points per thread) — the M-1 dependent iterations never touch HBM or L2 again;
+//   * per iteration: P fused distance/min/argmax updates per thread, a two-instruction warp argmax
+//     (REDUX.MAX on the distance bits, REDUX.MIN on a tie-break key), one 24-byte record per warp
+//     pushed into every CTA of the cluster through distributed shared memory, ONE barrier
+//     (__syncthreads or barrier.cluster), and a second warp-REDUX over the <=128 records that every
+//     warp performs redundantly, so there is no broadcast step;
+//   * the winner's coordinates travel with its record (read from a shared-memory copy of the cloud
+//     by the owning lane), so the next iteration starts without a global load.
+//
+// Tie-breaking.  The reference reduces BLOCK = min(nextpow2(N),512) per-thread candidates with a
+// shared-memory tree (offset = BLOCK/2 .. 1) that keeps the LOWER slot on ties, after each thread
+// kept the first strict maximum of its strided points.  That tournament is a total order:
+//     larger distance first, then smaller bitreverse_{log2 BLOCK}(j mod BLOCK), then smaller j,
+// and if the maximum distance is 0 the previous index repeats.  The key below encodes exactly that
+// order, so any reduction shape gives the reference's answer bit-for-bit:
+//     tb(j) = __brev(j & (BLOCK-1)) | (j >> log2 BLOCK)        (minimised among equal distances)
+#include <cooperative_groups.h>
+
+#include "common.cuh"
+
+namespace cg = cooperative_groups;
+
+namespace s4g {
+
+constexpr int kFpsThreads = 512;
+constexpr int kFpsWarps = kFpsThreads / 32;
+
+template <int P, int CLUSTER, typename IndexT>
+__global__ void __launch_bounds__(kFpsThreads, 1)
+fps_kernel(const float* __restrict__ points, int N, int M, int L, IndexT* __restrict__ index) {
+  extern __shared__ float s_xyz[];  // [3][kFpsThreads * P]: this CTA's slice of the cloud
+  constexpr int kLocal = kFpsThreads * P;
+  constexpr int kEntries = kFpsWarps * CLUSTER;
+  __shared__ uint2 s_key[2][kEntries];   // (distance bits, tie-break key) per warp of the cluster
+  __shared__ float4 s_pos[2][kEntries];  // coordinates of that warp's candidate
+
+  const int t = threadIdx.x;
+  const int lane = t & 31;
+  const int warp = t >> 5;
+  unsigned rank = 0;
+  if constexpr (CLUSTER > 1) rank = cg::this_cluster().block_rank();
+  const int cloud = blockIdx.x / CLUSTER;
+  const float* X = points + (size_t)cloud * 3 * N;
+  const float* Y = X + N;
+  const float* Z = Y + N;
+  IndexT* out = index + (size_t)cloud * M;
+
+  float* sx = s_xyz;
+  float* sy = s_xyz + kLocal;
+  float* sz = s_xyz + 2 * kLocal;
+
+  // Thread t of CTA `rank` owns points j = t + 512 * (rank * P + p), p = 0..P-1: increasing j and
+  // (for BLOCK = 512) a constant reduction slot, so "first strict maximum" inside the thread is
+  // the reference's per-thread rule.
+  const int chunk = rank * P;
+  float px[P], py[P], pz[P], dist[P];
+#pragma unroll
+  for (int p = 0; p < P; ++p) {
+    const int j = t + kFpsThreads * (chunk + p);
+    const bool valid = j < N;
+    px[p] = valid ? X[j] : 0.f;
+    py[p] = valid ? Y[j] : 0.f;
+    pz[p] = valid ? Z[j] : 0.f;
+    dist[p] = valid ? __int_as_float(0x7f800000) : 0.f;  // padding can never exceed a real point
+    sx[p * kFpsThreads + t] = px[p];
+    sy[p * kFpsThreads + t] = py[p];
+    sz[p * kFpsThreads + t] = pz[p];
+  }
+  const unsigned bmask = (1u << L) - 1u;
+  const unsigned lowmask = (L == 0) ? 0xffffffffu : ((1u << (32 - L)) - 1u);
+
+  int cur = 0;
+  float cx = X[0], cy = Y[0], cz = Z[0];
+  if (rank == 0 && t == 0) out[0] = 0;
+
+  if constexpr (CLUSTER > 1) cg::this_cluster().sync();  // peers are resident before any DSMEM store
+  else __syncthreads();
+
+  for (int i = 1; i < M; ++i) {
+    const int buf = i & 1;
+    float best = 0.f;
+    int bi = 0;
+#pragma unroll
+    for (int p = 0; p < P; ++p) {
+      const float d = sqdist(__fsub_rn(px[p], cx), __fsub_rn(py[p], cy), __fsub_rn(pz[p], cz));
+      const float dd = fminf(dist[p], d);
+      dist[p] = dd;
+      if (dd > best) { best = dd; bi = p; }
+    }
+    // ---- warp argmax: 2 REDUX ----
+    const unsigned db = __float_as_uint(best);  // distances are >= 0: bit order == value order
+    const unsigned wmax = __reduce_max_sync(0xffffffffu, db);
+    const unsigned j = (unsigned)(t + kFpsThreads * (chunk + bi));
+    const unsigned tb = (db == wmax) ? (__brev(j & bmask) | (j >> L)) : 0xffffffffu;
+    const unsigned wtb = __reduce_min_sync(0xffffffffu, tb);
+    if (tb == wtb) {  // exactly one lane: keys are distinct per point
+      const int lp = bi * kFpsThreads + t;
+      const uint2 key = make_uint2(wmax, wtb);
+      const float4 pos = make_float4(sx[lp], sy[lp], sz[lp], 0.f);
+      const int e = rank * kFpsWarps + warp;
+      if constexpr (CLUSTER > 1) {
+        cg::cluster_group cluster = cg::this_cluster();
+#pragma unroll
+        for (int q = 0; q < CLUSTER; ++q) {
+          uint2* rk = cluster.map_shared_rank(&s_key[buf][e], q);
+          float4* rp = cluster.map_shared_rank(&s_pos[buf][e], q);
+          *rk = key;
+          *rp = pos;
+        }
+      } else {
+        s_key[buf][e] = key;
+        s_pos[buf][e] = pos;
+      }
+    }
+    if constexpr (CLUSTER > 1) cg::this_cluster().sync();
+    else __syncthreads();
+    // ---- every warp reduces the cluster's records redundantly ----
+    unsigned d = 0u, k = 0xffffffffu;
+    int e = 0;
+#pragma unroll
+    for (int q = lane; q < kEntries; q += 32) {
+      const uint2 kv = s_key[buf][q];
+      if (kv.x > d || (kv.x == d && kv.y < k)) { d = kv.x; k = kv.y; e = q; }
+    }
+    const unsigned gmax = __reduce_max_sync(0xffffffffu, d);
+    const unsigned gk = __reduce_min_sync(0xffffffffu, (d == gmax) ? k : 0xffffffffu);
+    const unsigned who = __ballot_sync(0xffffffffu, d == gmax && k == gk);
+    const int src = __ffs(who) - 1;
+    const int ge = __shfl_sync(0xffffffffu, e, src);
+    if (gmax != 0u) {  // all remaining distances 0 -> the reference repeats the previous index
+      const float4 pos = s_pos[buf][ge];
+      cx = pos.x; cy = pos.y; cz = pos.z;
+      cur = (int)(__brev(gk & ~lowmask) + ((gk & lowmask) << L));
+    }
+    if (rank == 0 && t == 0) out[i] = (IndexT)cur;
+  }
+}
+
+template <int P, int CLUSTER, typename IndexT>
+static int launch_fps(const float* points, int B, int N, int M, int L, IndexT* index, cudaStream_t stream) {
+  auto kern = fps_kernel<P, CLUSTER, IndexT>;
+  const size_t smem = (size_t)3 * kFpsThreads * P * sizeof(float);
+  S4G_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)(B * CLUSTER));
+  cfg.blockDim = dim3(kFpsThreads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CLUSTER;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  S4G_CUDA(cudaLaunchKernelEx(&cfg, kern, points, N, M, L, index));
+  return S4G_OK;
+}
+
+template <int CLUSTER, typename IndexT>
+static int dispatch_p(int P, const float* points, int B, int N, int M, int L, IndexT* index, cudaStream_t stream) {
+#define S4G_FPS_CASE(PP) \
+  if (P <= PP) return launch_fps<PP, CLUSTER, IndexT>(points, B, N, M, L, index, stream);
+  S4G_FPS_CASE(1)
+  S4G_FPS_CASE(2)
+  S4G_FPS_CASE(4)
+  S4G_FPS_CASE(7)
+  S4G_FPS_CASE(10)
+  S4G_FPS_CASE(13)
+  S4G_FPS_CASE(16)
+  S4G_FPS_CASE(20)
+  S4G_FPS_CASE(25)
+#undef S4G_FPS_CASE
+  return set_error(S4G_E_UNSUPPORTED, "farthest_point_sample: %d points per thread exceeds the register budget", P);
+}
+
+constexpr int kFpsMaxP = 25;
+
+template <typename IndexT>
+static int fps_entry(const float* points, int B, int N, int M, IndexT* index, cudaStream_t stream) {
+  S4G_CHECK_ARG(points != nullptr && index != nullptr, "farthest_point_sample: null pointer");
+  S4G_CHECK_ARG(B >= 0 && N > 0, "farthest_point_sample: bad shape B=%d N=%d", B, N);
+  S4G_CHECK_ARG(M > 0, "farthest_point_sample: num_centroids <= 0");           // CHECK_GT, sampling_kernel.cu:138
+  S4G_CHECK_ARG(N >= M, "farthest_point_sample: num_points < num_centroids");  // CHECK_GE, :139
+  if (B == 0) return S4G_OK;
+  // BLOCK of the reference (sampling_kernel.cu:34-42,150-167) only enters through the tie rule.
+  int L = 0;
+  while ((1 << L) < N && L < 9) ++L;
+  if (L < 4) L = 4;
+  // smallest cluster that holds the cloud in registers, then grow it while the GPU has idle SMs
+  int cluster = 1;
+  while (cluster < 8 && (N + kFpsThreads * cluster - 1) / (kFpsThreads * cluster) > kFpsMaxP) cluster *= 2;
+  if ((N + kFpsThreads * cluster - 1) / (kFpsThreads * cluster) > kFpsMaxP)
+    return set_error(S4G_E_UNSUPPORTED, "farthest_point_sample: N=%d exceeds the on-chip capacity (%d points)", N,
+                     kFpsThreads * 8 * kFpsMaxP);
+  const int sms = num_sms();
+  while (cluster < 8 && B * cluster * 2 <= sms && N > kFpsThreads * cluster) cluster *= 2;
+  const int P = (N + kFpsThreads * cluster - 1) / (kFpsThreads * cluster);
+  switch (cluster) {
+    case 1: return dispatch_p<1, IndexT>(P, points, B, N, M, L, index, stream);
+    case 2: return dispatch_p<2, IndexT>(P, points, B, N, M, L, index, stream);
+    case 4: return dispatch_p<4, IndexT>(P, points, B, N, M, L, index, stream);
+    default: return dispatch_p<8, IndexT>(P, points, B, N, M, L, index, stream);
+  }
+}
+
+}  // namespace s4g
+
+extern "C" int s4g_farthest_point_sample_f32(const float* points, int B, int N, int M, int64_t* index, void* stream) {
+  return s4g::fps_entry<int64_t>(points, B, N, M, index, (cudaStream_t)stream);
+}
+
+extern "C" int s4g_farthest_point_sample_f32_i32(const float* points, int B, int N, int M, int32_t* index,
+                                                 void* stream) {
+  return s4g::fps_entry<int32_t>(points, B, N, M, index, (cudaStream_t)stream);
+}

@@ -1,0 +1,256 @@
+"""Fused inference engine for PN2_CLS on one B200.
+
+Geometry (FPS, ball query, 3-NN) runs in fp32 with the hand-written sm_100a kernels through the C ABI
+(int32 indices, no transposed copies).  The shared MLPs (set abstraction incl. gather + max-pool,
+feature propagation, heads) run as fused chains with eval-mode BatchNorm folded into a per-channel
+scale/shift (reference nn_utils/conv.py:70-76 → y = relu(W'x + b')).
+
+``mlp_backend``
+  * ``"tcgen05"`` — the product path: csrc/mlp_chain.cu (bf16 operands, fp32 accumulation in TMEM);
+  * ``"torch"``   — plain torch fp32 matmuls on the same folded weights.  Kept ONLY as the on-device
+    fp32 reference the numerics tests compare the tcgen05 kernels against; it is not a fallback —
+    nothing selects it implicitly.
+"""
+import torch
+
+from ._lib import check, lib, ptr, stream_ptr
+from .chain import IN_GATHER, IN_ROWS, OUT_LOGITS, OUT_MAXPOOL, OUT_ROWS, MlpChain
+
+BN_EPS = 1e-5
+
+
+def _fold_block(block):
+    """conv (no bias) + BN(eval) -> (W', b') with y = W' x + b'."""
+    w = block.conv.weight.detach().float()
+    w = w.reshape(w.shape[0], w.shape[1])
+    bn = block.bn
+    scale = bn.weight.detach().float() / torch.sqrt(bn.running_var.detach().float() + bn.eps)
+    shift = bn.bias.detach().float() - bn.running_mean.detach().float() * scale
+    return (w * scale[:, None]).contiguous(), shift.contiguous()
+
+
+def _fold_mlp(mlp):
+    return [_fold_block(b) for b in mlp]
+
+
+class FusedPointNet2:
+    def __init__(self, model, mlp_backend="tcgen05"):
+        self.cfg = model.config
+        self.device = next(model.parameters()).device
+        if self.device.type != "cuda":
+            raise RuntimeError("FusedPointNet2 needs the model on a CUDA device (there is no CPU path)")
+        self.mlp_backend = mlp_backend
+        self.sa = [_fold_mlp(m.mlp) for m in model.sa_modules]
+        self.fp = [_fold_mlp(m.mlp) for m in model.fp_modules]
+        heads = []
+        for mlp, logit in ((model.mlp_seg, model.seg_logit), (model.mlp_R, model.R_logit),
+                           (model.mlp_t, model.t_logit), (model.mlp_movable, model.movable_logit[0])):
+            w = logit.weight.detach().float()
+            heads.append((_fold_mlp(mlp), w.reshape(w.shape[0], w.shape[1]).contiguous(),
+                          logit.bias.detach().float().contiguous()))
+        self.heads = heads
+        if mlp_backend == "tcgen05":
+            self._build_chains()
+        elif mlp_backend != "torch":
+            raise ValueError("mlp_backend must be 'tcgen05' or 'torch'")
+
+    def _row_chains(self, layers):
+        """Split a row chain wherever a hidden activation is too wide to stay on chip (> 512 channels)."""
+        chains, cur = [], []
+        for i, (w, b) in enumerate(layers):
+            cur.append((w, b, True))
+            if i + 1 < len(layers) and w.shape[0] > 512:
+                chains.append(MlpChain(cur, self.device, IN_ROWS, 0, OUT_ROWS))
+                cur = []
+        chains.append(MlpChain(cur, self.device, IN_ROWS, 0, OUT_ROWS))
+        return chains
+
+    def _build_chains(self):
+        cfg = self.cfg
+        self.sa_chains = []
+        feat_c = 0
+        for i, layers in enumerate(self.sa):
+            self.sa_chains.append(MlpChain([(w, b, True) for w, b in layers], self.device, IN_GATHER, feat_c,
+                                           OUT_MAXPOOL, group=cfg["num_neighbours"][i]))
+            feat_c = layers[-1][0].shape[0]
+        self.fp_chains = [self._row_chains(layers) for layers in self.fp]
+        self.head_chains = []
+        for k, (layers, w, b) in enumerate(self.heads):
+            self.head_chains.append(MlpChain([(lw, lb, True) for lw, lb in layers] + [(w, b, False)], self.device,
+                                             IN_ROWS, 0, OUT_LOGITS, sigmoid=(k == 3)))
+
+    def tolerance(self):
+        """Max abs error of the head outputs relative to max(|ref|, 1) against the fp32 oracle."""
+        return 2e-3 if self.mlp_backend == "torch" else 6e-2
+
+    # ---------------------------------------------------------------- geometry (fp32, exact)
+    @staticmethod
+    def fps(xyz, m):
+        B, _, N = xyz.shape
+        idx = torch.empty((B, m), dtype=torch.int32, device=xyz.device)
+        check(lib.s4g_farthest_point_sample_f32_i32(ptr(xyz), B, N, m, ptr(idx), stream_ptr(xyz.device)), "fps")
+        return idx
+
+    @staticmethod
+    def ball_query(xyz, new_xyz, radius, k):
+        B, _, N = xyz.shape
+        M = new_xyz.shape[2]
+        idx = torch.empty((B, M, k), dtype=torch.int32, device=xyz.device)
+        check(lib.s4g_ball_query_f32_i32(ptr(xyz), ptr(new_xyz), B, N, M, float(radius), k, ptr(idx), None,
+                                         stream_ptr(xyz.device)), "ball_query")
+        return idx
+
+    @staticmethod
+    def three_nn(query, key):
+        B, _, Nq = query.shape
+        Nk = key.shape[2]
+        idx = torch.empty((B, Nq, 3), dtype=torch.int64, device=query.device)
+        d2 = torch.empty((B, Nq, 3), dtype=torch.float32, device=query.device)
+        check(lib.s4g_point_search_f32(ptr(query), ptr(key), B, Nq, Nk, 3, ptr(idx), ptr(d2),
+                                       stream_ptr(query.device)), "point_search")
+        return idx, d2
+
+    # ---------------------------------------------------------------- torch fp32 reference MLPs
+    @staticmethod
+    def _chain_torch(x, layers):
+        """x: (..., Cin) channel-last; layers: [(W', b')]."""
+        for w, b in layers:
+            x = torch.relu(torch.addmm(b, x.reshape(-1, x.shape[-1]), w.t()).reshape(*x.shape[:-1], w.shape[0]))
+        return x
+
+    def _sa_torch(self, xyz, feat_cl, new_xyz, nbr, layers, chunk=4):
+        """xyz (B,3,N); feat_cl (B,N,C) or None; nbr (B,M,K) -> (B,M,Cout) channel-last."""
+        B, M, K = nbr.shape
+        out = []
+        xyz_cl = xyz.transpose(1, 2)  # (B,N,3)
+        ctr_cl = new_xyz.transpose(1, 2)  # (B,M,3)
+        for b0 in range(0, B, chunk):
+            sl = slice(b0, b0 + chunk)
+            idx = nbr[sl].long().reshape(nbr[sl].shape[0], M * K)
+            g_xyz = torch.gather(xyz_cl[sl], 1, idx.unsqueeze(-1).expand(-1, -1, 3)).reshape(-1, M, K, 3)
+            g = g_xyz - ctr_cl[sl].unsqueeze(2)
+            if feat_cl is not None:
+                C = feat_cl.shape[-1]
+                g_f = torch.gather(feat_cl[sl], 1, idx.unsqueeze(-1).expand(-1, -1, C)).reshape(-1, M, K, C)
+                g = torch.cat([g, g_f], dim=-1)
+            out.append(self._chain_torch(g, layers).max(dim=2)[0])
+        return torch.cat(out, 0)
+
+    def _fp_torch(self, dense_xyz, sparse_xyz, dense_cl, sparse_cl, layers):
+        idx, d2 = self.three_nn(dense_xyz, sparse_xyz)
+        inv = 1.0 / torch.clamp(d2, min=1e-10)
+        w = inv / inv.sum(dim=2, keepdim=True)
+        B, Nq, _ = idx.shape
+        C = sparse_cl.shape[-1]
+        g = torch.gather(sparse_cl, 1, idx.reshape(B, Nq * 3, 1).expand(-1, -1, C)).reshape(B, Nq, 3, C)
+        # reference order of the 3-term sum: fma(in2,w2,fma(in1,w1,in0*w0))
+        interp = g[:, :, 0] * w[:, :, 0:1]
+        interp = torch.addcmul(interp, g[:, :, 1], w[:, :, 1:2])
+        interp = torch.addcmul(interp, g[:, :, 2], w[:, :, 2:3])
+        x = interp if dense_cl is None else torch.cat([interp, dense_cl], dim=-1)
+        return self._chain_torch(x, layers)
+
+    # ---------------------------------------------------------------- fused-path helpers
+    @staticmethod
+    def gather_xyz(xyz, idx):
+        B, _, N = xyz.shape
+        M = idx.shape[1]
+        out = torch.empty((B, 3, M), dtype=torch.float32, device=xyz.device)
+        check(lib.s4g_gather_xyz_f32_i32(ptr(xyz), ptr(idx), B, N, M, ptr(out), stream_ptr(xyz.device)), "gather_xyz")
+        return out
+
+    @staticmethod
+    def three_nn_weights(query, key):
+        B, _, Nq = query.shape
+        Nk = key.shape[2]
+        idx = torch.empty((B, Nq, 3), dtype=torch.int32, device=query.device)
+        w = torch.empty((B, Nq, 3), dtype=torch.float32, device=query.device)
+        check(lib.s4g_three_nn_weights_f32_i32(ptr(query), ptr(key), B, Nq, Nk, ptr(idx), ptr(w),
+                                               stream_ptr(query.device)), "three_nn_weights")
+        return idx, w
+
+    @staticmethod
+    def interp_concat(sparse, idx, w, dense, B, Nk, Nq):
+        C2 = sparse.shape[1]
+        C1 = dense.shape[1] if dense is not None else 0
+        out = torch.empty((B * Nq, C2 + C1), dtype=torch.bfloat16, device=sparse.device)
+        check(lib.s4g_interp_concat_bf16(ptr(sparse), ptr(idx), ptr(w), ptr(dense) if dense is not None else None,
+                                         B, Nk, Nq, C2, C1, ptr(out), stream_ptr(sparse.device)), "interp_concat")
+        return out
+
+    def _forward_tcgen05(self, points, return_trace):
+        cfg = self.cfg
+        xyz = points.float().contiguous()
+        B = xyz.shape[0]
+        feat = None  # bf16 [B*N, C] channel-last
+        lv_xyz, lv_feat = [xyz], [None]
+        trace = {"fps": [], "ball": []}
+        for i, chain in enumerate(self.sa_chains):
+            idx = self.fps(xyz, cfg["num_centroids"][i])
+            new_xyz = self.gather_xyz(xyz, idx)
+            nbr = self.ball_query(xyz, new_xyz, cfg["radius"][i], cfg["num_neighbours"][i])
+            feat = chain.run_gather(feat, xyz, new_xyz, nbr)
+            xyz = new_xyz
+            lv_xyz.append(xyz)
+            lv_feat.append(feat)
+            if return_trace:
+                trace["fps"].append(idx)
+                trace["ball"].append(nbr)
+        sparse_xyz, sparse = xyz, feat
+        for i, chains in enumerate(self.fp_chains):
+            dense_xyz, dense = lv_xyz[-2 - i], lv_feat[-2 - i]
+            idx3, w = self.three_nn_weights(dense_xyz, sparse_xyz)
+            x = self.interp_concat(sparse, idx3, w, dense, B, sparse_xyz.shape[2], dense_xyz.shape[2])
+            for ch in chains:
+                x = ch.run_rows(x)
+            sparse_xyz, sparse = dense_xyz, x
+        n = sparse_xyz.shape[2]
+        outs = [ch.run_rows(sparse, n_points=n) for ch in self.head_chains]
+        preds = {"score": outs[0], "frame_R": outs[1], "frame_t": outs[2], "movable_logits": outs[3]}
+        if return_trace:
+            trace["point_feature"] = sparse.float().reshape(B, n, -1)
+            trace["sa_feature"] = [f.float().reshape(B, -1, f.shape[1]) for f in lv_feat[1:]]
+            return preds, trace
+        return preds
+
+    # ---------------------------------------------------------------- forward
+    @torch.no_grad()
+    def forward(self, points, return_trace=False):
+        if not points.is_cuda:
+            raise RuntimeError("scene_points must be a CUDA tensor (there is no CPU path)")
+        if self.mlp_backend == "tcgen05":
+            with torch.cuda.device(points.device):
+                return self._forward_tcgen05(points, return_trace)
+        cfg = self.cfg
+        with torch.cuda.device(points.device):
+            xyz = points.float().contiguous()
+            feat = None
+            lv_xyz, lv_feat = [xyz], [None]
+            trace = {"fps": [], "ball": []}
+            for i, layers in enumerate(self.sa):
+                idx = self.fps(xyz, cfg["num_centroids"][i])
+                new_xyz = torch.gather(xyz, 2, idx.long().unsqueeze(1).expand(-1, 3, -1)).contiguous()
+                nbr = self.ball_query(xyz, new_xyz, cfg["radius"][i], cfg["num_neighbours"][i])
+                feat = self._sa_torch(xyz, feat, new_xyz, nbr, layers)
+                xyz = new_xyz
+                lv_xyz.append(xyz)
+                lv_feat.append(feat)
+                if return_trace:
+                    trace["fps"].append(idx)
+                    trace["ball"].append(nbr)
+            sparse_xyz, sparse = xyz, feat
+            for i, layers in enumerate(self.fp):
+                dense_xyz, dense = lv_xyz[-2 - i], lv_feat[-2 - i]
+                sparse = self._fp_torch(dense_xyz, sparse_xyz, dense, sparse, layers)
+                sparse_xyz = dense_xyz
+            outs = []
+            for layers, w, b in self.heads:
+                h = self._chain_torch(sparse, layers)
+                outs.append((torch.matmul(h, w.t()) + b).transpose(1, 2).contiguous())
+            preds = {"score": outs[0], "frame_R": outs[1], "frame_t": outs[2],
+                     "movable_logits": torch.sigmoid(outs[3])}
+        if return_trace:
+            trace["point_feature"] = sparse
+            trace["sa_feature"] = lv_feat[1:]
+            return preds, trace
+        return preds

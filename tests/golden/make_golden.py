@@ -35,6 +35,7 @@ REF = "/root/reference/inference"
 sys.path.insert(0, ROOT)
 
 from oracle import model_cpu, pn2_ext_cpu  # noqa: E402
+from tests.inputs import TINY_CONFIG  # noqa: E402
 
 
 def import_reference():
@@ -65,18 +66,6 @@ def seed_reference_weights(model):
     return model
 
 
-TINY_CONFIG = dict(
-    score_classes=3,
-    num_centroids=(256, 64, 16),
-    radius=(0.1, 0.2, 0.4),
-    num_neighbours=(16, 16, 8),
-    sa_channels=((16, 16, 32), (32, 32, 64), (64, 64, 128)),
-    fp_channels=((128, 128), (64, 64), (32, 32, 32)),
-    num_fp_neighbours=(3, 3, 3),
-    seg_channels=(64, 32, 32, 16),
-    num_removal_directions=5,
-    dropout_prob=0.5,
-)
 
 
 def sha(t):

@@ -1,0 +1,133 @@
+"""GPU numerics suite for the tcgen05 MLP-chain kernel (csrc/mlp_chain.cu) against a plain torch fp32
+reference of the same op on the same bf16-rounded operands.  Tolerances are stated per test: the kernel
+multiplies bf16 operands exactly and accumulates in fp32, so against a reference that (a) uses the same
+bf16-rounded weights/inputs and (b) rounds hidden activations to bf16 at the same places, the only
+difference is fp32 summation order:  |err| <= 2e-2 * max|ref| is a loose bound, 1 bf16 ulp = 2^-8."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _bf(x):
+    return x.to(torch.bfloat16).float()
+
+
+def _ref_chain(x, layers, round_hidden=True):
+    """x fp32 [P, Cin] (already bf16-representable); layers [(W, b, relu)] fp32."""
+    for i, (w, b, relu) in enumerate(layers):
+        x = x @ _bf(w).t() + b
+        if relu:
+            x = torch.relu(x)
+        if round_hidden and i + 1 < len(layers):
+            x = _bf(x)
+    return x
+
+
+def _layers(dims, seed, relu_last=True, scale=1.0):
+    g = torch.Generator().manual_seed(seed)
+    out = []
+    for i in range(len(dims) - 1):
+        w = torch.randn(dims[i + 1], dims[i], generator=g) * (scale / np.sqrt(dims[i]))
+        b = torch.randn(dims[i + 1], generator=g) * 0.1
+        out.append((w, b, relu_last or i + 2 < len(dims)))
+    return out
+
+
+def _check(got, want, tol=2e-2):
+    err = (got.float().cpu() - want).abs().max().item()
+    ref = want.abs().max().item()
+    assert err <= tol * max(ref, 1e-3), "max abs err %.4e vs max|ref| %.4e" % (err, ref)
+
+
+@pytest.mark.parametrize("dims,P", [
+    ([64, 64], 128), ([64, 128], 128), ([16, 32], 128), ([128, 256], 256), ([256, 512], 384), ([512, 256], 1024),
+    ([64, 64], 100), ([64, 64], 1), ([128, 96], 333), ([1536, 1024], 512), ([1024, 1024], 640), ([1280, 512], 256),
+])
+def test_single_layer_rows(dims, P):
+    from s4g_release_b200.chain import MlpChain
+    layers = _layers(dims, seed=sum(dims))
+    x = _bf(torch.randn(P, dims[0], generator=torch.Generator().manual_seed(P)))
+    ch = MlpChain(layers, "cuda")
+    got = ch.run_rows(x.cuda().to(torch.bfloat16))
+    torch.cuda.synchronize()
+    _check(got, _bf(_ref_chain(x, layers)))
+
+
+@pytest.mark.parametrize("dims,P", [
+    ([64, 64, 64], 256), ([512, 256, 256, 256], 1000), ([1280, 512, 512], 512), ([256, 512, 256, 256, 128], 2048),
+    ([32, 16, 32], 77),
+])
+def test_multi_layer_rows(dims, P):
+    from s4g_release_b200.chain import MlpChain
+    layers = _layers(dims, seed=sum(dims) + 1)
+    x = _bf(torch.randn(P, dims[0], generator=torch.Generator().manual_seed(P)))
+    got = MlpChain(layers, "cuda").run_rows(x.cuda().to(torch.bfloat16))
+    torch.cuda.synchronize()
+    _check(got, _bf(_ref_chain(x, layers)))
+
+
+@pytest.mark.parametrize("dims,n_out,B,n_points,sigmoid", [([256, 512, 256, 256, 128], 3, 2, 1280, False),
+                                                           ([64, 32], 9, 3, 100, False), ([64, 32], 5, 1, 4096, True)])
+def test_logits_head(dims, n_out, B, n_points, sigmoid):
+    from s4g_release_b200.chain import OUT_LOGITS, MlpChain
+    layers = _layers(dims + [n_out], seed=n_out, relu_last=False)
+    P = B * n_points
+    x = _bf(torch.randn(P, dims[0], generator=torch.Generator().manual_seed(P)))
+    got = MlpChain(layers, "cuda", out_mode=OUT_LOGITS, sigmoid=sigmoid).run_rows(x.cuda().to(torch.bfloat16), n_points)
+    torch.cuda.synchronize()
+    want = _ref_chain(x, layers).reshape(B, n_points, n_out).transpose(1, 2)
+    if sigmoid:
+        want = torch.sigmoid(want)
+    assert tuple(got.shape) == (B, n_out, n_points) and got.dtype == torch.float32
+    _check(got, want)
+
+
+@pytest.mark.parametrize("feat_c,dims,B,N,M,K", [(0, [128, 128, 256], 2, 2048, 256, 64), (64, [64, 64, 128], 2, 1024, 64, 16),
+                                                  (256, [256, 256, 512], 1, 2048, 128, 64), (512, [512, 512, 1024], 1, 512, 64, 64),
+                                                  (32, [32, 64], 3, 300, 50, 8), (0, [16, 32], 1, 100, 7, 32)])
+def test_set_abstraction_gather_maxpool(feat_c, dims, B, N, M, K):
+    """gather + centroid subtraction + concat + chain + max over K, vs torch fp32 on the same operands."""
+    from s4g_release_b200.chain import IN_GATHER, OUT_MAXPOOL, MlpChain
+    g = torch.Generator().manual_seed(feat_c + M)
+    layers = _layers([feat_c + 3] + dims, seed=M, scale=2.0)
+    xyz = torch.rand(B, 3, N, generator=g)
+    sel = torch.stack([torch.randperm(N, generator=g)[:M] for _ in range(B)])
+    ctr = torch.gather(xyz, 2, sel.unsqueeze(1).expand(-1, 3, -1)).contiguous()
+    nbr = torch.randint(0, N, (B, M, K), generator=g, dtype=torch.int32)
+    feat = _bf(torch.randn(B * N, feat_c, generator=g)) if feat_c else None
+    ch = MlpChain(layers, "cuda", IN_GATHER, feat_c, OUT_MAXPOOL, group=K)
+    got = ch.run_gather(feat.cuda().to(torch.bfloat16) if feat_c else None, xyz.cuda(), ctr.cuda(), nbr.cuda())
+    torch.cuda.synchronize()
+    # reference: reference channel order [rel_xyz | features] (modules.py:48)
+    idx = nbr.long().reshape(B, M * K)
+    gx = torch.gather(xyz.transpose(1, 2), 1, idx.unsqueeze(-1).expand(-1, -1, 3)).reshape(B, M, K, 3)
+    rel = _bf(gx - ctr.transpose(1, 2).unsqueeze(2))
+    x = rel
+    if feat_c:
+        gf = torch.gather(feat.reshape(B, N, feat_c), 1, idx.unsqueeze(-1).expand(-1, -1, feat_c)).reshape(B, M, K, feat_c)
+        x = torch.cat([rel, gf], dim=-1)
+    want = _ref_chain(x.reshape(-1, feat_c + 3), layers).reshape(B * M, K, -1).max(dim=1)[0]
+    assert tuple(got.shape) == (B * M, dims[-1])
+    _check(got, _bf(want))
+
+
+def test_fp_front_end():
+    from s4g_release_b200.engine import FusedPointNet2 as E
+    from oracle import pn2_ext_cpu as ora
+    g = torch.Generator().manual_seed(4)
+    B, Nq, Nk, C2, C1 = 2, 700, 90, 64, 32
+    q = torch.rand(B, 3, Nq, generator=g)
+    k = torch.rand(B, 3, Nk, generator=g)
+    idx, w = E.three_nn_weights(q.cuda(), k.cuda())
+    o_idx, o_d = ora.point_search(q, k, 3)
+    assert torch.equal(idx.cpu().long(), o_idx)
+    inv = 1.0 / torch.clamp(o_d, min=1e-10)
+    np.testing.assert_allclose(w.cpu().numpy(), (inv / inv.sum(2, keepdim=True)).numpy(), rtol=1e-6)
+    sparse = _bf(torch.randn(B * Nk, C2, generator=g))
+    dense = _bf(torch.randn(B * Nq, C1, generator=g))
+    out = E.interp_concat(sparse.cuda().to(torch.bfloat16), idx, w, dense.cuda().to(torch.bfloat16), B, Nk, Nq)
+    want = ora.interpolate_forward(sparse.reshape(B, Nk, C2).transpose(1, 2).contiguous(), o_idx, w.cpu())
+    _check(out[:, :C2], _bf(want.transpose(1, 2).reshape(B * Nq, C2)), tol=1e-2)
+    assert torch.equal(out[:, C2:].float().cpu(), dense)

@@ -1,0 +1,94 @@
+"""GPU suite for the whole PN2_CLS forward: module (drop-in / training) path and fused inference engine
+against the golden fixtures produced by the reference's python modules (tests/golden/make_golden.py) and
+the CPU oracle.  Geometry must be bit-exact; head outputs within the stated tolerance:
+  * module path, fp32 (TF32 off):                 |err| <= 2e-3 * max(1, max|ref|)
+  * fused engine, torch fp32 MLP reference:        same
+  * fused engine, tcgen05 (bf16 operands, fp32 acc, bf16 activations between layers, 17 layers deep):
+                                                   |err| <= 6e-2 * max(1, max|ref|)   (engine.tolerance())"""
+import numpy as np
+import pytest
+import torch
+
+from tests.inputs import TINY_CONFIG
+
+pytestmark = pytest.mark.gpu
+HEADS = ("score", "frame_R", "frame_t", "movable_logits")
+
+
+@pytest.fixture(scope="module")
+def tiny_net(golden_tiny):
+    from s4g_release_b200.network_models.models.PointNet2_tcls import PointNet2
+    net = PointNet2(**TINY_CONFIG)
+    sd = {k[3:]: torch.from_numpy(v) for k, v in golden_tiny.items() if k.startswith("sd/")}
+    net.load_state_dict(sd, strict=True)
+    return net.cuda().eval()
+
+
+def _rel_err(got, want):
+    want = torch.as_tensor(want)
+    return ((got.float().cpu() - want).abs().max() / max(1.0, want.abs().max().item())).item()
+
+
+def test_module_path_reproduces_reference_modules(tiny_net, golden_tiny):
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    with torch.no_grad():
+        out = tiny_net({"scene_points": torch.from_numpy(golden_tiny["points"]).cuda()}, fused=False)
+    for k in HEADS:
+        assert _rel_err(out[k], golden_tiny["out/" + k]) <= 2e-3, k
+
+
+@pytest.mark.parametrize("backend", ["torch", "tcgen05"])
+def test_fused_engine_tiny(tiny_net, golden_tiny, backend):
+    from s4g_release_b200.engine import FusedPointNet2
+    torch.backends.cuda.matmul.allow_tf32 = False
+    eng = FusedPointNet2(tiny_net, mlp_backend=backend)
+    out, trace = eng.forward(torch.from_numpy(golden_tiny["points"]).cuda(), return_trace=True)
+    torch.cuda.synchronize()
+    for i in range(3):
+        assert np.array_equal(trace["fps"][i].cpu().numpy(), golden_tiny[f"sa{i}/fps_index"])
+        assert np.array_equal(trace["ball"][i].cpu().numpy(), golden_tiny[f"sa{i}/ball_index"])
+        sa = trace["sa_feature"][i].float().cpu().transpose(1, 2)
+        assert _rel_err(sa, golden_tiny[f"sa{i}/new_feature"]) <= eng.tolerance(), "sa%d" % i
+    for k in HEADS:
+        assert _rel_err(out[k], golden_tiny["out/" + k]) <= eng.tolerance(), k
+
+
+def test_default_forward_is_the_fused_tcgen05_path(tiny_net, golden_tiny):
+    with torch.no_grad():
+        out = tiny_net({"scene_points": torch.from_numpy(golden_tiny["points"]).cuda()})
+    assert tiny_net.fused_engine().mlp_backend == "tcgen05"
+    for k in HEADS:
+        assert _rel_err(out[k], golden_tiny["out/" + k]) <= tiny_net.fused_engine().tolerance(), k
+
+
+@pytest.mark.parametrize("backend", ["torch", "tcgen05"])
+def test_full_model_on_fixture_cloud(cloud_2638, golden_full, backend):
+    """BASELINE config 1: 2638_view_0 subsample, shipped architecture, seeded weights."""
+    from s4g_release_b200.engine import FusedPointNet2
+    from s4g_release_b200.network_models.models.PointNet2_tcls import PN2_CLS_CONFIG, PointNet2
+    from tests.golden.make_golden import seed_reference_weights
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.manual_seed(0)
+    net = seed_reference_weights(PointNet2(**PN2_CLS_CONFIG)).cuda().eval()
+    eng = FusedPointNet2(net, mlp_backend=backend)
+    out, trace = eng.forward(torch.from_numpy(cloud_2638)[None].cuda(), return_trace=True)
+    torch.cuda.synchronize()
+    for i in range(3):
+        assert np.array_equal(trace["fps"][i].cpu().numpy(), golden_full[f"sa{i}/fps_index"])
+        assert np.array_equal(trace["ball"][i].sum(dim=2).cpu().numpy(), golden_full[f"sa{i}/ball_index_sum"])
+        sa = trace["sa_feature"][i].float().cpu().transpose(1, 2)[:, ::8, ::8]
+        assert _rel_err(sa, golden_full[f"sa{i}/new_feature_s"]) <= eng.tolerance(), "sa%d" % i
+    stride = int(golden_full["stride"])
+    for k in HEADS:
+        assert _rel_err(out[k][:, :, ::stride], golden_full["out/" + k]) <= eng.tolerance(), k
+
+
+def test_fused_engine_batch_consistency(tiny_net, golden_tiny):
+    """A scene inside a batch gives the same result as the scene alone (scenes are independent units)."""
+    eng = tiny_net.fused_engine()
+    pts = torch.from_numpy(golden_tiny["points"]).cuda()
+    both = eng.forward(pts)
+    one = eng.forward(pts[1:2].contiguous())
+    for k in HEADS:
+        assert torch.equal(both[k][1:2], one[k]), k

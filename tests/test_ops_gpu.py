@@ -1,0 +1,213 @@
+"""GPU parity suite: every pn2_ext replacement (through the C ABI) against the oracle on the same seeded
+inputs — bit-exact for indices / gathers, including the reference's tie-breaking and padding rules —
+plus size-independent properties at BASELINE sizes where the oracle would take too long."""
+import numpy as np
+import pytest
+import torch
+
+from tests import inputs
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ext():
+    from s4g_release_b200.network_models.models.pointnet2_utils import pn2_ext
+    return pn2_ext
+
+
+@pytest.fixture(scope="module")
+def ora():
+    from oracle import pn2_ext_cpu
+    return pn2_ext_cpu
+
+
+FPS_CASES = [
+    # (generator, B, N, M)
+    ("uniform", 2, 1024, 256), ("uniform", 3, 5120, 1024), ("uniform", 1, 25600, 5120), ("uniform", 4, 1000, 1000),
+    ("uniform", 2, 777, 300), ("uniform", 2, 13, 13), ("uniform", 5, 1, 1), ("uniform", 2, 17, 5),
+    ("uniform", 2, 256, 100), ("uniform", 2, 257, 100), ("uniform", 1, 12801, 700), ("uniform", 70, 3000, 64),
+    ("lattice", 3, 2000, 600), ("lattice", 2, 700, 700), ("lattice", 2, 200, 150), ("lattice", 2, 40, 40),
+    ("lattice", 2, 30000, 2000), ("dup", 2, 3000, 1500), ("dup", 1, 26000, 3000), ("identical", 2, 600, 50),
+    ("uniform", 1, 60000, 512), ("lattice", 1, 100000, 600),
+]
+
+
+def _gen(kind, B, N, seed):
+    return {"uniform": lambda: inputs.uniform_cloud(B, N, seed), "lattice": lambda: inputs.lattice_cloud(B, N, seed, side=8),
+            "dup": lambda: inputs.duplicated_cloud(B, N, seed), "identical": lambda: inputs.identical_cloud(B, N)}[kind]()
+
+
+@pytest.mark.parametrize("kind,B,N,M", FPS_CASES)
+def test_fps_bit_exact(ext, ora, kind, B, N, M):
+    pts = _gen(kind, B, N, seed=N + M)
+    want = ora.farthest_point_sample(pts, M)
+    got = ext.farthest_point_sample(pts.cuda(), M)
+    assert got.dtype == torch.int64 and tuple(got.shape) == (B, M)
+    assert torch.equal(got.cpu(), want)
+
+
+def test_fps_fixture_cloud_golden(ext, cloud_2638, golden_full):
+    xyz = torch.from_numpy(cloud_2638)[None].cuda()
+    for i, m in enumerate((5120, 1024, 256)):
+        idx = ext.farthest_point_sample(xyz, m)
+        assert np.array_equal(idx.cpu().numpy(), golden_full[f"sa{i}/fps_index"])
+        xyz = torch.gather(xyz, 2, idx.unsqueeze(1).expand(-1, 3, -1)).contiguous()
+
+
+def test_fps_noncontiguous_and_errors(ext, ora):
+    base = inputs.uniform_cloud(2, 900, 5)
+    nc = base.transpose(1, 2).contiguous().transpose(1, 2)  # (B,3,N) view of a (B,N,3) buffer
+    assert not nc.is_contiguous()
+    assert torch.equal(ext.farthest_point_sample(nc.cuda(), 100).cpu(), ora.farthest_point_sample(base, 100))
+    with pytest.raises(RuntimeError):
+        ext.farthest_point_sample(base.cuda(), 901)
+    with pytest.raises(RuntimeError):
+        ext.farthest_point_sample(base.cuda(), 0)
+    with pytest.raises(RuntimeError):
+        ext.farthest_point_sample(base[:, :2].cuda(), 10)
+    with pytest.raises(RuntimeError):
+        ext.farthest_point_sample(base.double().cuda(), 10)
+
+
+def test_fps_full_batch_properties(ext):
+    """B = 64 x 25 600 -> 5 120 (BASELINE config 2 shape): properties that do not need the oracle."""
+    pts = inputs.tabletop_batch(64).cuda()
+    idx = ext.farthest_point_sample(pts, 5120)
+    assert (idx[:, 0] == 0).all()
+    sel = torch.gather(pts, 2, idx.unsqueeze(1).expand(-1, 3, -1))
+    # the distance of each new sample to the already-selected set never increases
+    for b in (0, 17, 63):
+        s = sel[b].t().double()
+        d = torch.cdist(s[:600], s[:600])
+        far = torch.stack([d[i, :i].min() for i in range(1, 600)])
+        assert (far[1:] <= far[:-1] + 1e-12).all()
+    # and a cloud processed alone gives the same answer as inside the batch
+    assert torch.equal(ext.farthest_point_sample(pts[5:6].contiguous(), 5120), idx[5:6])
+
+
+BQ_CASES = [
+    ("uniform", 2, 1024, 256, 0.1, 16), ("uniform", 2, 5120, 1024, 0.08, 64), ("uniform", 1, 25600, 700, 0.02, 64),
+    ("uniform", 3, 777, 333, 0.2, 7), ("uniform", 2, 100, 100, 0.5, 128), ("uniform", 2, 50, 3, 1e-4, 8),
+    ("lattice", 2, 2000, 500, 0.125, 32), ("lattice", 2, 2000, 500, 0.25, 64), ("dup", 2, 3000, 400, 0.05, 32),
+    ("identical", 2, 300, 20, 0.1, 16), ("uniform", 2, 33, 33, 10.0, 40), ("uniform", 1, 4099, 517, 0.07, 33),
+]
+
+
+@pytest.mark.parametrize("kind,B,N,M,r,K", BQ_CASES)
+def test_ball_query_bit_exact(ext, ora, kind, B, N, M, r, K):
+    pts = _gen(kind, B, N, seed=N + K)
+    sel = ora.farthest_point_sample(pts, M)
+    ctr = ora.gather_points(pts, sel)
+    want_idx, want_cnt = ora.ball_query(pts, ctr, r, K)
+    got_idx, got_cnt = ext.ball_query(pts.cuda(), ctr.cuda(), r, K)
+    assert got_idx.dtype == torch.int64 and got_cnt.dtype == torch.int64
+    assert torch.equal(got_cnt.cpu(), want_cnt)
+    assert torch.equal(got_idx.cpu(), want_idx)
+
+
+def test_ball_query_no_hits_and_far_centroids(ext, ora):
+    pts = inputs.uniform_cloud(2, 500, 3)
+    far = (pts[:, :, :37] + 10.0).contiguous()
+    idx, cnt = ext.ball_query(pts.cuda(), far.cuda(), 0.1, 8)
+    assert (idx == 0).all() and (cnt == 0).all()
+    mixed = torch.cat([far[:, :, :5], pts[:, :, :6]], dim=2).contiguous()
+    w_idx, w_cnt = ora.ball_query(pts, mixed, 0.05, 12)
+    g_idx, g_cnt = ext.ball_query(pts.cuda(), mixed.cuda(), 0.05, 12)
+    assert torch.equal(g_idx.cpu(), w_idx) and torch.equal(g_cnt.cpu(), w_cnt)
+
+
+def test_ball_query_fixture_cloud_golden(ext, cloud_2638, golden_full):
+    xyz = torch.from_numpy(cloud_2638)[None].cuda()
+    for i, (m, r) in enumerate(((5120, 0.02), (1024, 0.08), (256, 0.32))):
+        sel = torch.from_numpy(golden_full[f"sa{i}/fps_index"]).long().cuda()
+        ctr = torch.gather(xyz, 2, sel.unsqueeze(1).expand(-1, 3, -1)).contiguous()
+        idx, cnt = ext.ball_query(xyz, ctr, r, 64)
+        assert np.array_equal(cnt.cpu().numpy(), golden_full[f"sa{i}/ball_count"])
+        assert np.array_equal(idx.sum(dim=2).cpu().numpy(), golden_full[f"sa{i}/ball_index_sum"])
+        xyz = ctr
+
+
+def test_ball_query_full_batch_properties(ext):
+    pts = inputs.tabletop_batch(8).cuda()
+    sel = ext.farthest_point_sample(pts, 5120)
+    ctr = torch.gather(pts, 2, sel.unsqueeze(1).expand(-1, 3, -1)).contiguous()
+    idx, cnt = ext.ball_query(pts, ctr, 0.02, 64)
+    assert (cnt >= 1).all()  # every centroid is a point of the cloud, so it finds itself
+    k = torch.arange(64, device="cuda")[None, None, :]
+    live = k < cnt[:, :, None]
+    # ascending index order inside the live part, padding == first neighbour outside
+    assert ((idx[:, :, 1:] > idx[:, :, :-1]) | ~live[:, :, 1:]).all()
+    assert ((idx == idx[:, :, :1]) | live).all()
+    # every listed neighbour is strictly inside the ball (fp32 arithmetic of the reference)
+    nb = torch.gather(pts.unsqueeze(2).expand(-1, -1, 5120, -1), 3, idx.unsqueeze(1).expand(-1, 3, -1, -1))
+    d = nb - ctr.unsqueeze(-1)
+    d2 = torch.addcmul(torch.addcmul(d[:, 1] * d[:, 1], d[:, 0], d[:, 0]), d[:, 2], d[:, 2])
+    assert (d2 < np.float32(0.02) * np.float32(0.02) + 1e-9).all()
+
+
+@pytest.mark.parametrize("B,C,N,M,K", [(2, 3, 500, 60, 16), (3, 131, 1000, 77, 9), (1, 259, 5120, 64, 64), (2, 1, 10, 10, 1)])
+def test_group_points_forward_backward(ext, ora, B, C, N, M, K):
+    rs = np.random.RandomState(B * C + N)
+    x = torch.from_numpy(rs.randn(B, C, N).astype(np.float32))
+    idx = torch.from_numpy(rs.randint(0, N, size=(B, M, K)).astype(np.int64))
+    got = ext.group_points_forward(x.cuda(), idx.cuda())
+    assert torch.equal(got.cpu(), ora.group_points_forward(x, idx))
+    g = torch.from_numpy(rs.randn(B, C, M, K).astype(np.float32))
+    gi = ext.group_points_backward(g.cuda(), idx.cuda(), N)
+    # atomicAdd order is unspecified in the reference too: fp32 tolerance, not bit-exact
+    np.testing.assert_allclose(gi.cpu().numpy(), ora.group_points_backward(g, idx, N).numpy(), rtol=1e-4, atol=1e-5)
+    # unique indices -> exact
+    if M * K <= N:
+        perm = torch.stack([torch.from_numpy(rs.permutation(N)[:M * K]) for _ in range(B)]).reshape(B, M, K)
+        gi = ext.group_points_backward(g.cuda(), perm.cuda(), N)
+        assert torch.equal(gi.cpu(), ora.group_points_backward(g, perm, N))
+
+
+@pytest.mark.parametrize("kind,B,Nq,Nk", [("uniform", 2, 1024, 256), ("uniform", 2, 5120, 1024), ("uniform", 1, 25600, 5120),
+                                          ("lattice", 2, 3000, 300), ("dup", 2, 2000, 900), ("uniform", 3, 101, 3),
+                                          ("identical", 2, 50, 10), ("uniform", 1, 300, 2049)])
+def test_point_search_bit_exact(ext, ora, kind, B, Nq, Nk):
+    q = _gen(kind, B, Nq, seed=Nq)
+    k = _gen(kind, B, Nk, seed=Nk + 1)
+    w_idx, w_d = ora.point_search(q, k, 3)
+    g_idx, g_d = ext.point_search(q.cuda(), k.cuda(), 3)
+    assert torch.equal(g_idx.cpu(), w_idx)
+    assert torch.equal(g_d.cpu(), w_d)
+    with pytest.raises(RuntimeError):
+        ext.point_search(q.cuda(), k.cuda(), 2)
+    with pytest.raises(RuntimeError):
+        ext.point_search(q.cuda(), k[:, :, :2].contiguous().cuda(), 3)
+
+
+@pytest.mark.parametrize("B,C,Nk,Nq", [(2, 5, 40, 90), (2, 256, 256, 1024), (1, 512, 1024, 5120)])
+def test_interpolate_forward_backward(ext, ora, B, C, Nk, Nq):
+    rs = np.random.RandomState(C)
+    x = torch.from_numpy(rs.randn(B, C, Nk).astype(np.float32))
+    idx = torch.from_numpy(rs.randint(0, Nk, size=(B, Nq, 3)).astype(np.int64))
+    w = torch.from_numpy(rs.rand(B, Nq, 3).astype(np.float32))
+    got = ext.interpolate_forward(x.cuda(), idx.cuda(), w.cuda())
+    assert torch.equal(got.cpu(), ora.interpolate_forward(x, idx, w))  # same fma chain -> bit-exact
+    g = torch.from_numpy(rs.randn(B, C, Nq).astype(np.float32))
+    gi = ext.interpolate_backward(g.cuda(), idx.cuda(), w.cuda(), Nk)
+    np.testing.assert_allclose(gi.cpu().numpy(), ora.interpolate_backward(g, idx, w, Nk).numpy(), rtol=1e-4, atol=1e-4)
+
+
+def test_autograd_wrappers_match_reference_behaviour(ext):
+    from s4g_release_b200.network_models.models.pointnet2_utils import functions as F_
+    pts = inputs.uniform_cloud(2, 400, 9).cuda()
+    feat = torch.randn(2, 6, 400, device="cuda", requires_grad=True)
+    idx = F_.farthest_point_sample(pts, 50)
+    ctr = F_.gather_points(pts, idx)
+    nbr, _ = F_.ball_query(pts, ctr, 0.3, 8)
+    grouped = F_.group_points(feat, nbr)
+    grouped.sum().backward()
+    want = torch.zeros_like(feat)
+    want.scatter_add_(2, nbr.reshape(2, 1, -1).expand(-1, 6, -1), torch.ones(2, 6, 400, device="cuda"))
+    assert torch.allclose(feat.grad, want)
+    nn_idx, d2 = F_.search_nn_distance(pts, ctr, 3)
+    w = torch.softmax(-d2, dim=2)
+    feat2 = torch.randn(2, 6, 50, device="cuda", requires_grad=True)
+    out = F_.feature_interpolate(feat2, nn_idx, w)
+    out.sum().backward()
+    assert torch.allclose(feat2.grad.sum(), torch.tensor(6.0 * 2 * 400, device="cuda"), rtol=1e-4)
