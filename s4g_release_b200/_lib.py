@@ -61,8 +61,13 @@ def exported_symbols():
     return sorted(_SIGNATURES)
 
 
+launches = 0  # number of C-ABI kernel launches issued by this process (bench.py reports it)
+
+
 def check(status, what):
     """Non-zero status -> RuntimeError, as the reference's TORCH_CHECK macros raise."""
+    global launches
+    launches += 1
     if status != 0:
         msg = lib.s4g_last_error().decode("utf-8", "replace")
         raise RuntimeError("%s failed (status %d): %s" % (what, status, msg))

@@ -19,6 +19,44 @@ from .chain import IN_GATHER, IN_ROWS, OUT_LOGITS, OUT_MAXPOOL, OUT_ROWS, MlpCha
 BN_EPS = 1e-5
 
 
+class StageTimer:
+    """CUDA-event stopwatch for the stages of one forward, recorded on the launching stream."""
+
+    def __init__(self):
+        self.records = []
+
+    def section(self, name):
+        return _Section(self, name)
+
+    def totals_ms(self):
+        """{name: [ms per occurrence]} — call after torch.cuda.synchronize()."""
+        out = {}
+        for name, a, b in self.records:
+            out.setdefault(name, []).append(a.elapsed_time(b))
+        return out
+
+
+class _Section:
+    def __init__(self, timer, name):
+        self.timer, self.name = timer, name
+
+    def __enter__(self):
+        if self.timer is not None:
+            self.a = torch.cuda.Event(enable_timing=True)
+            self.a.record()
+
+    def __exit__(self, *exc):
+        if self.timer is not None:
+            b = torch.cuda.Event(enable_timing=True)
+            b.record()
+            self.timer.records.append((self.name, self.a, b))
+        return False
+
+
+def _sec(timer, name):
+    return _Section(timer, name)
+
+
 def _fold_block(block):
     """conv (no bias) + BN(eval) -> (W', b') with y = W' x + b'."""
     w = block.conv.weight.detach().float()
@@ -178,7 +216,7 @@ class FusedPointNet2:
                                          B, Nk, Nq, C2, C1, ptr(out), stream_ptr(sparse.device)), "interp_concat")
         return out
 
-    def _forward_tcgen05(self, points, return_trace):
+    def _forward_tcgen05(self, points, return_trace, timer=None):
         cfg = self.cfg
         xyz = points.float().contiguous()
         B = xyz.shape[0]
@@ -186,10 +224,14 @@ class FusedPointNet2:
         lv_xyz, lv_feat = [xyz], [None]
         trace = {"fps": [], "ball": []}
         for i, chain in enumerate(self.sa_chains):
-            idx = self.fps(xyz, cfg["num_centroids"][i])
-            new_xyz = self.gather_xyz(xyz, idx)
-            nbr = self.ball_query(xyz, new_xyz, cfg["radius"][i], cfg["num_neighbours"][i])
-            feat = chain.run_gather(feat, xyz, new_xyz, nbr)
+            with _sec(timer, "sa%d.fps" % i):
+                idx = self.fps(xyz, cfg["num_centroids"][i])
+            with _sec(timer, "sa%d.gather_xyz" % i):
+                new_xyz = self.gather_xyz(xyz, idx)
+            with _sec(timer, "sa%d.ball_query" % i):
+                nbr = self.ball_query(xyz, new_xyz, cfg["radius"][i], cfg["num_neighbours"][i])
+            with _sec(timer, "sa%d.mlp" % i):
+                feat = chain.run_gather(feat, xyz, new_xyz, nbr)
             xyz = new_xyz
             lv_xyz.append(xyz)
             lv_feat.append(feat)
@@ -199,13 +241,17 @@ class FusedPointNet2:
         sparse_xyz, sparse = xyz, feat
         for i, chains in enumerate(self.fp_chains):
             dense_xyz, dense = lv_xyz[-2 - i], lv_feat[-2 - i]
-            idx3, w = self.three_nn_weights(dense_xyz, sparse_xyz)
-            x = self.interp_concat(sparse, idx3, w, dense, B, sparse_xyz.shape[2], dense_xyz.shape[2])
-            for ch in chains:
-                x = ch.run_rows(x)
+            with _sec(timer, "fp%d.three_nn" % i):
+                idx3, w = self.three_nn_weights(dense_xyz, sparse_xyz)
+            with _sec(timer, "fp%d.interp_concat" % i):
+                x = self.interp_concat(sparse, idx3, w, dense, B, sparse_xyz.shape[2], dense_xyz.shape[2])
+            with _sec(timer, "fp%d.mlp" % i):
+                for ch in chains:
+                    x = ch.run_rows(x)
             sparse_xyz, sparse = dense_xyz, x
         n = sparse_xyz.shape[2]
-        outs = [ch.run_rows(sparse, n_points=n) for ch in self.head_chains]
+        with _sec(timer, "heads.mlp"):
+            outs = [ch.run_rows(sparse, n_points=n) for ch in self.head_chains]
         preds = {"score": outs[0], "frame_R": outs[1], "frame_t": outs[2], "movable_logits": outs[3]}
         if return_trace:
             trace["point_feature"] = sparse.float().reshape(B, n, -1)
@@ -215,12 +261,12 @@ class FusedPointNet2:
 
     # ---------------------------------------------------------------- forward
     @torch.no_grad()
-    def forward(self, points, return_trace=False):
+    def forward(self, points, return_trace=False, timer=None):
         if not points.is_cuda:
             raise RuntimeError("scene_points must be a CUDA tensor (there is no CPU path)")
         if self.mlp_backend == "tcgen05":
             with torch.cuda.device(points.device):
-                return self._forward_tcgen05(points, return_trace)
+                return self._forward_tcgen05(points, return_trace, timer)
         cfg = self.cfg
         with torch.cuda.device(points.device):
             xyz = points.float().contiguous()
