@@ -32,8 +32,10 @@
 namespace s4g {
 
 constexpr int kTileRows = 128;
-constexpr int kWorkerThreads = 128;
-constexpr int kChainThreads = kWorkerThreads + 32;  // 4 epilogue/loader warps + 1 control warp
+constexpr int kWorkerThreads = 256;                 // 8 warps: two per TMEM lane quadrant
+constexpr int kControlWarp = kWorkerThreads / 32;
+constexpr int kProducerWarp = kControlWarp + 1;
+constexpr int kChainThreads = kWorkerThreads + 64;  // + MMA-issue warp + TMA-producer warp
 constexpr int kStageBytes = 32768;                  // one weight chunk: <=256 rows x 64 channels bf16
 constexpr int kMaxPhases = 16;
 constexpr int kMaxLayers = 6;
@@ -46,6 +48,7 @@ struct Phase {
   int k_begin, k_end;  // input-channel range accumulated in this phase (multiples of 16)
   int n_begin, n_end;  // output-channel range produced in this phase
   int n_chunk;         // rows per weight chunk (<=256; 128 when transposed)
+  int k_chunk;         // channels per weight chunk: n_chunk * k_chunk * 2 B <= 32 KB (one ring stage)
   int transposed;      // 1: A = weights, B = act
   int first;           // 1: first accumulation phase of its (layer, n-range): overwrite TMEM
   int action;          // what the workers do once the phase's MMAs are complete
@@ -61,6 +64,8 @@ struct ChainParams {
   const __nv_bfloat16* weights;  // all chunks of one tile, in consumption order
   unsigned w_bytes;              // total bytes of `weights`
   const float* bias[kMaxLayers];
+  int bias_off[kMaxLayers], bias_len[kMaxLayers], bias_total;  // shifts staged in smem (floats)
+  int n_layers;
   int P;                         // rows (positions)
   int act_c;                     // capacity of the act buffer in channels
   int stages;
@@ -192,32 +197,34 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// worker: stage channels [c_begin, c_end) of the layer-0 input of `tile` into act (local channel 0..)
+// worker: stage channels [c_begin, c_end) of the layer-0 input of `tile` into act (local channel 0..).
+// Thread (r, hh): row r of the tile, 16-byte pieces hh, hh+2, ... of that row (conflict-free smem
+// writes: consecutive rows are consecutive 16-byte slots of one K chunk).
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ void stage_input(const ChainParams& p, uint8_t* act, int tile, int c_begin, int c_end,
-                                            int r) {
+                                            int r, int hh) {
   const long long row = (long long)tile * kTileRows + r;
   const bool valid = row < p.P;
   uint8_t* dst = act + (size_t)r * 16;
   if (p.in_mode == IN_ROWS) {
     const __nv_bfloat16* src = p.in_rows + (valid ? row : 0) * (long long)p.in_stride + c_begin;
     const int pieces = (c_end - c_begin) >> 3;
-    for (int c = 0; c < pieces; ++c) cp_async16(dst + (size_t)c * (kTileRows * 16), src + c * 8, valid);
+    for (int c = hh; c < pieces; c += 2) cp_async16(dst + (size_t)c * (kTileRows * 16), src + c * 8, valid);
   } else {
     // row -> (b, m, k); gathered feature row first, then the 16-wide relative-xyz chunk
     const int per_b = p.M * p.K;
     const long long rr = valid ? row : 0;
     const int b = (int)(rr / per_b);
-    const int m = (int)((rr % per_b) / p.K);
-    const int j = p.nbr[rr];
+    const int m = (int)((rr - (long long)b * per_b) / p.K);
+    const int j = __ldg(p.nbr + rr);
     const int fc = p.feat_c;
     if (c_begin < fc) {
       const int e = min(c_end, fc);
       const __nv_bfloat16* src = p.feat + ((long long)b * p.N + j) * fc + c_begin;
       const int pieces = (e - c_begin) >> 3;
-      for (int c = 0; c < pieces; ++c) cp_async16(dst + (size_t)c * (kTileRows * 16), src + c * 8, valid);
+      for (int c = hh; c < pieces; c += 2) cp_async16(dst + (size_t)c * (kTileRows * 16), src + c * 8, valid);
     }
-    if (c_end > fc) {  // the xyz chunk [fc, fc+16) lies in this part
+    if (c_end > fc && hh == 0) {  // the xyz chunk [fc, fc+16) lies in this part
       const float* X = p.xyz + (long long)b * 3 * p.N;
       const float* C = p.ctr + (long long)b * 3 * p.M;
       float dx = 0.f, dy = 0.f, dz = 0.f;
@@ -227,31 +234,73 @@ __device__ __forceinline__ void stage_input(const ChainParams& p, uint8_t* act, 
         dz = __fsub_rn(__ldg(X + 2 * p.N + j), __ldg(C + 2 * p.M + m));
       }
       const int c0 = (fc - c_begin) >> 3;
-      uint4 v0 = make_uint4(pack_bf16(dx, dy), pack_bf16(dz, 0.f), 0u, 0u);
-      uint4 z = make_uint4(0u, 0u, 0u, 0u);
-      *reinterpret_cast<uint4*>(dst + (size_t)c0 * (kTileRows * 16)) = v0;
-      *reinterpret_cast<uint4*>(dst + (size_t)(c0 + 1) * (kTileRows * 16)) = z;
+      *reinterpret_cast<uint4*>(dst + (size_t)c0 * (kTileRows * 16)) =
+          make_uint4(pack_bf16(dx, dy), pack_bf16(dz, 0.f), 0u, 0u);
+      *reinterpret_cast<uint4*>(dst + (size_t)(c0 + 1) * (kTileRows * 16)) = make_uint4(0u, 0u, 0u, 0u);
     }
   }
 }
 
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
+
+// issue the (non-blocking) TMEM load of 32 / 16 accumulator columns; pair with tmem_wait()
+__device__ __forceinline__ void tmem_ld32_issue(uint32_t taddr, float* v) {
+  uint32_t* r = reinterpret_cast<uint32_t*>(v);
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// one 32-column slab of a row-oriented epilogue: + shift, ReLU, bf16 pack, 4 x 16-byte stores
+template <bool TO_GLOBAL>
+__device__ __forceinline__ void epi_store32(const float* v, const float* sb, int relu, uint8_t* dst, size_t piece_stride) {
+#pragma unroll
+  for (int g = 0; g < 4; ++g) {
+    const float4 b0 = *reinterpret_cast<const float4*>(sb + g * 8);
+    const float4 b1 = *reinterpret_cast<const float4*>(sb + g * 8 + 4);
+    float o[8] = {v[g * 8 + 0] + b0.x, v[g * 8 + 1] + b0.y, v[g * 8 + 2] + b0.z, v[g * 8 + 3] + b0.w,
+                  v[g * 8 + 4] + b1.x, v[g * 8 + 5] + b1.y, v[g * 8 + 6] + b1.z, v[g * 8 + 7] + b1.w};
+    if (relu) {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) o[e] = fmaxf(o[e], 0.f);
+    }
+    *reinterpret_cast<uint4*>(dst + g * piece_stride) =
+        make_uint4(pack_bf16(o[0], o[1]), pack_bf16(o[2], o[3]), pack_bf16(o[4], o[5]), pack_bf16(o[6], o[7]));
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
-// the kernel
+// the kernel: warps 0..7 = workers (input staging + epilogues), warp 8 = control (TMA + MMA issue)
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kChainThreads, 1) mlp_chain_kernel(const __grid_constant__ ChainParams p) {
   extern __shared__ __align__(128) uint8_t smem[];
-  // carve: [act | weight ring | barriers]
+  // carve: [act | weight ring | bias | barriers]
   uint8_t* act = smem;
   uint8_t* ring = smem + (size_t)p.act_c * kTileRows * 2;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(ring + (size_t)p.stages * kStageBytes);
-  uint64_t* full = bars;                  // [stages] weights landed
-  uint64_t* empty = bars + p.stages;      // [stages] MMAs that read the stage are complete
+  float* s_bias = reinterpret_cast<float*>(ring + (size_t)p.stages * kStageBytes);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_bias + p.bias_total);
+  uint64_t* full = bars;                     // [stages] weights landed
+  uint64_t* empty = bars + p.stages;         // [stages] MMAs that read the stage are complete
   uint64_t* mma_done = bars + 2 * p.stages;  // a phase's MMAs are complete
   uint64_t* act_ready = mma_done + 1;        // workers staged / rewrote act and drained TMEM
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(act_ready + 1);
 
   const int warp = threadIdx.x >> 5;
-  const int lane = threadIdx.x & 31;
   const int n_tiles = (p.P + kTileRows - 1) / kTileRows;
 
   if (threadIdx.x == 0) {
@@ -260,95 +309,94 @@ __global__ void __launch_bounds__(kChainThreads, 1) mlp_chain_kernel(const __gri
     mbar_init(act_ready, kWorkerThreads);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 4) tmem_alloc(tmem_slot, (unsigned)p.tmem_cols);
+  for (int l = 0; l < p.n_layers; ++l)
+    for (int c = threadIdx.x; c < p.bias_len[l]; c += kChainThreads) s_bias[p.bias_off[l] + c] = __ldg(p.bias[l] + c);
+  if (warp == kControlWarp) tmem_alloc(tmem_slot, (unsigned)p.tmem_cols);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp == 4) {
-    // =========================== control warp: TMA producer + MMA issuer ===========================
-    if (lane == 0) {
-      // producer cursor (runs `stages` chunks ahead) and consumer cursor over the same sequence
-      long long produced = 0, consumed = 0;
-      int pr_tile = blockIdx.x, pr_phase = 0, pr_k = p.phase[0].k_begin, pr_n = p.phase[0].n_begin;
-      unsigned pr_off = 0;
-      bool pr_end = pr_tile >= n_tiles;
-      unsigned ready_count = 0;
-      auto produce_one = [&]() {
-        const Phase& ph = p.phase[pr_phase];
-        const int kw = min(64, ph.k_end - pr_k);
-        const unsigned bytes = (unsigned)kw * ph.n_chunk * 2u;
-        const int s = (int)(produced % p.stages);
-        if (produced >= p.stages) mbar_wait(&empty[s], (unsigned)((produced / p.stages - 1) & 1));
-        mbar_expect_tx(&full[s], bytes);
-        bulk_g2s(ring + (size_t)s * kStageBytes, reinterpret_cast<const uint8_t*>(p.weights) + pr_off, bytes, &full[s]);
-        ++produced;
-        pr_off += bytes;
-        pr_n += ph.n_chunk;
-        if (pr_n >= ph.n_end) {
-          pr_n = ph.n_begin;
-          pr_k += kw;
-          if (pr_k >= ph.k_end) {
-            ++pr_phase;
-            if (pr_phase == p.n_phases) {
-              pr_phase = 0;
-              pr_off = 0;
-              pr_tile += gridDim.x;
-              if (pr_tile >= n_tiles) pr_end = true;
+  if (warp == kProducerWarp) {
+    // ============== TMA producer warp: streams the weight chunks of every tile, in consumption order ==============
+    int s = 0, wrap = 0;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+      const uint8_t* src = reinterpret_cast<const uint8_t*>(p.weights);
+      for (int q = 0; q < p.n_phases; ++q) {
+        const Phase& ph = p.phase[q];
+        const int n_n = (ph.n_end - ph.n_begin) / ph.n_chunk;
+        for (int k = ph.k_begin; k < ph.k_end; k += ph.k_chunk) {
+          const unsigned bytes = (unsigned)min(ph.k_chunk, ph.k_end - k) * (unsigned)ph.n_chunk * 2u;
+          for (int i = 0; i < n_n; ++i) {
+            if (wrap > 0) mbar_wait(&empty[s], (unsigned)((wrap - 1) & 1));
+            if (elect_one()) {
+              mbar_expect_tx(&full[s], bytes);
+              bulk_g2s(ring + (size_t)s * kStageBytes, src, bytes, &full[s]);
             }
-            pr_k = p.phase[pr_phase].k_begin;
-            pr_n = p.phase[pr_phase].n_begin;
+            __syncwarp();
+            src += bytes;
+            if (++s == p.stages) { s = 0; ++wrap; }
           }
-        }
-      };
-      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        for (int q = 0; q < p.n_phases; ++q) {
-          const Phase& ph = p.phase[q];
-          const uint32_t idesc = make_idesc(128, ph.transposed ? kTileRows : ph.n_chunk);
-          bool waited_ready = false;
-          for (int k = ph.k_begin; k < ph.k_end; k += 64) {
-            const int kw = min(64, ph.k_end - k);
-            for (int n = ph.n_begin; n < ph.n_end; n += ph.n_chunk) {
-              while (!pr_end && produced < consumed + p.stages) produce_one();
-              if (!waited_ready) {  // act staged / previous epilogue finished with act and TMEM
-                mbar_wait(act_ready, ready_count & 1);
-                ++ready_count;
-                tc_fence_after();
-                waited_ready = true;
-              }
-              const int s = (int)(consumed % p.stages);
-              mbar_wait(&full[s], (unsigned)((consumed / p.stages) & 1));
-              tc_fence_after();
-              const uint32_t w_addr = smem_u32(ring + (size_t)s * kStageBytes);
-              const uint32_t a_addr = smem_u32(act) + (uint32_t)((k - ph.k_begin) >> 3) * (kTileRows * 16);
-              const uint32_t d_addr = tmem_base + (uint32_t)(n - ph.n_begin);
-              const uint32_t w_lbo = (uint32_t)ph.n_chunk * 16u;
-#pragma unroll 1
-              for (int kk = 0; kk < kw; kk += 16) {
-                const uint64_t act_desc = make_desc(a_addr + (uint32_t)(kk >> 3) * (kTileRows * 16), kTileRows * 16, 128);
-                const uint64_t w_desc = make_desc(w_addr + (uint32_t)(kk >> 3) * w_lbo, w_lbo, 128);
-                const uint32_t acc = (ph.first && k == ph.k_begin && kk == 0) ? 0u : 1u;
-                if (ph.transposed) umma_bf16(d_addr, w_desc, act_desc, idesc, acc);
-                else umma_bf16(d_addr, act_desc, w_desc, idesc, acc);
-              }
-              umma_commit(&empty[s]);  // stage reusable once these MMAs have read it
-              ++consumed;
-            }
-          }
-          umma_commit(mma_done);
         }
       }
     }
-    __syncwarp();
+  } else if (warp == kControlWarp) {
+    // ============== MMA warp (converged; one elected lane issues tcgen05.mma / commit) ==============
+    int s = 0, wrap = 0;
+    unsigned ready_count = 0;
+    const uint32_t act16 = smem_u32(act) >> 4;
+    const uint32_t ring16 = smem_u32(ring) >> 4;
+    // descriptor high word: SBO = 128 B, version 1;  low word: (addr >> 4) | (LBO >> 4) << 16
+    const uint64_t desc_hi = (uint64_t)((128u >> 4) | (1u << 14)) << 32;
+    const uint32_t a_lbo16 = (uint32_t)kTileRows;  // (128 rows * 16 B) >> 4
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+      for (int q = 0; q < p.n_phases; ++q) {
+        const Phase& ph = p.phase[q];
+        const uint32_t idesc = make_idesc(128, ph.transposed ? kTileRows : ph.n_chunk);
+        const uint32_t w_lbo16 = (uint32_t)ph.n_chunk;  // (n_chunk rows * 16 B) >> 4
+        const int n_n = (ph.n_end - ph.n_begin) / ph.n_chunk;
+        const bool transposed = ph.transposed != 0;
+        mbar_wait(act_ready, ready_count & 1);  // act staged / previous epilogue done with act and TMEM
+        ++ready_count;
+        for (int k = ph.k_begin; k < ph.k_end; k += ph.k_chunk) {
+          const int steps = min(ph.k_chunk, ph.k_end - k) >> 4;
+          const bool last_k = k + ph.k_chunk >= ph.k_end;
+          const uint32_t a_lo0 = (act16 + (uint32_t)((k - ph.k_begin) >> 3) * a_lbo16) | (a_lbo16 << 16);
+          const uint32_t acc0 = (ph.first && k == ph.k_begin) ? 0u : 1u;
+          for (int i = 0; i < n_n; ++i) {
+            mbar_wait(&full[s], (unsigned)(wrap & 1));
+            tc_fence_after();
+            if (elect_one()) {
+              uint32_t a_lo = a_lo0;
+              uint32_t w_lo = (ring16 + (uint32_t)s * (kStageBytes >> 4)) | (w_lbo16 << 16);
+              const uint32_t d_addr = tmem_base + (uint32_t)(i * ph.n_chunk);
+              uint32_t acc = acc0;
+#pragma unroll 4
+              for (int j = 0; j < steps; ++j) {
+                if (transposed) umma_bf16(d_addr, desc_hi | w_lo, desc_hi | a_lo, idesc, acc);
+                else umma_bf16(d_addr, desc_hi | a_lo, desc_hi | w_lo, idesc, acc);
+                acc = 1u;
+                a_lo += 2u * a_lbo16;  // next 16 channels = 2 K pieces
+                w_lo += 2u * w_lbo16;
+              }
+              umma_commit(&empty[s]);  // stage reusable once these MMAs have read it
+              if (last_k && i == n_n - 1) umma_commit(mma_done);
+            }
+            __syncwarp();
+            if (++s == p.stages) { s = 0; ++wrap; }
+          }
+        }
+      }
+    }
   } else {
-    // =========================== worker warps: input staging + epilogues ===========================
-    const int r = threadIdx.x;  // row of the tile == TMEM lane
-    const uint32_t lane_base = tmem_base + ((uint32_t)(warp * 32) << 16);
+    // ======================== worker warps: input staging + epilogues ========================
+    const int r = threadIdx.x & (kTileRows - 1);  // row of the tile == TMEM lane (quadrant = warp & 3)
+    const int hh = threadIdx.x >> 7;              // which half of the columns / pieces this warp takes
+    const uint32_t lane_base = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
     unsigned done_count = 0;
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
       const long long row = (long long)tile * kTileRows + r;
-      stage_input(p, act, tile, p.phase[0].k_begin, p.in_first_load_end, r);
+      stage_input(p, act, tile, p.phase[0].k_begin, p.in_first_load_end, r, hh);
       cp_async_wait_all();
       fence_proxy_async();
       mbar_arrive(act_ready);
@@ -357,44 +405,60 @@ __global__ void __launch_bounds__(kChainThreads, 1) mlp_chain_kernel(const __gri
         mbar_wait(mma_done, done_count & 1);
         ++done_count;
         tc_fence_after();
-        const float* bias = p.bias[ph.layer];
+        const float* sb = s_bias + p.bias_off[ph.layer];
         if (ph.action == ACT_LOAD_A) {
-          stage_input(p, act, tile, ph.load_begin, ph.load_end, r);
+          stage_input(p, act, tile, ph.load_begin, ph.load_end, r, hh);
           cp_async_wait_all();
-        } else if (ph.action == ACT_EPI_HIDDEN) {
-          for (int c = ph.n_begin; c < ph.n_end; c += 32) {
-            float v[32];
-            tmem_ld32(lane_base + (uint32_t)(c - ph.n_begin), v);
-#pragma unroll
-            for (int g = 0; g < 4; ++g) {
-              float o[8];
-#pragma unroll
-              for (int e = 0; e < 8; ++e) {
-                float t = v[g * 8 + e] + __ldg(bias + c + g * 8 + e);
-                o[e] = ph.relu ? fmaxf(t, 0.f) : t;
-              }
-              uint4 pk = make_uint4(pack_bf16(o[0], o[1]), pack_bf16(o[2], o[3]), pack_bf16(o[4], o[5]),
-                                    pack_bf16(o[6], o[7]));
-              *reinterpret_cast<uint4*>(act + ((size_t)((c >> 3) + g) * kTileRows + r) * 16) = pk;
-            }
-          }
-        } else if (ph.action == ACT_EPI_ROWS) {
+        } else if (ph.action == ACT_EPI_HIDDEN || ph.action == ACT_EPI_ROWS) {
+          // 32-column slabs, alternating between the two warps of a lane quadrant; the TMEM load of the
+          // next slab is in flight while the current one is processed
+          const bool to_global = ph.action == ACT_EPI_ROWS;
           __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(p.out);
-          for (int c = ph.n_begin; c < ph.n_end; c += 32) {
-            float v[32];
-            tmem_ld32(lane_base + (uint32_t)(c - ph.n_begin), v);
-            if (row < p.P) {
+          const int width = ph.n_end - ph.n_begin;
+          if ((width & 31) == 0) {
+            float va[32], vb[32];
+            int c = ph.n_begin + 32 * hh;
+            if (c < ph.n_end) tmem_ld32_issue(lane_base + (uint32_t)(c - ph.n_begin), va);
+            for (; c < ph.n_end; c += 128) {
+              tmem_wait();
+              const int c2 = c + 64;
+              if (c2 < ph.n_end) tmem_ld32_issue(lane_base + (uint32_t)(c2 - ph.n_begin), vb);
+              if (to_global) {
+                if (row < p.P) epi_store32<true>(va, sb + c, ph.relu, reinterpret_cast<uint8_t*>(out + row * (long long)p.out_c + c), 16);
+              } else {
+                epi_store32<false>(va, sb + c, ph.relu, act + ((size_t)(c >> 3) * kTileRows + r) * 16, kTileRows * 16);
+              }
+              if (c2 < ph.n_end) {
+                tmem_wait();
+                const int c3 = c2 + 64;
+                if (c3 < ph.n_end) tmem_ld32_issue(lane_base + (uint32_t)(c3 - ph.n_begin), va);
+                if (to_global) {
+                  if (row < p.P) epi_store32<true>(vb, sb + c2, ph.relu, reinterpret_cast<uint8_t*>(out + row * (long long)p.out_c + c2), 16);
+                } else {
+                  epi_store32<false>(vb, sb + c2, ph.relu, act + ((size_t)(c2 >> 3) * kTileRows + r) * 16, kTileRows * 16);
+                }
+              }
+            }
+          } else {
+            // narrow layers (width a multiple of 16 only): 16-column slabs, hidden activations only
+            for (int c = ph.n_begin + 16 * hh; c < ph.n_end; c += 32) {
+              float v[16];
+              tmem_ld16(lane_base + (uint32_t)(c - ph.n_begin), v);
 #pragma unroll
-              for (int g = 0; g < 4; ++g) {
+              for (int g = 0; g < 2; ++g) {
                 float o[8];
 #pragma unroll
                 for (int e = 0; e < 8; ++e) {
-                  float t = v[g * 8 + e] + __ldg(bias + c + g * 8 + e);
+                  const float t = v[g * 8 + e] + sb[c + g * 8 + e];
                   o[e] = ph.relu ? fmaxf(t, 0.f) : t;
                 }
-                uint4 pk = make_uint4(pack_bf16(o[0], o[1]), pack_bf16(o[2], o[3]), pack_bf16(o[4], o[5]),
-                                      pack_bf16(o[6], o[7]));
-                *reinterpret_cast<uint4*>(out + row * (long long)p.out_c + c + g * 8) = pk;
+                const uint4 pk = make_uint4(pack_bf16(o[0], o[1]), pack_bf16(o[2], o[3]), pack_bf16(o[4], o[5]),
+                                            pack_bf16(o[6], o[7]));
+                if (to_global) {
+                  if (row < p.P) *reinterpret_cast<uint4*>(out + row * (long long)p.out_c + c + g * 8) = pk;
+                } else {
+                  *reinterpret_cast<uint4*>(act + ((size_t)((c >> 3) + g) * kTileRows + r) * 16) = pk;
+                }
               }
             }
           }
@@ -405,11 +469,14 @@ __global__ void __launch_bounds__(kChainThreads, 1) mlp_chain_kernel(const __gri
           const int G = p.group;
           const long long group0 = (long long)tile * (kTileRows / G);
           const long long n_groups = p.P / G;
+          // groups <= 64 wide: warp half hh owns columns [64 hh, 64 hh + 64); a 128-wide group: half 0 only
+          const int col0 = (G <= 64) ? 64 * hh : 0;
+          const int col1 = (G <= 64) ? col0 + 64 : (hh == 0 ? kTileRows : 0);
           for (int cb = ph.n_begin; cb < ph.n_end; cb += kTileRows) {
             const int ch = cb + r;
-            const float b = __ldg(bias + ch);
+            const float b = sb[ch];
             float run = 0.f;
-            for (int s0 = 0; s0 < kTileRows; s0 += 32) {
+            for (int s0 = col0; s0 < col1; s0 += 32) {
               float v[32];
               tmem_ld32(lane_base + (uint32_t)(cb - ph.n_begin + s0), v);
               if (G >= 32) {
@@ -420,34 +487,48 @@ __global__ void __launch_bounds__(kChainThreads, 1) mlp_chain_kernel(const __gri
                 if ((s0 + 32) % G == 0) {
                   const long long gi = group0 + s0 / G;
                   if (gi < n_groups && ch < p.out_c) {
-                    float t = run + b;
+                    const float t = run + b;
                     out[gi * p.out_c + ch] = __float2bfloat16(ph.relu ? fmaxf(t, 0.f) : t);
                   }
                 }
-              } else {
-                for (int g = 0; g < 32; g += G) {
+              } else if (G == 16) {
+#pragma unroll
+                for (int g = 0; g < 32; g += 16) {
                   float m = v[g];
-                  for (int e = 1; e < G; ++e) m = fmaxf(m, v[g + e]);
-                  const long long gi = group0 + (s0 + g) / G;
+#pragma unroll
+                  for (int e = 1; e < 16; ++e) m = fmaxf(m, v[g + e]);
+                  const long long gi = group0 + (s0 + g) / 16;
                   if (gi < n_groups && ch < p.out_c) {
-                    float t = m + b;
+                    const float t = m + b;
+                    out[gi * p.out_c + ch] = __float2bfloat16(ph.relu ? fmaxf(t, 0.f) : t);
+                  }
+                }
+              } else {  // G == 8 (or smaller powers of two folded into 8-wide pieces by the host check)
+#pragma unroll
+                for (int g = 0; g < 32; g += 8) {
+                  float m = v[g];
+#pragma unroll
+                  for (int e = 1; e < 8; ++e) m = fmaxf(m, v[g + e]);
+                  const long long gi = group0 + (s0 + g) / 8;
+                  if (gi < n_groups && ch < p.out_c) {
+                    const float t = m + b;
                     out[gi * p.out_c + ch] = __float2bfloat16(ph.relu ? fmaxf(t, 0.f) : t);
                   }
                 }
               }
             }
           }
-        } else {  // ACT_EPI_LOGITS: fp32, channel-first (B, out_c, n_points), bias, optional sigmoid
+        } else if (hh == 0) {  // ACT_EPI_LOGITS: fp32, channel-first (B, out_c, n_points), bias, optional sigmoid
           float* out = reinterpret_cast<float*>(p.out);
           float v[16];
           tmem_ld16(lane_base, v);
           if (row < p.P) {
             const long long bb = row / p.n_points;
-            const long long n = row % p.n_points;
+            const long long n = row - bb * p.n_points;
 #pragma unroll
             for (int c = 0; c < 16; ++c) {
               if (c < p.out_c) {
-                float t = v[c] + __ldg(bias + c);
+                float t = v[c] + sb[c];
                 if (ph.relu) t = fmaxf(t, 0.f);
                 if (p.sigmoid) t = 1.f / (1.f + __expf(-t));
                 out[(bb * p.out_c + c) * p.n_points + n] = t;
@@ -456,7 +537,7 @@ __global__ void __launch_bounds__(kChainThreads, 1) mlp_chain_kernel(const __gri
           }
         }
         if (ph.reload) {
-          stage_input(p, act, tile, ph.load_begin, ph.load_end, r);
+          stage_input(p, act, tile, ph.load_begin, ph.load_end, r, hh);
           cp_async_wait_all();
         }
         tc_fence_before();
@@ -469,7 +550,7 @@ __global__ void __launch_bounds__(kChainThreads, 1) mlp_chain_kernel(const __gri
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 4) tmem_dealloc(tmem_base, (unsigned)p.tmem_cols);
+  if (warp == kControlWarp) tmem_dealloc(tmem_base, (unsigned)p.tmem_cols);
 }
 
 }  // namespace s4g
@@ -527,7 +608,8 @@ static int plan_chain(s4g_chain* ch, int n_layers, const int* cin, const int* co
   }
   if (out_mode == ACT_EPI_MAXPOOL) {
     ch->cout_pad[L - 1] = round_up(cout[L - 1], 128);
-    S4G_CHECK_ARG(group >= 1 && group <= 128 && (128 % group) == 0, "mlp_chain: max-pool group must divide 128");
+    S4G_CHECK_ARG(group == 8 || group == 16 || group == 32 || group == 64 || group == 128,
+                  "mlp_chain: max-pool group (neighbours per centroid) must be 8, 16, 32, 64 or 128");
   } else if (out_mode == ACT_EPI_LOGITS) {
     S4G_CHECK_ARG(cout[L - 1] <= 16, "mlp_chain: logits layer supports <= 16 outputs");
     ch->cout_pad[L - 1] = 16;
@@ -561,6 +643,7 @@ static int plan_chain(s4g_chain* ch, int n_layers, const int* cin, const int* co
         ph.n_begin = ns[ni].first; ph.n_end = ns[ni].second;
         ph.transposed = (last && out_mode == ACT_EPI_MAXPOOL) ? 1 : 0;
         ph.n_chunk = ph.transposed ? 128 : pick_n_chunk(ph.n_end - ph.n_begin);
+        ph.k_chunk = std::max(16, (kStageBytes / 2 / ph.n_chunk) / 16 * 16);  // ~32 KB per TMA request
         ph.first = (ki == 0);
         ph.relu = relu[l];
         ph.reload = 0;
@@ -580,6 +663,14 @@ static int plan_chain(s4g_chain* ch, int n_layers, const int* cin, const int* co
   }
   p.n_phases = np;
   p.act_c = act_c;
+  p.n_layers = L;
+  int boff = 0;
+  for (int l = 0; l < L; ++l) {
+    p.bias_off[l] = boff;
+    p.bias_len[l] = ch->cout_pad[l];
+    boff += ch->cout_pad[l];
+  }
+  p.bias_total = boff;
   int cols = 32;
   while (cols < tmem) cols *= 2;
   S4G_CHECK_ARG(cols <= 512, "mlp_chain: accumulator wider than TMEM");
@@ -599,13 +690,14 @@ static int plan_chain(s4g_chain* ch, int n_layers, const int* cin, const int* co
   p.w_bytes = (unsigned)wb;
   // shared memory: act + ring + barriers
   const size_t act_bytes = (size_t)act_c * kTileRows * 2;
-  const size_t budget = 227 * 1024 - 256;
+  const size_t tail = (size_t)p.bias_total * 4 + 256;  // staged shifts + barriers
+  const size_t budget = 227 * 1024 - tail;
   int stages = (int)((budget - act_bytes) / kStageBytes);
   S4G_CHECK_ARG(stages >= 2, "mlp_chain: activation tile leaves no room for the weight ring");
   // two CTAs per SM hide each other's epilogue when TMEM (<=256 columns) and smem allow it
   ch->ctas_per_sm = 1;
   if (cols <= 256) {
-    const size_t half = budget / 2 - 1024;
+    const size_t half = (227 * 1024) / 2 - 1024 - tail;
     if (act_bytes + 2 * kStageBytes <= half) {
       ch->ctas_per_sm = 2;
       stages = std::min(stages, (int)((half - act_bytes) / kStageBytes));
@@ -613,7 +705,7 @@ static int plan_chain(s4g_chain* ch, int n_layers, const int* cin, const int* co
   }
   stages = std::min(stages, 4);
   p.stages = stages;
-  ch->smem_bytes = act_bytes + (size_t)stages * kStageBytes + 256;
+  ch->smem_bytes = act_bytes + (size_t)stages * kStageBytes + tail;
   return S4G_OK;
 }
 
@@ -664,8 +756,8 @@ extern "C" int s4g_chain_pack_weights(const s4g_chain* ch, int layer, const floa
   const int fc = p.feat_c;
   for (int q = 0; q < p.n_phases; ++q) {
     const s4g::Phase& ph = p.phase[q];
-    for (int k = ph.k_begin; k < ph.k_end; k += 64) {
-      const int kw = std::min(64, ph.k_end - k);
+    for (int k = ph.k_begin; k < ph.k_end; k += ph.k_chunk) {
+      const int kw = std::min(ph.k_chunk, ph.k_end - k);
       for (int n = ph.n_begin; n < ph.n_end; n += ph.n_chunk) {
         if (ph.layer == layer) {
           for (int kk = 0; kk < kw; ++kk) {
