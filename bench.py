@@ -72,17 +72,21 @@ class ClockSampler:
     """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-         "clocks_event_reasons.sw_power_cap")
+         "clocks_event_reasons.sw_power_cap,timestamp")
 
     def __init__(self, gpu_index):
         self.gpu = gpu_index
         self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
         self.p = None
+        self.windows = []  # (t0, t1) wall-clock windows of the timed regions
+
+    def window(self, t0, t1):
+        self.windows.append((t0, t1))
 
     def __enter__(self):
         try:
             self.p = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
-                                       "--format=csv,noheader,nounits", "-lms", "100"], stdout=self.f,
+                                       "--format=csv,noheader,nounits", "-lms", "20"], stdout=self.f,
                                       stderr=subprocess.DEVNULL)
         except OSError:
             self.p = None
@@ -98,12 +102,22 @@ class ClockSampler:
         return False
 
     def summary(self):
+        import datetime
         sm, mx, reasons = [], [], set()
+        all_sm, all_mx = [], []
         try:
             self.f.flush()
             for line in open(self.f.name):
                 c = [x.strip() for x in line.split(",")]
-                if len(c) < 9:
+                if len(c) < 10:
+                    continue
+                all_sm.append(float(c[1]))
+                all_mx.append(float(c[2]))
+                try:
+                    ts = datetime.datetime.strptime(c[9], "%Y/%m/%d %H:%M:%S.%f").timestamp()
+                except ValueError:
+                    ts = None
+                if self.windows and ts is not None and not any(a - 0.02 <= ts <= b + 0.02 for a, b in self.windows):
                     continue
                 sm.append(float(c[1]))
                 mx.append(float(c[2]))
@@ -113,6 +127,9 @@ class ClockSampler:
             os.unlink(self.f.name)
         except (OSError, ValueError):
             pass
+        if not sm and all_sm:  # no sample fell inside a window: report the whole run, say so
+            return {"sm_mhz": statistics.median(all_sm), "sm_max_mhz": max(all_mx), "reasons": sorted(reasons),
+                    "samples": len(all_sm), "note": "no sample inside the timed windows; median over the whole run"}
         if not sm:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
         return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
@@ -189,7 +206,7 @@ def run_reference(args, rank, world):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=64, help="scenes per GPU per step")
@@ -231,13 +248,16 @@ def main():
             torch.cuda.synchronize()
 
     # ---------------- device-resident throughput ----------------
+    clocks = ClockSampler(local_rank)
+    clocks.__enter__()
     for _ in range(args.warmup):
         eng.forward(scenes)
     sync_all()
     launches0 = _lib.launches
     timers, step_events = [], []
-    with ClockSampler(local_rank) as clocks:
+    if True:
         sync_all()
+        t_w0 = time.time()
         for _ in range(args.steps):
             flush.zero_()  # evict L2 between steps (outside the per-step event pair)
             t = StageTimer()
@@ -248,6 +268,7 @@ def main():
             timers.append(t)
             step_events.append((a, b))
         sync_all()
+        clocks.window(t_w0, time.time())
     launches = (_lib.launches - launches0) // args.steps
     step_ms = [a.elapsed_time(b) for a, b in step_events]
     ms_local = sum(step_ms) / len(step_ms)
@@ -271,7 +292,10 @@ def main():
         torch.cuda.synchronize()
         if i >= args.warmup:
             e2e_ms.append(1e3 * (time.perf_counter() - t0))
+            clocks.window(time.time() - e2e_ms[-1] * 1e-3, time.time())
     e2e_local = sum(e2e_ms) / len(e2e_ms)
+    time.sleep(0.05)
+    clocks.__exit__(None, None, None)
 
     # ---------------- reduce over ranks (max time) ----------------
     if world > 1:
