@@ -9,6 +9,7 @@
 // soon as all of its centroids are full.  Every output slot is written exactly once (padding with
 // the first neighbour, zeros when there is none), so the outputs need no memset.
 #include "common.cuh"
+#include "grid.cuh"
 
 namespace s4g {
 
@@ -96,6 +97,8 @@ static int ball_query_entry(const float* points, const float* centroids, int B, 
   S4G_CHECK_ARG(B >= 0 && N > 0 && M > 0 && K > 0, "ball_query: bad shape B=%d N=%d M=%d K=%d", B, N, M, K);
   S4G_CHECK_ARG(B <= 65535, "ball_query: batch too large for one launch");
   if (B == 0) return S4G_OK;
+  if (N >= kGridBallMinPoints && K <= kGridBallMaxK && radius > 0.f)  // output-sensitive exact path (grid.cu)
+    return ball_query_grid<IndexT>(points, centroids, B, N, M, radius, K, index, count, stream);
   const float r2 = radius * radius;  // fp32 product, ball_query_kernel.cu:48
   const int per_cta = kBqWarps * kBqCentroids;
   dim3 grid((M + per_cta - 1) / per_cta, B);

@@ -8,6 +8,7 @@
 #include <cuda_bf16.h>
 
 #include "common.cuh"
+#include "grid.cuh"
 
 namespace s4g {
 
@@ -125,6 +126,8 @@ extern "C" int s4g_three_nn_weights_f32_i32(const float* query, const float* key
   S4G_CHECK_ARG(Nk >= 3, "three_nn_weights: num_key < 3");
   S4G_CHECK_ARG(B >= 0 && B <= 65535 && Nq > 0, "three_nn_weights: bad shape");
   if (B == 0) return S4G_OK;
+  if (Nk >= s4g::kGridKnnMinKeys)
+    return s4g::three_nn_grid<1>(query, key, B, Nq, Nk, index, weight, (cudaStream_t)stream);
   dim3 grid((Nq + s4g::kNnwThreads - 1) / s4g::kNnwThreads, B);
   s4g::three_nn_weights_kernel<<<grid, s4g::kNnwThreads, 0, (cudaStream_t)stream>>>(query, key, Nq, Nk, index, weight);
   S4G_LAUNCH_CHECK("three_nn_weights");

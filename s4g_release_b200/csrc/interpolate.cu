@@ -6,6 +6,7 @@
 // float4 tiles so every key costs one broadcast LDS.128 for 256 queries.  The candidate list is the
 // reference's strict-'<' insertion in key order (earlier key wins ties, ascending output).
 #include "common.cuh"
+#include "grid.cuh"
 
 namespace s4g {
 
@@ -116,6 +117,8 @@ extern "C" int s4g_point_search_f32(const float* query, const float* key, int B,
   S4G_CHECK_ARG(B >= 0 && Nq > 0, "point_search: bad shape");
   S4G_CHECK_ARG(B <= 65535, "point_search: batch too large for one launch");
   if (B == 0) return S4G_OK;
+  if (Nk >= s4g::kGridKnnMinKeys)
+    return s4g::three_nn_grid<0>(query, key, B, Nq, Nk, index, distance, (cudaStream_t)stream);
   dim3 grid((Nq + s4g::kNnThreads - 1) / s4g::kNnThreads, B);
   s4g::point_search_kernel<<<grid, s4g::kNnThreads, 0, (cudaStream_t)stream>>>(query, key, Nq, Nk, index, distance);
   S4G_LAUNCH_CHECK("point_search");

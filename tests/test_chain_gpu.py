@@ -113,11 +113,12 @@ def test_set_abstraction_gather_maxpool(feat_c, dims, B, N, M, K):
     _check(got, _bf(want))
 
 
-def test_fp_front_end():
+@pytest.mark.parametrize("Nq,Nk", [(700, 90), (3000, 1200)])
+def test_fp_front_end(Nq, Nk):
     from s4g_release_b200.engine import FusedPointNet2 as E
     from oracle import pn2_ext_cpu as ora
     g = torch.Generator().manual_seed(4)
-    B, Nq, Nk, C2, C1 = 2, 700, 90, 64, 32
+    B, C2, C1 = 2, 64, 32
     q = torch.rand(B, 3, Nq, generator=g)
     k = torch.rand(B, 3, Nk, generator=g)
     idx, w = E.three_nn_weights(q.cuda(), k.cuda())

@@ -91,6 +91,10 @@ BQ_CASES = [
     ("uniform", 3, 777, 333, 0.2, 7), ("uniform", 2, 100, 100, 0.5, 128), ("uniform", 2, 50, 3, 1e-4, 8),
     ("lattice", 2, 2000, 500, 0.125, 32), ("lattice", 2, 2000, 500, 0.25, 64), ("dup", 2, 3000, 400, 0.05, 32),
     ("identical", 2, 300, 20, 0.1, 16), ("uniform", 2, 33, 33, 10.0, 40), ("uniform", 1, 4099, 517, 0.07, 33),
+    # grid path (N >= 4096): ties, duplicates, buffer overflow -> exact linear-scan fallback, huge / tiny radii
+    ("lattice", 2, 6000, 700, 0.125, 32), ("lattice", 2, 6000, 300, 0.3, 64), ("dup", 2, 8000, 900, 0.05, 32),
+    ("identical", 2, 5000, 40, 0.1, 16), ("uniform", 2, 5000, 300, 10.0, 128), ("uniform", 2, 5000, 300, 1e-4, 8),
+    ("uniform", 1, 20000, 1000, 0.05, 200), ("uniform", 3, 4096, 512, 0.11, 64),
 ]
 
 
@@ -106,8 +110,9 @@ def test_ball_query_bit_exact(ext, ora, kind, B, N, M, r, K):
     assert torch.equal(got_idx.cpu(), want_idx)
 
 
-def test_ball_query_no_hits_and_far_centroids(ext, ora):
-    pts = inputs.uniform_cloud(2, 500, 3)
+@pytest.mark.parametrize("n", [500, 6000])
+def test_ball_query_no_hits_and_far_centroids(ext, ora, n):
+    pts = inputs.uniform_cloud(2, n, 3)
     far = (pts[:, :, :37] + 10.0).contiguous()
     idx, cnt = ext.ball_query(pts.cuda(), far.cuda(), 0.1, 8)
     assert (idx == 0).all() and (cnt == 0).all()
@@ -166,7 +171,10 @@ def test_group_points_forward_backward(ext, ora, B, C, N, M, K):
 
 @pytest.mark.parametrize("kind,B,Nq,Nk", [("uniform", 2, 1024, 256), ("uniform", 2, 5120, 1024), ("uniform", 1, 25600, 5120),
                                           ("lattice", 2, 3000, 300), ("dup", 2, 2000, 900), ("uniform", 3, 101, 3),
-                                          ("identical", 2, 50, 10), ("uniform", 1, 300, 2049)])
+                                          ("identical", 2, 50, 10), ("uniform", 1, 300, 2049),
+                                          # grid path (Nk >= 1024): ties, duplicates, 3-D clouds (many fall back)
+                                          ("lattice", 2, 3000, 1500), ("dup", 2, 2000, 2000), ("identical", 1, 300, 1100),
+                                          ("uniform", 2, 4000, 1024)])
 def test_point_search_bit_exact(ext, ora, kind, B, Nq, Nk):
     q = _gen(kind, B, Nq, seed=Nq)
     k = _gen(kind, B, Nk, seed=Nk + 1)
