@@ -111,8 +111,19 @@ s4g_chain* s4g_chain_create(int n_layers, const int* cin, const int* cout, const
 void s4g_chain_destroy(s4g_chain* chain);
 size_t s4g_chain_weight_bytes(const s4g_chain* chain);
 int s4g_chain_cout_pad(const s4g_chain* chain, int layer);
-int s4g_chain_info(const s4g_chain* chain, int* n_phases, int* act_c, int* stages, int* tmem_cols, int* smem_bytes,
-                   int* ctas_per_sm);
+/* Plan of the chain: MMA jobs per 128-row tile, activation slots / weight-ring stages in shared memory,
+ * input blocks each loader thread keeps in flight, dynamic shared memory, and the planner's estimate of SM
+ * cycles per tile (total, and tensor-pipe busy).  Works without a GPU. */
+int s4g_chain_info(const s4g_chain* chain, int* n_jobs, int* slots, int* stages, int* load_depth, int* smem_bytes,
+                   int* sim_cycles, int* mma_cycles);
+/* Optional per-CTA cycle counters (16 x int64 per CTA, for >= 148 CTAs, device memory; NULL switches them
+ * off): [0] producer total, [1] producer waiting for a free stage; [2] MMA warp total, [3..5] waiting for
+ * activations / TMEM / weights; [6] epilogue warps total, [7] waiting for an accumulator, [12] for a free
+ * slot, [10] epilogue work; [11] loader total, [8] loader waiting for a free slot, [9] for cp.async.
+ * Measurement aid for profiles/chain_prof.py. */
+int s4g_chain_set_profile(s4g_chain* chain, void* counters_dev);
+/* Human-readable dump of the job streams into buf (debugging); returns bytes written. */
+int s4g_chain_describe(const s4g_chain* chain, char* buf, int cap);
 int s4g_chain_pack_weights(const s4g_chain* chain, int layer, const float* w_host, int cout_real, int cin_real,
                            void* packed_host);
 int s4g_chain_set_params(s4g_chain* chain, const void* weights_dev, const float* const* bias_dev);

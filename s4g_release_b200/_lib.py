@@ -44,7 +44,9 @@ _SIGNATURES = {
     "s4g_chain_destroy": ([_vp], None),
     "s4g_chain_weight_bytes": ([_vp], ctypes.c_size_t),
     "s4g_chain_cout_pad": ([_vp, _i], _i),
-    "s4g_chain_info": ([_vp, _ip, _ip, _ip, _ip, _ip, _ip], _i),
+    "s4g_chain_info": ([_vp, _ip, _ip, _ip, _ip, _ip, _ip, _ip], _i),
+    "s4g_chain_describe": ([_vp, ctypes.c_char_p, _i], _i),
+    "s4g_chain_set_profile": ([_vp, _vp], _i),
     "s4g_chain_pack_weights": ([_vp, _i, _vp, _i, _i, _vp], _i),
     "s4g_chain_set_params": ([_vp, _vp, _vp], _i),
     "s4g_chain_run_rows": ([_vp, _vp, _i, ctypes.c_longlong, _vp, _i, _vp], _i),

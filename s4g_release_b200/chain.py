@@ -48,10 +48,20 @@ class MlpChain:
               "chain_set_params")
 
     def info(self):
-        vals = [ctypes.c_int() for _ in range(6)]
+        vals = [ctypes.c_int() for _ in range(7)]
         check(lib.s4g_chain_info(self._h, *[ctypes.byref(v) for v in vals]), "chain_info")
-        keys = ("n_phases", "act_c", "stages", "tmem_cols", "smem_bytes", "ctas_per_sm")
+        keys = ("n_jobs", "slots", "stages", "load_depth", "smem_bytes", "sim_cycles", "mma_cycles")
         return {k: v.value for k, v in zip(keys, vals)}
+
+    def describe(self):
+        buf = ctypes.create_string_buffer(1 << 16)
+        lib.s4g_chain_describe(self._h, buf, len(buf))
+        return buf.value.decode()
+
+    def set_profile(self, counters):
+        """counters: int64 CUDA tensor [>=148, 16] (or None) — see s4g_chain_set_profile."""
+        self._prof = counters
+        check(lib.s4g_chain_set_profile(self._h, ptr(counters) if counters is not None else None), "chain_set_profile")
 
     def flops(self, rows):
         return 2.0 * rows * sum(ci * co for ci, co in zip(self.cin, self.cout))
