@@ -11,6 +11,7 @@ from bench import seeded_model  # noqa: E402
 from s4g_release_b200.engine import FusedPointNet2  # noqa: E402
 
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 64
+TRACE = sys.argv[2].split(",") if len(sys.argv) > 2 else []
 net = seeded_model().cuda()
 eng = FusedPointNet2(net)
 cfg = eng.cfg
@@ -21,7 +22,7 @@ NAMES = ["prod_total", "prod_wait_stage", "mma_total", "mma_wait_act", "mma_wait
 
 
 def timed(name, chain, fn, rows):
-    cnt = torch.zeros(148, 16, dtype=torch.int64, device=dev)
+    cnt = torch.zeros(148 * 16 + 4 * 128 + 4 * 32, dtype=torch.int64, device=dev)
     chain.set_profile(cnt)
     fn()
     torch.cuda.synchronize()
@@ -33,7 +34,8 @@ def timed(name, chain, fn, rows):
     torch.cuda.synchronize()
     ms = a.elapsed_time(b)
     chain.set_profile(None)
-    c = cnt.double().mean(0).cpu().tolist()
+    c = cnt[:148 * 16].reshape(148, 16).double().mean(0).cpu().tolist()
+    trace = cnt[148 * 16:].cpu().tolist()
     info = chain.info()
     tiles = (rows + 127) // 128 / 148.0
     tf = chain.flops(rows) / ms / 1e9
@@ -41,6 +43,19 @@ def timed(name, chain, fn, rows):
           (name, ms, tf, tiles, c[2] / tiles, info["sim_cycles"], info["mma_cycles"], info["slots"], info["stages"],
            info["n_jobs"]))
     print("           " + "  ".join("%s %.0f" % (n, v / tiles) for n, v in zip(NAMES, c)))
+    if TRACE and name in TRACE:
+        nj, ne = info["n_jobs"], 32
+        t0 = min(v for v in trace if v > 0)
+        print("   MMA jobs of CTA 0, 3rd tile (cycles from the tile's first event): wait_begin waits_done issued probed")
+        for j in range(nj):
+            r = trace[4 * j: 4 * j + 4]
+            print("     job %2d: %6d %6d %6d %6d   (wait %5d, issue %5d, probe %5d)" % (j, r[0] - t0, r[1] - t0, r[2] - t0, r[3] - t0,
+                  r[1] - r[0], r[2] - r[1], r[3] - r[2]))
+        print("   epilogue jobs (first warp of the group that ran it): wait_begin acc_full done")
+        for j in range(ne):
+            r = trace[4 * 128 + 4 * j: 4 * 128 + 4 * j + 3]
+            if r[0] > 0:
+                print("     epi %2d: %6d %6d %6d   (waited %5d, work %5d)" % (j, r[0] - t0, r[1] - t0, r[2] - t0, r[1] - r[0], r[2] - r[1]))
 
 
 N = cfg["num_points"] if "num_points" in cfg else 25600

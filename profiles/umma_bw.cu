@@ -22,7 +22,7 @@ __device__ __forceinline__ void commit(uint64_t* bar) {
 
 // warp 0: MMA issue; warps 1..tma_warps: TMA streams; warps 8..15: STS traffic (if sts != 0)
 __global__ void __launch_bounds__(512, 1) k(const uint8_t* src, size_t src_bytes, int N, int n_mma, int tma_warps, int chunk,
-                                            int sts, int same_operand, long long* out) {
+                                            int sts, int same_operand, long long* out, int fill = 0) {
   extern __shared__ __align__(1024) uint8_t smem[];
   // [0,64K) A region, [64K,128K) B region, [128K, 128K+64K) TMA ring (4 x 16K), [192K, 208K) STS scratch, then barriers
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 208 * 1024);
@@ -40,6 +40,17 @@ __global__ void __launch_bounds__(512, 1) k(const uint8_t* src, size_t src_bytes
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tm = tslot;
+  if (fill) {  // operand data: 1 = random bf16 in [-1, 1), 2 = zeros (tensor-pipe power depends on the data)
+    uint32_t* w = reinterpret_cast<uint32_t*>(smem);
+    uint32_t x = 0x9E3779B9u * (threadIdx.x + 1) + blockIdx.x;
+    for (int i = threadIdx.x; i < 128 * 1024 / 4; i += blockDim.x) {
+      x = x * 1664525u + 1013904223u;
+      const uint32_t lo = 0x3F00u | ((x >> 9) & 0x807Fu), hi = 0x3F00u | ((x >> 20) & 0x807Fu);
+      w[i] = fill == 1 ? (lo | (hi << 16)) : 0u;
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncthreads();
+  }
   volatile int* stop = reinterpret_cast<volatile int*>(smem + 208 * 1024 + 512);
   if (threadIdx.x == 0) *stop = 0;
   __syncthreads();
@@ -116,17 +127,19 @@ int main() {
   int clk_khz = 0;
   cudaDeviceGetAttribute(&clk_khz, cudaDevAttrClockRate, 0);
   printf("N  same tma_warps chunk sts | cyc/MMA  flop/cyc/SM  tma_B/cyc/SM  sts_B/cyc/SM   (grid 148)\n");
-  const int n_mma = 20000;
-  struct Cfg { int N, same, tw, chunk, sts; };
+  const int n_mma = 200000;  // ~13 ms per configuration: long enough for the power limiter to act
+  struct Cfg { int N, same, tw, chunk, sts, fill; };
   Cfg cfgs[] = {{128, 1, 0, 16384, 0}, {128, 0, 0, 16384, 0}, {256, 0, 0, 16384, 0}, {64, 0, 0, 16384, 0},
                 {128, 0, 1, 16384, 0}, {128, 0, 2, 16384, 0}, {128, 0, 4, 16384, 0}, {128, 0, 2, 8192, 0},
                 {128, 0, 1, 32768, 0}, {256, 0, 2, 16384, 0}, {256, 0, 4, 16384, 0},
                 {128, 0, 0, 16384, 1}, {128, 0, 0, 16384, 200}, {256, 0, 0, 16384, 1}, {128, 0, 2, 16384, 200},
-                {256, 0, 2, 16384, 200}, {16, 0, 0, 16384, 0}};
+                {256, 0, 2, 16384, 200}, {16, 0, 0, 16384, 0},
+                {256, 0, 0, 16384, 0, 2}, {256, 0, 0, 16384, 0, 1}, {128, 0, 0, 16384, 0, 1}, {256, 0, 2, 16384, 0, 1},
+                {256, 0, 2, 16384, 200, 1}};
   for (const Cfg& c : cfgs) {
     if (c.tw * 2 * c.chunk > 64 * 1024) continue;
     cudaMemset(out, 0, 148 * 4 * sizeof(long long));
-    k<<<148, 512, 210 * 1024>>>(src, src_bytes, c.N, n_mma, c.tw, c.chunk, c.sts, c.same, out);
+    k<<<148, 512, 210 * 1024>>>(src, src_bytes, c.N, n_mma, c.tw, c.chunk, c.sts, c.same, out, c.fill);
     cudaError_t e = cudaDeviceSynchronize();
     if (e != cudaSuccess) { printf("error: %s\n", cudaGetErrorString(e)); return 1; }
     long long h[148 * 4];
@@ -134,7 +147,8 @@ int main() {
     double cyc = 0, tma = 0, sts = 0;
     for (int i = 0; i < 148; ++i) { cyc += h[i * 4]; tma += h[i * 4 + 1]; sts += h[i * 4 + 2]; }
     cyc /= 148;
-    printf("%3d %4d %9d %5d %3d | %7.1f  %10.0f  %11.1f  %11.1f\n", c.N, c.same, c.tw, c.chunk, c.sts, cyc / n_mma,
+    printf("%3d %4d %9d %5d %3d %s | %7.1f  %10.0f  %11.1f  %11.1f\n", c.N, c.same, c.tw, c.chunk, c.sts,
+           c.fill == 1 ? "random" : c.fill == 2 ? "zeros " : "uninit", cyc / n_mma,
            2.0 * 128 * c.N * 16 * n_mma / cyc, tma / 148 / cyc, sts / 148 / cyc);
   }
   return 0;

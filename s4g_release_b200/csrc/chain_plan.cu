@@ -61,7 +61,10 @@ bool build_draft(const s4g_chain* ch, const int* relu, int feat_c, int S, bool p
     // N-outer (one output block after the other, each over all K-blocks; the epilogue of block n overlaps
     // the MMAs of block n+1) needs every K-block and all but the last output block resident at once;
     // otherwise K-outer: up to 4 accumulators filled K-block by K-block, inputs released as they go.
-    const int need = nk + (last ? 0 : nn - 1);
+    // (the outputs of the LAST N-group — a pair of blocks when pairs are allowed — are written only after
+    // every K-block of the layer has been released, so they need no slot of their own)
+    const int last_grp = (pair_ok && !transposed && nn >= 2 && nn % 2 == 0 && (d.n_acc % 2 == 0)) ? 2 : 1;
+    const int need = nk + (last ? 0 : nn - last_grp);
     const bool n_outer = need <= S;
     if (!n_outer && l > 0 && nn > kAccBlocks) return false;  // a hidden layer cannot be re-read in passes
     if (!n_outer && !last && nn > S) return false;

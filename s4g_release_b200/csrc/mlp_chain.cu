@@ -66,6 +66,16 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity) {
     if (++spins > (1u << 22)) __trap();
   }
 }
+// non-blocking probe (try_wait may suspend the thread for a hardware-defined time when the phase is pending)
+__device__ __forceinline__ bool mbar_test(uint64_t* bar, unsigned parity) {
+  unsigned ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+  return ok != 0;
+}
 __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned bytes, uint64_t* bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
                    smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
@@ -266,55 +276,105 @@ __global__ void __launch_bounds__(kChainThreads, 1) mlp_chain_kernel(const __gri
     }
   } else if (warp == kMmaWarp) {
     // ===================== MMA warp (converged; one elected lane issues tcgen05.mma / commit) =====================
-    int s = 0;
-    unsigned wuse = 0;
-    Ring base = {0, 0u};
-    unsigned base_q = 0;
+    // The issuing thread is the scarce resource (profiles/mma_loop.cu): everything a job needs — its table
+    // entry, ring positions and the state of the (up to four) barriers it waits on — is fetched and probed
+    // right after the PREVIOUS job's MMAs were issued, so those latencies overlap the tensor pipe.
     const uint32_t slots16 = smem_u32(slots) >> 4;
     const uint32_t ring16 = smem_u32(ring) >> 4;
     // descriptor high word: SBO = 128 B, version 1;  low word: (addr >> 4) | (LBO >> 4) << 16
     const uint64_t desc_hi = (uint64_t)((128u >> 4) | (1u << 14)) << 32;
     const uint32_t a_lbo16 = (uint32_t)kTileRows;  // (128 rows * 16 B) >> 4
     long long c_act = 0, c_tm = 0, c_w = 0;
-    bool w_ready = false;
     const long long t_begin = tick<PROF>();
+    struct Next {
+      MmaJob job;
+      int slot, s;
+      unsigned use, q, tb, wuse;
+      bool ok_act, ok_tm, ok_w;
+    };
+    Ring base = {0, 0u};
+    unsigned base_q = 0;
+    int s = 0;
+    unsigned wuse = 0;
+    auto prepare = [&](int j) -> Next {
+      Next x;
+      x.job = p.mma[j];
+      ring_at(base, p, x.job.blk_mod, x.job.blk_div, x.slot, x.use);
+      x.q = base_q + x.job.acc;
+      x.tb = x.q & (kAccBlocks - 1);
+      x.s = s;
+      x.wuse = wuse;
+      x.ok_act = !(x.job.flags & MF_WAIT_ACT) || mbar_test(&act_ready[x.slot], x.use & 1);
+      const bool need_tm = (x.job.flags & MF_FIRST_K) && x.q >= (unsigned)kAccBlocks;
+      x.ok_tm = !need_tm || (mbar_test(&tm_empty[x.tb], ((x.q >> 2) - 1) & 1) &&
+                             (!(x.job.flags & MF_PAIR) || mbar_test(&tm_empty[x.tb + 1], ((x.q >> 2) - 1) & 1)));
+      x.ok_w = mbar_test(&w_full[s], wuse & 1);
+      return x;
+    };
+    Next cur = {};
+    if (n_my > 0) cur = prepare(0);
     for (int it = 0; it < n_my; ++it) {
       for (int j = 0; j < p.n_mma; ++j) {
-        const MmaJob job = p.mma[j];
-        int slot;
-        unsigned use;
-        ring_at(base, p, job.blk_mod, job.blk_div, slot, use);
-        const unsigned q = base_q + job.acc;
-        const unsigned tb = q & (kAccBlocks - 1);
+        const MmaJob job = cur.job;
+        const int slot = cur.slot;
+        const unsigned q = cur.q, tb = cur.tb;
         const long long t0 = tick<PROF>();
-        if (job.flags & MF_WAIT_ACT) mbar_wait(&act_ready[slot], use & 1);
+        if (!cur.ok_act) mbar_wait(&act_ready[slot], cur.use & 1);
         const long long t1 = tick<PROF>();
-        if ((job.flags & MF_FIRST_K) && q >= (unsigned)kAccBlocks) {
+        if (!cur.ok_tm) {
           mbar_wait(&tm_empty[tb], ((q >> 2) - 1) & 1);
           if (job.flags & MF_PAIR) mbar_wait(&tm_empty[tb + 1], ((q >> 2) - 1) & 1);
         }
         const long long t2 = tick<PROF>();
-        if (!w_ready) mbar_wait(&w_full[s], wuse & 1);
+        if (!cur.ok_w) mbar_wait(&w_full[cur.s], cur.wuse & 1);
         const long long t3 = tick<PROF>();
         c_act += t1 - t0; c_tm += t2 - t1; c_w += t3 - t2;
+        if (PROF && p.prof && blockIdx.x == 0 && it == 2 && lane == 0) {
+          long long* tr = p.prof + 148 * 16 + j * 4;
+          tr[0] = t0; tr[1] = t3;
+        }
         tc_fence_after();
+        // The MMA queue is shallow (an issue blocks until the previous MMA has started), so the thread-side
+        // work for the NEXT job is done between this job's MMAs, while the tensor pipe is busy: all but the
+        // last MMA, then fetch + probe the next job, then the last MMA and the commits.
+        const uint32_t n = (uint32_t)job.n8 * 8u;
+        const bool transposed = (job.flags & MF_TRANSPOSED) != 0;
+        const uint32_t idesc = make_idesc(128, transposed ? kTileRows : (int)n);
+        const uint32_t a_lo = (slots16 + (uint32_t)slot * (kSlotBytes >> 4) + (uint32_t)job.koff * (2u * a_lbo16)) | (a_lbo16 << 16);
+        const uint32_t w_lo = (ring16 + (uint32_t)cur.s * (kStageBytes >> 4)) | (n << 16);  // LBO = n rows * 16 B
+        // operand order is swapped BEFORE the loop: a predicated-off tcgen05.mma still costs an issue slot
+        const uint32_t x0 = transposed ? w_lo : a_lo, y0 = transposed ? a_lo : w_lo;
+        const uint32_t x_step = transposed ? 2u * n : 2u * a_lbo16;  // next 16 channels = 2 K pieces
+        const uint32_t y_step = transposed ? 2u * a_lbo16 : 2u * n;
+        const uint32_t d_addr = tmem_base + tb * 128u;
+        const uint32_t acc0 = (job.flags & MF_FIRST_K) ? 0u : 1u;
+        const int k_last = job.k16 - 1;
         if (elect_one()) {
-          const uint32_t n = (uint32_t)job.n8 * 8u;
-          const bool transposed = (job.flags & MF_TRANSPOSED) != 0;
-          const uint32_t idesc = make_idesc(128, transposed ? kTileRows : (int)n);
-          uint32_t a_lo = (slots16 + (uint32_t)slot * (kSlotBytes >> 4) + (uint32_t)job.koff * (2u * a_lbo16)) | (a_lbo16 << 16);
-          uint32_t w_lo = (ring16 + (uint32_t)s * (kStageBytes >> 4)) | (n << 16);  // LBO = n rows * 16 B
-          const uint32_t d_addr = tmem_base + tb * 128u;
-          uint32_t acc = (job.flags & MF_FIRST_K) ? 0u : 1u;
+          uint32_t x_lo = x0, y_lo = y0, acc = acc0;
 #pragma unroll 1
-          for (int k = 0; k < job.k16; ++k) {
-            if (transposed) umma_bf16(d_addr, desc_hi | w_lo, desc_hi | a_lo, idesc, acc);
-            else umma_bf16(d_addr, desc_hi | a_lo, desc_hi | w_lo, idesc, acc);
+          for (int k = 0; k < k_last; ++k) {
+            umma_bf16(d_addr, desc_hi | x_lo, desc_hi | y_lo, idesc, acc);
             acc = 1u;
-            a_lo += 2u * a_lbo16;  // next 16 channels = 2 K pieces
-            w_lo += 2u * n;
+            x_lo += x_step;
+            y_lo += y_step;
           }
-          umma_commit(&w_empty[s]);                                  // stage reusable once these MMAs have read it
+        }
+        __syncwarp();
+        // advance to the next job (possibly the first one of the CTA's next tile) and probe its barriers
+        const int s_cur = cur.s;
+        if (++s == p.stages) { s = 0; ++wuse; }
+        int jn = j + 1;
+        if (jn == p.n_mma) {
+          jn = 0;
+          ring_advance(base, p);
+          base_q += (unsigned)p.n_acc;
+        }
+        if (jn != 0 || it + 1 < n_my) cur = prepare(jn);
+        if (PROF && p.prof && blockIdx.x == 0 && it == 2 && lane == 0) p.prof[148 * 16 + j * 4 + 2] = tick<PROF>();
+        if (elect_one()) {
+          umma_bf16(d_addr, desc_hi | (x0 + x_step * (uint32_t)k_last), desc_hi | (y0 + y_step * (uint32_t)k_last), idesc,
+                    k_last > 0 ? 1u : acc0);
+          umma_commit(&w_empty[s_cur]);                              // stage reusable once these MMAs have read it
           if (job.flags & MF_LAST_K) {                               // accumulator(s) complete
             umma_commit(&tm_full[tb]);
             if (job.flags & MF_PAIR) umma_commit(&tm_full[tb + 1]);
@@ -322,12 +382,8 @@ __global__ void __launch_bounds__(kChainThreads, 1) mlp_chain_kernel(const __gri
           if (job.flags & MF_RELEASE) umma_commit(&blk_free[job.blk]);  // activation block dead
         }
         __syncwarp();
-        if (++s == p.stages) { s = 0; ++wuse; }
-        // poll the next chunk's barrier now: the probe's latency overlaps the MMAs just issued
-        w_ready = mbar_try_wait(&w_full[s], wuse & 1);
+        if (PROF && p.prof && blockIdx.x == 0 && it == 2 && lane == 0) p.prof[148 * 16 + j * 4 + 3] = tick<PROF>();
       }
-      ring_advance(base, p);
-      base_q += (unsigned)p.n_acc;
     }
     if (PROF && p.prof && lane == 0) {
       p.prof[blockIdx.x * 16 + 2] = tick<PROF>() - t_begin;
@@ -551,6 +607,10 @@ __global__ void __launch_bounds__(kChainThreads, 1) mlp_chain_kernel(const __gri
             mbar_arrive(&tm_empty[tb]);
           }
           c_epi += tick<PROF>() - t1;
+          if (PROF && p.prof && blockIdx.x == 0 && it == 2 && (threadIdx.x & 255) == 0) {
+            long long* tr = p.prof + 148 * 16 + 4 * kMaxMmaJobs + j * 4;
+            tr[0] = t0; tr[1] = t1; tr[2] = tick<PROF>();
+          }
           continue;
         }
         const long long t0 = tick<PROF>();
@@ -632,6 +692,10 @@ __global__ void __launch_bounds__(kChainThreads, 1) mlp_chain_kernel(const __gri
         __syncwarp();
         if (lane == 0) mbar_arrive(&tm_empty[tb]);
         c_epi += tick<PROF>() - t1;
+        if (PROF && p.prof && blockIdx.x == 0 && it == 2 && (threadIdx.x & 255) == 0) {
+          long long* tr = p.prof + 148 * 16 + 4 * kMaxMmaJobs + j * 4;
+          tr[0] = t0; tr[1] = t1; tr[2] = tick<PROF>();
+        }
       }
       ring_advance(base, p);
       base_q += (unsigned)p.n_acc;
