@@ -132,6 +132,40 @@ int s4g_chain_run_rows(const s4g_chain* chain, const void* in_rows, int in_strid
 int s4g_chain_run_gather(const s4g_chain* chain, const void* feat, const float* xyz, const float* ctr, const int* nbr,
                          int B, int N, int M, int K, void* out, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Device-side grasp post-processing (csrc/postprocess.cu) — replaces the numpy / python tail of
+ * GraspDetector: post_processing + orthogonalization (grasp_detector.py:124-185), the per-pose collision loop
+ * (:214-232 over cloud_processor/view_collision_checker.py:37-65), importance sampling (:235-251), and adds
+ * the translation de-duplication sketched at utils/file_logger_cls.py:220-225 (the reference ships no NMS).
+ * All pointers are device pointers unless said otherwise.
+ * ------------------------------------------------------------------------------------------------ */
+/* softmax over the C score classes (fp32) and expectation with np.linspace(0,1,C+1)[1:] (fp64): (B,C,N) -> (B,N). */
+int s4g_grasp_scores_f32(const float* score_logits, int B, int C, int N, double* score, void* stream);
+/* threshold -> descending-score ranks -> verticalness filter, with the reference's indexing (see the file
+ * header).  approach_row (HOST, 3 x fp64) = third row of -(camera2base_R @ TRAIN2REAL_R).  workspace: 2*B*N
+ * int32.  n_out[b] may exceed max_out (then only max_out entries were written: enlarge and call again). */
+int s4g_grasp_select(const double* score, const float* frame_R, int B, int N, double score_threshold,
+                     double vertical_threshold, const double* approach_row, int* workspace, int max_out, int* out_point,
+                     int* out_rot, int* n_out, int* n_high, void* stream);
+/* translation decode + Gram-Schmidt + TRAIN2REAL: poses [B][max_out][4][4] fp64, out_score [B][max_out] fp64.
+ * n_high and workspace are the outputs of s4g_grasp_select (the rank table lives in the workspace);
+ * train2real (16 x fp64, row-major) and t_score (T x fp64) are HOST pointers. */
+int s4g_grasp_poses(const float* points, const float* frame_R, const float* frame_t, const double* score, int B, int N,
+                    int T, const int* out_point, const int* out_rot, const int* n_out, const int* n_high,
+                    const int* workspace, int max_out, const double* train2real, const double* t_score, double* poses,
+                    double* out_score, void* stream);
+/* view_non_collision for every pose against the (n_points,3) cloud; ok[p] = 1 if the grasp is collision free.
+ * gripper (HOST, 8 floats): finger_length, bottom_length, half_hand_thickness, half_bottom_width,
+ * half_bottom_space, back_margin, back_threshold, finger_threshold.  counts (optional): [n_poses][2]. */
+int s4g_grasp_collision_f32(const double* poses, int n_poses, const float* cloud_n3, int n_points, const float* gripper,
+                            unsigned char* ok, int* counts, void* stream);
+/* greedy de-duplication in the given order: drop a pose whose translation is within L1 distance min_dist of a
+ * kept one.  kept: [n] int32, n_kept: 1 int32. */
+int s4g_grasp_nms(const double* poses, const int* order, int n, double min_dist, int* kept, int* n_kept, void* stream);
+/* importance sampling: cum = cumsum(exp(5 * scores)); picked[i] = first index with cum >= sorted_uniform[i] * cum[-1]. */
+int s4g_grasp_importance_sample(const double* scores, int n, const double* sorted_uniform, int m, double* cum, int* picked,
+                                void* stream);
+
 #ifdef __cplusplus
 }
 #endif

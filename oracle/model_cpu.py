@@ -160,13 +160,21 @@ def orthogonalization(batch_rotation, batch_translation):
     return mat44
 
 
-def post_processing(points_array, predictions, score_threshold=0.7, vertical_degree_threshold=0.2):
-    """grasp_detector.py:137-185 for batch element 0, including the behaviour that
-    ``frame_R`` is indexed with positions *within* the filtered set (:153)."""
-    all_scores = torch.softmax(predictions["score"][0], dim=0).detach().cpu().numpy()
+def grasp_scores(score_logits):
+    """grasp_detector.py:142-145 for one scene: (C, N) logits -> (N,) fp64 expected score."""
+    all_scores = torch.softmax(score_logits, dim=0).detach().cpu().numpy()
     score_classes = all_scores.shape[0]
     score_value = np.linspace(0, 1, score_classes + 1)[1:][:, np.newaxis]
-    all_scores = np.sum(score_value * all_scores, axis=0)
+    return np.sum(score_value * all_scores, axis=0)
+
+
+def post_processing(points_array, predictions, score_threshold=0.7, vertical_degree_threshold=0.2, all_scores=None,
+                    return_index=False):
+    """grasp_detector.py:137-185 for batch element 0, including the behaviour that
+    ``frame_R`` is indexed with positions *within* the filtered set (:153).  ``all_scores`` (optional)
+    replaces the first step so a test can check the index logic exactly on another implementation's scores."""
+    if all_scores is None:
+        all_scores = grasp_scores(predictions["score"][0])
     high_score_index = np.nonzero(all_scores > score_threshold)[0]
     index_high2low = np.argsort(all_scores[high_score_index])[::-1]
     rotation = predictions["frame_R"][0].detach().cpu().numpy()[:, index_high2low]
@@ -186,4 +194,77 @@ def post_processing(points_array, predictions, score_threshold=0.7, vertical_deg
     global_translation = -(translation * T_SCORE[np.newaxis, :]).sum(1, keepdims=True) * rotation[:, :, 0] + points
     global_mat44 = orthogonalization(rotation, global_translation)
     global_mat44 = np.matmul(TRAIN2REAL[np.newaxis, :, :], global_mat44)
+    if return_index:
+        return global_mat44, scores, valid_index, index_good_direction
     return global_mat44, scores
+
+
+# --------------------------------------------------------------------------- #
+# Collision check, importance sampling, de-duplication (CPU restatements; test infrastructure only)
+# --------------------------------------------------------------------------- #
+# configs/gripper_config.py:9-21, configs/processing_config.py:19,37-40
+GRIPPER = dict(half_bottom_width=0.057, bottom_length=0.16, finger_width=0.023, half_hand_thickness=0.012,
+               finger_length=0.09, back_collision_margin=0.0, back_collision_threshold=10 * np.sqrt(8),
+               finger_collision_threshold=10)
+GRIPPER["half_bottom_space"] = GRIPPER["half_bottom_width"] - GRIPPER["finger_width"]
+
+
+def batch_transformation_inv(poses):
+    """utils/math_utils.py:27-40 on fp32 copies of the (n,4,4) poses."""
+    t = torch.as_tensor(poses, dtype=torch.float32)
+    out = torch.eye(4, dtype=torch.float32).unsqueeze(0).repeat(t.shape[0], 1, 1)
+    out[:, :3, :3] = t[:, :3, :3].transpose(1, 2)
+    out[:, :3, 3:] = torch.bmm(-t[:, :3, :3].transpose(1, 2), t[:, :3, 3:])
+    return out
+
+
+def view_non_collision(global2local, cloud_homo, g=GRIPPER, return_counts=False):
+    """cloud_processor/view_collision_checker.py:37-65.  cloud_homo: (4, n) fp32."""
+    local = torch.matmul(global2local, cloud_homo)
+    close = (local[0] < g["finger_length"]) & (local[0] > -g["bottom_length"])
+    pts = local[:, close][0:3]
+    zc = (pts[2] < g["half_hand_thickness"]) & (pts[2] > -g["half_hand_thickness"])
+    back = (pts[1] < g["half_bottom_width"]) & (pts[1] > -g["half_bottom_width"]) & \
+           (pts[0] < -g["back_collision_margin"]) & zc
+    left = (pts[1] < g["half_bottom_width"]) & (pts[1] > g["half_bottom_space"])
+    right = (pts[1] > -g["half_bottom_width"]) & (pts[1] < -g["half_bottom_space"])
+    finger = zc & (left | right)
+    n_back, n_finger = int(back.sum()), int(finger.sum())
+    ok = not (n_back > g["back_collision_threshold"]) and not (n_finger > g["finger_collision_threshold"])
+    return (ok, n_back, n_finger) if return_counts else ok
+
+
+def collision_filter(poses, cloud_n3):
+    """grasp_detector.py:214-224: indices of the collision-free poses, plus the per-pose point counts."""
+    cloud = torch.as_tensor(cloud_n3, dtype=torch.float32)
+    homo = torch.cat([cloud.t(), torch.ones(1, cloud.shape[0])], dim=0)
+    inv = batch_transformation_inv(poses)
+    res = [view_non_collision(inv[i], homo, return_counts=True) for i in range(inv.shape[0])]
+    ok = np.array([r[0] for r in res], dtype=bool)
+    counts = np.array([[r[1], r[2]] for r in res], dtype=np.int64).reshape(-1, 2)
+    return np.nonzero(ok)[0], counts
+
+
+def importance_sampling(scores, sorted_uniform):
+    """grasp_detector.py:235-246 with the random numbers passed in (np.sort(np.random.rand(k)))."""
+    cum = np.cumsum(np.exp(5 * np.asarray(scores, dtype=np.float64)))
+    out, index = [], 0
+    for u in sorted_uniform:
+        target = u * cum[-1]
+        while cum[index] < target:
+            index += 1
+        out.append(index)
+    return np.array(out, dtype=np.int64)
+
+
+def translation_nms(poses, scores, min_dist):
+    """Greedy de-duplication in descending score order (ties: lower index first): a pose is dropped when
+    the L1 distance of its translation to a kept pose is < min_dist — the check sketched, commented out,
+    at utils/file_logger_cls.py:220-225.  The reference ships no NMS (README.md:58); this is OUR definition."""
+    order = np.argsort(-np.asarray(scores, dtype=np.float64), kind="stable")
+    kept = []
+    for c in order:
+        t = poses[c, :3, 3]
+        if all(np.abs(poses[k, :3, 3] - t).sum() >= min_dist for k in kept):
+            kept.append(int(c))
+    return np.array(kept, dtype=np.int64)

@@ -22,6 +22,7 @@ lib = ctypes.CDLL(LIB_PATH)
 _vp = ctypes.c_void_p
 _i = ctypes.c_int
 _f = ctypes.c_float
+_d = ctypes.c_double
 _ip = ctypes.POINTER(ctypes.c_int)
 
 _SIGNATURES = {
@@ -51,6 +52,12 @@ _SIGNATURES = {
     "s4g_chain_set_params": ([_vp, _vp, _vp], _i),
     "s4g_chain_run_rows": ([_vp, _vp, _i, ctypes.c_longlong, _vp, _i, _vp], _i),
     "s4g_chain_run_gather": ([_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp], _i),
+    "s4g_grasp_scores_f32": ([_vp, _i, _i, _i, _vp, _vp], _i),
+    "s4g_grasp_select": ([_vp, _vp, _i, _i, _d, _d, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp], _i),
+    "s4g_grasp_poses": ([_vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp], _i),
+    "s4g_grasp_collision_f32": ([_vp, _i, _vp, _i, _vp, _vp, _vp, _vp], _i),
+    "s4g_grasp_nms": ([_vp, _vp, _i, _d, _vp, _vp, _vp], _i),
+    "s4g_grasp_importance_sample": ([_vp, _i, _vp, _i, _vp, _vp, _vp], _i),
 }
 
 for _name, (_args, _res) in _SIGNATURES.items():

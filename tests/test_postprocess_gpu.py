@@ -1,0 +1,136 @@
+"""GPU parity of the device-side grasp post-processing (csrc/postprocess.cu) against the CPU restatement of
+grasp_detector.py:124-251 / view_collision_checker.py:37-65 in oracle/model_cpu.py.
+
+Tolerances: scores 1e-6 absolute (fp32 softmax: device expf vs torch's differ by an ulp); selection / ranking /
+indexing is exact when the oracle is given the device's scores; poses 1e-5 (fp32 Gram-Schmidt, fp64 translation);
+collision point counts exact up to points lying within float rounding of a gripper plane (<= 2 per pose)."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _predictions(B, N, seed, peaked=True):
+    g = torch.Generator().manual_seed(seed)
+    score = torch.randn(B, 3, N, generator=g) * (2.0 if peaked else 0.3)
+    frame_R = torch.randn(B, 9, N, generator=g)
+    frame_t = torch.randn(B, 4, N, generator=g)
+    points = torch.rand(B, 3, N, generator=g) * 0.4 - 0.2
+    points[:, 2] -= 1.0
+    return points, {"score": score, "frame_R": frame_R, "frame_t": frame_t}
+
+
+@pytest.mark.parametrize("B,N,thr", [(1, 2000, 0.7), (3, 5000, 0.6), (2, 25600, 0.7), (1, 300, 0.99), (2, 1500, 0.0)])
+def test_scores_selection_poses(B, N, thr):
+    from oracle import model_cpu as ora
+    from s4g_release_b200.postprocess import GraspPostProcessor
+    points, pred = _predictions(B, N, seed=N)
+    post = GraspPostProcessor()
+    r = post.select_and_decode(points.cuda(), {k: v.cuda() for k, v in pred.items()}, thr, 0.2)
+    torch.cuda.synchronize()
+    for b in range(B):
+        want_scores = ora.grasp_scores(pred["score"][b])
+        got_scores = r["all_scores"][b].cpu().numpy()
+        np.testing.assert_allclose(got_scores, want_scores, atol=1e-6, rtol=0)
+        one = {k: v[b:b + 1] for k, v in pred.items()}
+        poses, scores, valid_index, rot_index = ora.post_processing(points[b].numpy(), one, thr, 0.2, all_scores=got_scores,
+                                                                    return_index=True)
+        n = int(r["n"][b])
+        assert n == poses.shape[0]
+        assert int(r["n_high"][b]) == int((got_scores > thr).sum())
+        # selection, ranking and the reference's two indexing quirks: exact
+        assert np.array_equal(r["point_index"][b, :n].cpu().numpy(), valid_index)
+        assert np.array_equal(r["rotation_index"][b, :n].cpu().numpy(), rot_index)
+        np.testing.assert_array_equal(r["scores"][b, :n].cpu().numpy(), scores)
+        if n:
+            np.testing.assert_allclose(r["poses"][b, :n].cpu().numpy(), poses, atol=1e-5, rtol=1e-5)
+
+
+def test_reference_signature_and_empty_result():
+    from oracle import model_cpu as ora
+    from s4g_release_b200.postprocess import GraspPostProcessor
+    points, pred = _predictions(1, 4000, seed=5)
+    post = GraspPostProcessor()
+    cuda_pred = {k: v.cuda() for k, v in pred.items()}
+    poses, scores = post.post_processing(points[0].numpy(), cuda_pred, 0.7, 0.2, debug=False)
+    want_p, want_s = ora.post_processing(points[0].numpy(), pred, 0.7, 0.2)
+    assert poses.shape[0] == want_p.shape[0] and poses.dtype == torch.float64
+    np.testing.assert_allclose(scores.cpu().numpy(), want_s, atol=1e-6)
+    np.testing.assert_allclose(poses.cpu().numpy(), want_p, atol=1e-5)
+    # nothing above the threshold -> empty, like the reference's empty index arrays
+    poses, scores = post.post_processing(points[0].numpy(), cuda_pred, 1.5, 0.2)
+    assert poses.shape == (0, 4, 4) and scores.shape == (0,)
+    with pytest.raises(RuntimeError):
+        post.scores(pred["score"])  # CPU tensor: no CPU path
+
+
+def test_candidate_capacity_grows():
+    from s4g_release_b200.postprocess import GraspPostProcessor
+    points, pred = _predictions(1, 3000, seed=9)
+    small = GraspPostProcessor(max_candidates=16)
+    big = GraspPostProcessor()
+    a = small.select_and_decode(points.cuda(), {k: v.cuda() for k, v in pred.items()}, 0.3, -1.0)
+    b = big.select_and_decode(points.cuda(), {k: v.cuda() for k, v in pred.items()}, 0.3, -1.0)
+    n = int(b["n"][0])
+    assert n > 16 and int(a["n"][0]) == n
+    assert torch.equal(a["point_index"][0, :n], b["point_index"][0, :n])
+
+
+def test_collision_check_matches_oracle():
+    from oracle import model_cpu as ora
+    from s4g_release_b200.postprocess import GraspPostProcessor
+    g = np.random.RandomState(3)
+    # a table plane + a box, grasps scattered around the box
+    plane = np.stack([g.uniform(-0.3, 0.3, 6000), g.uniform(-0.3, 0.3, 6000), np.full(6000, -1.0)], 1)
+    box = np.stack([g.uniform(-0.03, 0.03, 3000), g.uniform(-0.02, 0.02, 3000), g.uniform(-1.0, -0.9, 3000)], 1)
+    cloud = np.concatenate([plane, box]).astype(np.float32)
+    n = 200
+    poses = np.tile(np.eye(4), (n, 1, 1))
+    for i in range(n):
+        q, _ = np.linalg.qr(g.randn(3, 3))
+        q *= np.sign(np.linalg.det(q))
+        poses[i, :3, :3] = q
+        poses[i, :3, 3] = [g.uniform(-0.1, 0.1), g.uniform(-0.1, 0.1), g.uniform(-1.05, -0.8)]
+    post = GraspPostProcessor()
+    ok, counts = post.collision_free(torch.from_numpy(poses).cuda(), torch.from_numpy(cloud).cuda(), return_counts=True)
+    want_ok, want_counts = ora.collision_filter(poses, cloud)
+    got_counts = counts.cpu().numpy()
+    assert np.abs(got_counts - want_counts).max() <= 2, "point counts differ by more than float rounding at a plane"
+    exact = np.all(got_counts == want_counts, axis=1)
+    want_mask = np.zeros(n, dtype=bool)
+    want_mask[want_ok] = True
+    assert np.array_equal(ok.cpu().numpy()[exact], want_mask[exact])
+    assert 0 < want_mask.sum() < n, "fixture must contain both colliding and free grasps"
+
+
+def test_importance_sampling_and_nms():
+    from oracle import model_cpu as ora
+    from s4g_release_b200.postprocess import GraspPostProcessor
+    g = np.random.RandomState(11)
+    scores = g.uniform(0.7, 1.0, 500)
+    u = np.sort(g.rand(5))
+    post = GraspPostProcessor()
+    got = post.importance_sample(torch.from_numpy(scores).cuda(), u).cpu().numpy()
+    assert np.array_equal(got, ora.importance_sampling(scores, u))
+    poses = np.tile(np.eye(4), (500, 1, 1))
+    poses[:, :3, 3] = g.uniform(-0.1, 0.1, (500, 3))
+    poses[100, :3, 3] = poses[7, :3, 3] + 1e-4  # near-duplicates
+    for d in (0.0, 0.01, 0.05, 1.0):
+        got = post.nms(torch.from_numpy(poses).cuda(), torch.from_numpy(scores).cuda(), d).cpu().numpy()
+        assert np.array_equal(got, ora.translation_nms(poses, scores, d)), d
+
+
+def test_detect_batch_runs_end_to_end():
+    from s4g_release_b200.postprocess import GraspPostProcessor
+    points, pred = _predictions(4, 6000, seed=21)
+    post = GraspPostProcessor()
+    res = post.detect_batch(points.cuda(), {k: v.cuda() for k, v in pred.items()}, num_selected=5, score_threshold=0.6,
+                            nms_min_dist=0.01, rng=np.random.RandomState(0))
+    assert len(res) == 4
+    for poses, scores in res:
+        assert poses.shape[0] <= 5 and poses.shape[1:] == (4, 4) and scores.shape[0] == poses.shape[0]
+        if poses.shape[0]:
+            R = poses[:, :3, :3]
+            eye = torch.eye(3, dtype=torch.float64, device=R.device)
+            assert torch.allclose(R @ R.transpose(1, 2), eye.expand_as(R), atol=1e-5)
