@@ -32,7 +32,9 @@ namespace s4g {
 constexpr int kFpsThreads = 512;
 constexpr int kFpsWarps = kFpsThreads / 32;
 
-template <int P, int CLUSTER, typename IndexT>
+// SMEM_XYZ: clouds too large for the register file (N > 102 400) keep only the running distances in registers
+// and re-read the coordinates from the CTA's shared-memory copy every iteration (clusters of up to 16 CTAs).
+template <int P, int CLUSTER, bool SMEM_XYZ, typename IndexT>
 __global__ void __launch_bounds__(kFpsThreads, 1)
 fps_kernel(const float* __restrict__ points, int N, int M, int L, IndexT* __restrict__ index) {
   extern __shared__ float s_xyz[];  // [3][kFpsThreads * P]: this CTA's slice of the cloud
@@ -60,18 +62,18 @@ fps_kernel(const float* __restrict__ points, int N, int M, int L, IndexT* __rest
   // (for BLOCK = 512) a constant reduction slot, so "first strict maximum" inside the thread is
   // the reference's per-thread rule.
   const int chunk = rank * P;
-  float px[P], py[P], pz[P], dist[P];
+  constexpr int PR = SMEM_XYZ ? 1 : P;
+  float px[PR], py[PR], pz[PR], dist[P];
 #pragma unroll
   for (int p = 0; p < P; ++p) {
     const int j = t + kFpsThreads * (chunk + p);
     const bool valid = j < N;
-    px[p] = valid ? X[j] : 0.f;
-    py[p] = valid ? Y[j] : 0.f;
-    pz[p] = valid ? Z[j] : 0.f;
+    const float x = valid ? X[j] : 0.f, y = valid ? Y[j] : 0.f, z = valid ? Z[j] : 0.f;
+    if constexpr (!SMEM_XYZ) { px[p] = x; py[p] = y; pz[p] = z; }
     dist[p] = valid ? __int_as_float(0x7f800000) : 0.f;  // padding can never exceed a real point
-    sx[p * kFpsThreads + t] = px[p];
-    sy[p * kFpsThreads + t] = py[p];
-    sz[p * kFpsThreads + t] = pz[p];
+    sx[p * kFpsThreads + t] = x;
+    sy[p * kFpsThreads + t] = y;
+    sz[p * kFpsThreads + t] = z;
   }
   const unsigned bmask = (1u << L) - 1u;
   const unsigned lowmask = (L == 0) ? 0xffffffffu : ((1u << (32 - L)) - 1u);
@@ -89,7 +91,10 @@ fps_kernel(const float* __restrict__ points, int N, int M, int L, IndexT* __rest
     int bi = 0;
 #pragma unroll
     for (int p = 0; p < P; ++p) {
-      const float d = sqdist(__fsub_rn(px[p], cx), __fsub_rn(py[p], cy), __fsub_rn(pz[p], cz));
+      float x, y, z;
+      if constexpr (SMEM_XYZ) { x = sx[p * kFpsThreads + t]; y = sy[p * kFpsThreads + t]; z = sz[p * kFpsThreads + t]; }
+      else { x = px[p]; y = py[p]; z = pz[p]; }
+      const float d = sqdist(__fsub_rn(x, cx), __fsub_rn(y, cy), __fsub_rn(z, cz));
       const float dd = fminf(dist[p], d);
       dist[p] = dd;
       if (dd > best) { best = dd; bi = p; }
@@ -143,11 +148,12 @@ fps_kernel(const float* __restrict__ points, int N, int M, int L, IndexT* __rest
   }
 }
 
-template <int P, int CLUSTER, typename IndexT>
+template <int P, int CLUSTER, bool SMEM_XYZ, typename IndexT>
 static int launch_fps(const float* points, int B, int N, int M, int L, IndexT* index, cudaStream_t stream) {
-  auto kern = fps_kernel<P, CLUSTER, IndexT>;
+  auto kern = fps_kernel<P, CLUSTER, SMEM_XYZ, IndexT>;
   const size_t smem = (size_t)3 * kFpsThreads * P * sizeof(float);
   S4G_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  if (CLUSTER > 8) S4G_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)(B * CLUSTER));
   cfg.blockDim = dim3(kFpsThreads);
@@ -167,7 +173,7 @@ static int launch_fps(const float* points, int B, int N, int M, int L, IndexT* i
 template <int CLUSTER, typename IndexT>
 static int dispatch_p(int P, const float* points, int B, int N, int M, int L, IndexT* index, cudaStream_t stream) {
 #define S4G_FPS_CASE(PP) \
-  if (P <= PP) return launch_fps<PP, CLUSTER, IndexT>(points, B, N, M, L, index, stream);
+  if (P <= PP) return launch_fps<PP, CLUSTER, false, IndexT>(points, B, N, M, L, index, stream);
   S4G_FPS_CASE(1)
   S4G_FPS_CASE(2)
   S4G_FPS_CASE(4)
@@ -194,12 +200,18 @@ static int fps_entry(const float* points, int B, int N, int M, IndexT* index, cu
   int L = 0;
   while ((1 << L) < N && L < 9) ++L;
   if (L < 4) L = 4;
+  // clouds beyond the register-resident capacity (8 CTAs x 512 threads x 25 points): coordinates in shared memory,
+  // 32 running distances per thread, clusters of 8 or 16 CTAs (up to 262 144 points)
+  if (N > kFpsThreads * 8 * kFpsMaxP) {
+    constexpr int kBigP = 32;
+    if (N <= kFpsThreads * 8 * kBigP) return launch_fps<kBigP, 8, true, IndexT>(points, B, N, M, L, index, stream);
+    if (N <= kFpsThreads * 16 * kBigP) return launch_fps<kBigP, 16, true, IndexT>(points, B, N, M, L, index, stream);
+    return set_error(S4G_E_UNSUPPORTED, "farthest_point_sample: N=%d exceeds the on-chip capacity (%d points)", N,
+                     kFpsThreads * 16 * kBigP);
+  }
   // smallest cluster that holds the cloud in registers, then grow it while the GPU has idle SMs
   int cluster = 1;
   while (cluster < 8 && (N + kFpsThreads * cluster - 1) / (kFpsThreads * cluster) > kFpsMaxP) cluster *= 2;
-  if ((N + kFpsThreads * cluster - 1) / (kFpsThreads * cluster) > kFpsMaxP)
-    return set_error(S4G_E_UNSUPPORTED, "farthest_point_sample: N=%d exceeds the on-chip capacity (%d points)", N,
-                     kFpsThreads * 8 * kFpsMaxP);
   const int sms = num_sms();
   while (cluster < 8 && B * cluster * 2 <= sms && N > kFpsThreads * cluster) cluster *= 2;
   const int P = (N + kFpsThreads * cluster - 1) / (kFpsThreads * cluster);

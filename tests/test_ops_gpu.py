@@ -219,3 +219,14 @@ def test_autograd_wrappers_match_reference_behaviour(ext):
     out = F_.feature_interpolate(feat2, nn_idx, w)
     out.sum().backward()
     assert torch.allclose(feat2.grad.sum(), torch.tensor(6.0 * 2 * 400, device="cuda"), rtol=1e-4)
+
+
+@pytest.mark.parametrize("kind,B,N,M", [("uniform", 1, 131072, 96), ("uniform", 2, 110000, 64), ("uniform", 1, 262144, 64),
+                                        ("lattice", 1, 150000, 48), ("dup", 1, 200000, 40)])
+def test_fps_large_clouds_bit_exact(ext, ora, kind, B, N, M):
+    """BASELINE config 3 sizes (N up to 262 144): the shared-memory-coordinate variant on 8 / 16-CTA clusters."""
+    pts = _gen(kind, B, N, seed=N + M)
+    got = ext.farthest_point_sample(pts.cuda(), M)
+    assert torch.equal(got.cpu(), ora.farthest_point_sample(pts, M))
+    with pytest.raises(RuntimeError):
+        ext.farthest_point_sample(torch.zeros(1, 3, 262145, device="cuda"), 4)

@@ -142,3 +142,18 @@ def test_post_processing_invariants():
     RtR = np.einsum("nij,nik->njk", R, R)
     np.testing.assert_allclose(RtR, np.tile(np.eye(3), (R.shape[0], 1, 1)), atol=1e-5)
     assert np.allclose(poses[:, 3], [0, 0, 0, 1])
+
+
+def test_post_processing_pinned_to_reference_code():
+    """oracle/model_cpu.py vs outputs of the reference's OWN post_processing / view_non_collision / importance
+    sampling code (cut out of /root/reference and executed by tests/golden/make_postprocess_golden.py)."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "postprocess_ref.npz"))
+    preds = {k: torch.from_numpy(g[k]) for k in ("score", "frame_R", "frame_t")}
+    for tag in ("a", "b"):
+        thr, vthr = g[f"post_{tag}/thr"]
+        poses, scores = model_cpu.post_processing(g["points"], preds, float(thr), float(vthr))
+        assert np.array_equal(poses, g[f"post_{tag}/poses"]) and np.array_equal(scores, g[f"post_{tag}/scores"])
+    ok, _ = model_cpu.collision_filter(g["coll/poses"], g["coll/cloud"])
+    assert np.array_equal(ok, np.nonzero(g["coll/ok"])[0])
+    assert np.array_equal(model_cpu.importance_sampling(g["samp/scores"], g["samp/u"]), g["samp/picked"])

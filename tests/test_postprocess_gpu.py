@@ -134,3 +134,23 @@ def test_detect_batch_runs_end_to_end():
             R = poses[:, :3, :3]
             eye = torch.eye(3, dtype=torch.float64, device=R.device)
             assert torch.allclose(R @ R.transpose(1, 2), eye.expand_as(R), atol=1e-5)
+
+
+def test_against_reference_golden():
+    """Device path vs the outputs of the reference's own code (tests/golden/postprocess_ref.npz)."""
+    import os
+    from s4g_release_b200.postprocess import GraspPostProcessor
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "postprocess_ref.npz"))
+    preds = {k: torch.from_numpy(g[k]).cuda() for k in ("score", "frame_R", "frame_t")}
+    post = GraspPostProcessor()
+    for tag in ("a", "b"):
+        thr, vthr = g[f"post_{tag}/thr"]
+        poses, scores = post.post_processing(g["points"], preds, float(thr), float(vthr))
+        want_p, want_s = g[f"post_{tag}/poses"], g[f"post_{tag}/scores"]
+        assert poses.shape[0] == want_p.shape[0], "selection differs from the reference (a score within 1e-7 of a threshold?)"
+        np.testing.assert_allclose(scores.cpu().numpy(), want_s, atol=1e-6)
+        np.testing.assert_allclose(poses.cpu().numpy(), want_p, atol=1e-5)
+    ok = post.collision_free(torch.from_numpy(g["coll/poses"]).cuda(), torch.from_numpy(g["coll/cloud"]).cuda())
+    assert np.array_equal(ok.cpu().numpy(), g["coll/ok"])
+    picked = post.importance_sample(torch.from_numpy(g["samp/scores"]).cuda(), g["samp/u"])
+    assert np.array_equal(picked.cpu().numpy(), g["samp/picked"])
