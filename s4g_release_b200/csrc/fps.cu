@@ -29,6 +29,38 @@ namespace cg = cooperative_groups;
 
 namespace s4g {
 
+__device__ __forceinline__ unsigned fps_smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void fps_mbar_init(unsigned long long* bar) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(fps_smem_u32(bar)));
+}
+__device__ __forceinline__ void fps_mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(fps_smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void fps_mbar_wait(unsigned long long* bar, unsigned parity) {
+  unsigned ok = 0, spins = 0;
+  while (!ok) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok) : "r"(fps_smem_u32(bar)), "r"(parity) : "memory");
+    if (!ok && ++spins > (1u << 24)) __trap();  // a protocol bug traps instead of hanging the GPU
+  }
+}
+__device__ __forceinline__ unsigned fps_mapa(unsigned addr, int rank) {
+  unsigned r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void fps_st_async_v4(unsigned raddr, uint4 v, unsigned rbar) {
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.b32 [%0], {%1, %2, %3, %4}, [%5];" ::"r"(raddr),
+               "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w), "r"(rbar) : "memory");
+}
+__device__ __forceinline__ void fps_st_async_b32(unsigned raddr, unsigned v, unsigned rbar) {
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b32 [%0], %1, [%2];" ::"r"(raddr), "r"(v), "r"(rbar)
+               : "memory");
+}
+
 constexpr int kFpsThreads = 512;
 constexpr int kFpsWarps = kFpsThreads / 32;
 
@@ -40,8 +72,9 @@ fps_kernel(const float* __restrict__ points, int N, int M, int L, IndexT* __rest
   extern __shared__ float s_xyz[];  // [3][kFpsThreads * P]: this CTA's slice of the cloud
   constexpr int kLocal = kFpsThreads * P;
   constexpr int kEntries = kFpsWarps * CLUSTER;
-  __shared__ uint2 s_key[2][kEntries];   // (distance bits, tie-break key) per warp of the cluster
-  __shared__ float4 s_pos[2][kEntries];  // coordinates of that warp's candidate
+  // one 32-byte record per warp of the cluster and iteration parity: {distance bits, tie-break key, x, y | z}
+  __shared__ __align__(16) uint4 s_rec[2][kEntries][2];
+  __shared__ __align__(8) unsigned long long s_bar[2];  // clusters: records of parity b have all landed
 
   const int t = threadIdx.x;
   const int lane = t & 31;
@@ -62,6 +95,8 @@ fps_kernel(const float* __restrict__ points, int N, int M, int L, IndexT* __rest
   // (for BLOCK = 512) a constant reduction slot, so "first strict maximum" inside the thread is
   // the reference's per-thread rule.
   const int chunk = rank * P;
+  // (a packed fp32x2 distance update — FADD2 / FMUL2 / FFMA2 — was measured and is bit-exact but not faster: the
+  // packed instructions issue at half rate, so the scalar form is kept)
   constexpr int PR = SMEM_XYZ ? 1 : P;
   float px[PR], py[PR], pz[PR], dist[P];
 #pragma unroll
@@ -82,8 +117,16 @@ fps_kernel(const float* __restrict__ points, int N, int M, int L, IndexT* __rest
   float cx = X[0], cy = Y[0], cz = Z[0];
   if (rank == 0 && t == 0) out[0] = 0;
 
-  if constexpr (CLUSTER > 1) cg::this_cluster().sync();  // peers are resident before any DSMEM store
-  else __syncthreads();
+  if constexpr (CLUSTER > 1) {
+    if (t == 0) {
+      fps_mbar_init(&s_bar[0]);
+      fps_mbar_init(&s_bar[1]);
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    cg::this_cluster().sync();  // peers are resident and their barriers initialised before any remote store
+  } else {
+    __syncthreads();
+  }
 
   for (int i = 1; i < M; ++i) {
     const int buf = i & 1;
@@ -105,33 +148,41 @@ fps_kernel(const float* __restrict__ points, int N, int M, int L, IndexT* __rest
     const unsigned j = (unsigned)(t + kFpsThreads * (chunk + bi));
     const unsigned tb = (db == wmax) ? (__brev(j & bmask) | (j >> L)) : 0xffffffffu;
     const unsigned wtb = __reduce_min_sync(0xffffffffu, tb);
+    constexpr unsigned kRecBytes = 20;  // 16-byte + 4-byte remote store per record
+    if constexpr (CLUSTER > 1) {
+      // arm this parity's barrier for the kEntries records of this iteration (a record that lands first just
+      // makes the transaction count negative for a moment: the phase cannot complete before this arrival)
+      if (t == 0) fps_mbar_expect_tx(&s_bar[buf], kEntries * kRecBytes);
+    }
     if (tb == wtb) {  // exactly one lane: keys are distinct per point
       const int lp = bi * kFpsThreads + t;
-      const uint2 key = make_uint2(wmax, wtb);
-      const float4 pos = make_float4(sx[lp], sy[lp], sz[lp], 0.f);
       const int e = rank * kFpsWarps + warp;
+      const uint4 lo = make_uint4(wmax, wtb, __float_as_uint(sx[lp]), __float_as_uint(sy[lp]));
+      const unsigned zb = __float_as_uint(sz[lp]);
       if constexpr (CLUSTER > 1) {
-        cg::cluster_group cluster = cg::this_cluster();
+        // push the record into every CTA of the cluster; each store signals the destination's barrier, so
+        // nobody waits for a cluster-wide barrier (no barrier.cluster, no L1 flush): DSMEM latency only
+        const unsigned rec = fps_smem_u32(&s_rec[buf][e][0]);
+        const unsigned bar = fps_smem_u32(&s_bar[buf]);
 #pragma unroll
         for (int q = 0; q < CLUSTER; ++q) {
-          uint2* rk = cluster.map_shared_rank(&s_key[buf][e], q);
-          float4* rp = cluster.map_shared_rank(&s_pos[buf][e], q);
-          *rk = key;
-          *rp = pos;
+          const unsigned rrec = fps_mapa(rec, q), rbar = fps_mapa(bar, q);
+          fps_st_async_v4(rrec, lo, rbar);
+          fps_st_async_b32(rrec + 16, zb, rbar);
         }
       } else {
-        s_key[buf][e] = key;
-        s_pos[buf][e] = pos;
+        s_rec[buf][e][0] = lo;
+        s_rec[buf][e][1] = make_uint4(zb, 0u, 0u, 0u);
       }
     }
-    if constexpr (CLUSTER > 1) cg::this_cluster().sync();
+    if constexpr (CLUSTER > 1) fps_mbar_wait(&s_bar[buf], (unsigned)((i - 1) >> 1) & 1u);  // ((i-1)/2)-th use of this parity
     else __syncthreads();
     // ---- every warp reduces the cluster's records redundantly ----
     unsigned d = 0u, k = 0xffffffffu;
     int e = 0;
 #pragma unroll
     for (int q = lane; q < kEntries; q += 32) {
-      const uint2 kv = s_key[buf][q];
+      const uint2 kv = *reinterpret_cast<const uint2*>(&s_rec[buf][q][0]);
       if (kv.x > d || (kv.x == d && kv.y < k)) { d = kv.x; k = kv.y; e = q; }
     }
     const unsigned gmax = __reduce_max_sync(0xffffffffu, d);
@@ -140,12 +191,13 @@ fps_kernel(const float* __restrict__ points, int N, int M, int L, IndexT* __rest
     const int src = __ffs(who) - 1;
     const int ge = __shfl_sync(0xffffffffu, e, src);
     if (gmax != 0u) {  // all remaining distances 0 -> the reference repeats the previous index
-      const float4 pos = s_pos[buf][ge];
-      cx = pos.x; cy = pos.y; cz = pos.z;
+      const uint4 lo = s_rec[buf][ge][0];
+      cx = __uint_as_float(lo.z); cy = __uint_as_float(lo.w); cz = __uint_as_float(s_rec[buf][ge][1].x);
       cur = (int)(__brev(gk & ~lowmask) + ((gk & lowmask) << L));
     }
     if (rank == 0 && t == 0) out[i] = (IndexT)cur;
   }
+  if constexpr (CLUSTER > 1) cg::this_cluster().sync();  // no CTA exits while a peer may still read or write it
 }
 
 template <int P, int CLUSTER, bool SMEM_XYZ, typename IndexT>
