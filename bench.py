@@ -203,6 +203,33 @@ def run_reference(args, rank, world):
     print(json.dumps(line), flush=True)
 
 
+TRAFFIC_FILE = "profiles/r01/ncu_launches_v5.json"
+
+
+def stage_traffic():
+    """DRAM bytes (read + write) per step of every stage, from the committed ncu launch list of one forward at this
+    workload (dram__bytes_read.sum + dram__bytes_write.sum per launch, summed over the stage's launches)."""
+    try:
+        launches = json.load(open(os.path.join(ROOT, TRAFFIC_FILE)))["launches"]
+    except Exception:
+        return {}
+    byts = lambda l: (l["dram_read_MB"] + l["dram_write_MB"]) * 1e6
+    fps = [l for l in launches if "fps_kernel" in l["kernel"]]
+    chains = [l for l in launches if "mlp_chain" in l["kernel"]]
+    interp = [l for l in launches if "interp_concat" in l["kernel"]]
+    out = {}
+    if len(fps) == 3 and len(chains) == 11 and len(interp) == 3:
+        for i in range(3):
+            out["sa%d.fps" % i] = byts(fps[i])
+            out["sa%d.mlp" % i] = byts(chains[i])
+            out["fp%d.interp_concat" % i] = byts(interp[i])
+        out["fp0.mlp"] = byts(chains[3]) + byts(chains[4])
+        out["fp1.mlp"] = byts(chains[5])
+        out["fp2.mlp"] = byts(chains[6])
+        out["heads.mlp"] = sum(byts(c) for c in chains[7:11])
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -253,7 +280,7 @@ def main():
     for _ in range(args.warmup):
         eng.forward(scenes)
     sync_all()
-    launches0 = _lib.launches
+    launches0 = _lib.lib.s4g_launch_count()
     timers, step_events = [], []
     if True:
         sync_all()
@@ -269,7 +296,7 @@ def main():
             step_events.append((a, b))
         sync_all()
         clocks.window(t_w0, time.time())
-    launches = (_lib.launches - launches0) // args.steps
+    launches = (_lib.lib.s4g_launch_count() - launches0) // args.steps  # kernels launched by libs4g_b200.so
     step_ms = [a.elapsed_time(b) for a, b in step_events]
     ms_local = sum(step_ms) / len(step_ms)
 
@@ -324,10 +351,15 @@ def main():
                 ach, peak, unit = work / (avg * 1e-3) / 1e12, peaks["bf16_tflops"], "TFLOP/s"
             kernels[name] = {"ms": round(avg, 4), "share": round(avg / ms_local, 4), "bound": bound,
                              "achieved": round(ach, 2), "peak": peak, "unit": unit, "frac": round(ach / peak, 4)}
+        traffic = stage_traffic()
+        for name, t in traffic.items():
+            if name in kernels:
+                kernels[name]["dram_bytes"] = t
         top = max(kernels, key=lambda k: kernels[k]["ms"])
         roof = {"kernel": top, "bound": kernels[top]["bound"], "achieved": kernels[top]["achieved"],
                 "peak": kernels[top]["peak"], "unit": kernels[top]["unit"], "frac": kernels[top]["frac"],
-                "traffic": None, "peak_source": peaks["source"] + (" — sustained bf16 (kernel timed inside the step)"
+                "traffic": traffic.get(top), "traffic_source": TRAFFIC_FILE if traffic.get(top) is not None else None,
+                "peak_source": peaks["source"] + (" — sustained bf16 (kernel timed inside the step)"
                                                                    if kernels[top]["bound"] == "tensor" else "")}
         total_flops = sum(w for b, w in model.values() if b == "tensor")
         line = {

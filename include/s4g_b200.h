@@ -35,6 +35,8 @@ extern "C" {
 int s4g_version(void);
 /* Text of the last error raised on the calling thread ("" if none). */
 const char* s4g_last_error(void);
+/* number of CUDA kernels this library has launched in the process so far (bench.py reports the per-step delta) */
+unsigned long long s4g_launch_count(void);
 
 /* ---- pn2_ext replacements --------------------------------------------------------------- */
 

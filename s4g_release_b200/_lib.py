@@ -28,6 +28,7 @@ _ip = ctypes.POINTER(ctypes.c_int)
 _SIGNATURES = {
     "s4g_version": ([], _i),
     "s4g_last_error": ([], ctypes.c_char_p),
+    "s4g_launch_count": ([], ctypes.c_ulonglong),
     "s4g_farthest_point_sample_f32": ([_vp, _i, _i, _i, _vp, _vp], _i),
     "s4g_farthest_point_sample_f32_i32": ([_vp, _i, _i, _i, _vp, _vp], _i),
     "s4g_gather_points_f32": ([_vp, _vp, _i, _i, _i, _i, _vp, _vp], _i),

@@ -19,7 +19,11 @@ int set_error(int code, const char* fmt, ...) {
   return code;
 }
 
+static unsigned long long g_launches = 0;
+void count_launch() { __atomic_fetch_add(&g_launches, 1ull, __ATOMIC_RELAXED); }
+
 }  // namespace s4g
 
 extern "C" int s4g_version(void) { return 1; }
+extern "C" unsigned long long s4g_launch_count(void) { return __atomic_load_n(&s4g::g_launches, __ATOMIC_RELAXED); }
 extern "C" const char* s4g_last_error(void) { return s4g::error_buffer(); }

@@ -23,8 +23,12 @@ int set_error(int code, const char* fmt, ...);
     if (_e != cudaSuccess) return s4g::set_error((int)_e, "%s: %s", #expr, cudaGetErrorString(_e)); \
   } while (0)
 
+// every kernel launch of the library passes here: s4g_launch_count() lets a caller report how many of OUR kernels ran
+void count_launch();
+
 #define S4G_LAUNCH_CHECK(name)                                                                 \
   do {                                                                                         \
+    s4g::count_launch();                                                                       \
     cudaError_t _e = cudaGetLastError();                                                       \
     if (_e != cudaSuccess) return s4g::set_error((int)_e, "%s launch: %s", name, cudaGetErrorString(_e)); \
   } while (0)

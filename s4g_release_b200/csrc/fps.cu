@@ -219,6 +219,7 @@ static int launch_fps(const float* points, int B, int N, int M, int L, IndexT* i
   cfg.attrs = attr;
   cfg.numAttrs = 1;
   S4G_CUDA(cudaLaunchKernelEx(&cfg, kern, points, N, M, L, index));
+  count_launch();
   return S4G_OK;
 }
 

@@ -1,5 +1,4 @@
 // Grid build + grid-accelerated ball query and 3-NN (see grid.cuh for the exactness argument).
-#include <cub/device/device_scan.cuh>
 
 #include "grid.cuh"
 
@@ -103,10 +102,86 @@ grid_scatter_kernel(const float* __restrict__ points, int N, const GridDesc* __r
 
 static size_t align_up(size_t x) { return (x + 255) & ~(size_t)255; }
 
+// ---- exclusive prefix sum of the cell counts (hand-written: no library kernel on the path) ----
+// scan_block_kernel: each block scans kScanTile consecutive items (4 per thread) and writes its total;
+// scan_sums_kernel: one block scans the block totals; scan_add_kernel adds them back.
+constexpr int kScanThreads = 1024;
+constexpr int kScanTile = kScanThreads * 4;
+
+__device__ __forceinline__ int scan_block_exclusive(int v, int* s_warp, int& total) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  int incl = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int t = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += t;
+  }
+  if (lane == 31) s_warp[warp] = incl;
+  __syncthreads();
+  if (warp == 0) {
+    const int w = s_warp[lane];
+    int wi = w;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int t = __shfl_up_sync(0xffffffffu, wi, o);
+      if (lane >= o) wi += t;
+    }
+    s_warp[lane] = wi - w;
+    if (lane == 31) s_warp[32] = wi;
+  }
+  __syncthreads();
+  total = s_warp[32];
+  const int res = s_warp[warp] + incl - v;
+  __syncthreads();
+  return res;
+}
+
+__global__ void __launch_bounds__(kScanThreads) scan_block_kernel(const int* __restrict__ in, int n, int* __restrict__ out,
+                                                                  int* __restrict__ sums) {
+  __shared__ int s_warp[33];
+  const int base = blockIdx.x * kScanTile + threadIdx.x * 4;
+  int v[4], t = 0;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    v[k] = base + k < n ? in[base + k] : 0;
+    t += v[k];
+  }
+  int total;
+  int run = scan_block_exclusive(t, s_warp, total);
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    if (base + k < n) out[base + k] = run;
+    run += v[k];
+  }
+  if (threadIdx.x == 0) sums[blockIdx.x] = total;
+}
+
+__global__ void __launch_bounds__(kScanThreads) scan_sums_kernel(int* __restrict__ sums, int n) {
+  __shared__ int s_warp[33];
+  int carry = 0;
+  for (int base = 0; base < n; base += kScanThreads) {
+    const int i = base + threadIdx.x;
+    const int v = i < n ? sums[i] : 0;
+    int total;
+    const int ex = scan_block_exclusive(v, s_warp, total);
+    if (i < n) sums[i] = carry + ex;
+    carry += total;
+  }
+}
+
+__global__ void __launch_bounds__(kScanThreads) scan_add_kernel(int* __restrict__ out, int n, const int* __restrict__ sums) {
+  const int add = sums[blockIdx.x];
+  const int base = blockIdx.x * kScanTile + threadIdx.x * 4;
+#pragma unroll
+  for (int k = 0; k < 4; ++k)
+    if (base + k < n) out[base + k] += add;
+}
+
 int grid_build(const float* points, int B, int N, int mode, float radius, Grid* g, cudaStream_t stream) {
   const size_t cells = (size_t)B * kGridCells;
-  size_t scan_tmp = 0;
-  S4G_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, scan_tmp, (int*)nullptr, (int*)nullptr, (int)cells + 1, stream));
+  const int scan_n = (int)cells + 1;
+  const int scan_blocks = (scan_n + kScanTile - 1) / kScanTile;
+  const size_t scan_tmp = sizeof(int) * (size_t)scan_blocks;
   const size_t o_desc = 0;
   const size_t o_count = o_desc + align_up(sizeof(GridDesc) * B);
   const size_t o_cursor = o_count + align_up(sizeof(int) * (cells + 1));
@@ -137,11 +212,21 @@ int grid_build(const float* points, int B, int N, int mode, float radius, Grid* 
   // count and cursor are adjacent: one memset clears both
   S4G_CUDA(cudaMemsetAsync(count, 0, o_start - o_count, stream));
   grid_desc_kernel<<<B, 256, 0, stream>>>(points, N, mode, radius, g->desc);
+  S4G_LAUNCH_CHECK("grid_desc");
   dim3 grid((N + 255) / 256, B);
   grid_count_kernel<<<grid, 256, 0, stream>>>(points, N, g->desc, count);
-  S4G_CUDA(cub::DeviceScan::ExclusiveSum(arena + o_tmp, scan_tmp, count, g->start, (int)cells + 1, stream));
+  S4G_LAUNCH_CHECK("grid_count");
+  int* sums = reinterpret_cast<int*>(arena + o_tmp);
+  scan_block_kernel<<<scan_blocks, kScanThreads, 0, stream>>>(count, scan_n, g->start, sums);
+  S4G_LAUNCH_CHECK("grid_scan");
+  if (scan_blocks > 1) {
+    scan_sums_kernel<<<1, kScanThreads, 0, stream>>>(sums, scan_blocks);
+    S4G_LAUNCH_CHECK("grid_scan_sums");
+    scan_add_kernel<<<scan_blocks, kScanThreads, 0, stream>>>(g->start, scan_n, sums);
+    S4G_LAUNCH_CHECK("grid_scan_add");
+  }
   grid_scatter_kernel<<<grid, 256, 0, stream>>>(points, N, g->desc, g->start, cursor, g->sorted);
-  S4G_LAUNCH_CHECK("grid_build");
+  S4G_LAUNCH_CHECK("grid_scatter");
   return S4G_OK;
 }
 
@@ -402,6 +487,7 @@ int three_nn_grid(const float* query, const float* key, int B, int Nq, int Nk, v
   dim3 grid((Nq + 255) / 256, B);
   three_nn_grid_kernel<MODE><<<grid, 256, 0, stream>>>(query, Nq, g.desc, g.start, g.sorted, index, out, pending,
                                                        n_pending);
+  S4G_LAUNCH_CHECK("three_nn_grid");
   three_nn_pending_kernel<MODE><<<num_sms() * 4, 256, 0, stream>>>(query, key, Nq, Nk, pending, n_pending, index, out);
   S4G_LAUNCH_CHECK("three_nn_grid");
   S4G_CUDA(cudaFreeAsync(pending, stream));
