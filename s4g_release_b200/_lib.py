@@ -9,7 +9,7 @@ import os
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libs4g_b200.so")
+LIB_PATH = os.environ.get("S4G_LIB_PATH") or os.path.join(_HERE, "libs4g_b200.so")  # override: A/B measurements only
 
 if not os.path.exists(LIB_PATH):
     raise ImportError(

@@ -147,6 +147,10 @@ bool build_draft(const s4g_chain* ch, const int* relu, int feat_c, int S, bool p
     same = b >= S ? 1 : 0;
     min_it = same ? 0 : (S - b + nB - 1) / nB;
   };
+  // The one-bit barrier phase makes "wait for the release of block pred in the previous tile" ambiguous when
+  // that block of the CURRENT tile can already be dead, i.e. when pred < b for an epilogue-produced block,
+  // which needs more slots than blocks per tile.  Chains with hidden layers therefore keep S <= blocks per tile.
+  if (!d.epi.empty() && d.epi[0].kind == WK_EPI_HIDDEN && S > nB) return false;
   for (HLoad& l : d.loads) pred_of(l.blk, l.pred, l.same, l.min_it);
   for (HEpi& e : d.epi)
     if (e.kind == WK_EPI_HIDDEN) pred_of(e.blk, e.pred, e.same, e.min_it);

@@ -163,8 +163,9 @@ __device__ __forceinline__ bool elect_one() {
 // (a + bias) -> bf16x2, ReLU applied on the packed pair (max commutes with the monotonic rounding)
 __device__ __forceinline__ uint32_t bias_act_pack(float a, float b, float ba, float bb, bool relu) {
   __nv_bfloat162 h = __floats2bfloat162_rn(a + ba, b + bb);
-  if (relu) h = __hmax2(h, __floats2bfloat162_rn(0.f, 0.f));
-  return *reinterpret_cast<uint32_t*>(&h);
+  uint32_t r = *reinterpret_cast<uint32_t*>(&h);
+  if (relu) asm("max.bf16x2 %0, %1, %2;" : "=r"(r) : "r"(r), "r"(0u));  // packed zero is the zero register
+  return r;
 }
 
 // 8 accumulator columns -> one 16-byte piece
