@@ -79,6 +79,29 @@ int s4g_interpolate_forward_f32(const float* input, const int64_t* index, const 
 int s4g_interpolate_backward_f32(const float* grad_out, const int64_t* index, const float* weight, int B, int C,
                                  int Nk, int Nq, float* grad_in, void* stream);
 
+/* ---- fp64 instantiation of the same seven operators ---------------------------------------
+ * The reference dispatches each kernel over float and double (AT_DISPATCH_FLOATING_TYPES:
+ * sampling_kernel.cu:21, ball_query_kernel.cu:116, grouping_kernel.cu:137, interpolate_kernel.cu:118,222,327).
+ * Same contracts as the _f32 entry points with double data; `radius` is the reference's float argument
+ * converted to double by the caller (ball_query_kernel.cu:119).  farthest_point_sample_f64 keeps its running
+ * minima in shared memory when a cloud fits and otherwise needs
+ * s4g_farthest_point_sample_f64_workspace(B, N) bytes of device scratch (0 = none). */
+size_t s4g_farthest_point_sample_f64_workspace(int B, int N);
+int s4g_farthest_point_sample_f64(const double* points, int B, int N, int M, int64_t* index, void* workspace,
+                                  size_t workspace_bytes, void* stream);
+int s4g_ball_query_f64(const double* points, const double* centroids, int B, int N, int M, double radius, int K,
+                       int64_t* index, int64_t* count, void* stream);
+int s4g_group_points_forward_f64(const double* input, const int64_t* index, int B, int C, int N, int M, int K,
+                                 double* out, void* stream);
+int s4g_group_points_backward_f64(const double* grad_out, const int64_t* index, int B, int C, int N, int M, int K,
+                                  double* grad_in, void* stream);
+int s4g_point_search_f64(const double* query, const double* key, int B, int Nq, int Nk, int num_neighbours,
+                         int64_t* index, double* distance, void* stream);
+int s4g_interpolate_forward_f64(const double* input, const int64_t* index, const double* weight, int B, int C, int Nk,
+                                int Nq, double* out, void* stream);
+int s4g_interpolate_backward_f64(const double* grad_out, const int64_t* index, const double* weight, int B, int C,
+                                 int Nk, int Nq, double* grad_in, void* stream);
+
 /* ---- fused inference path (channel-last bf16 features, int32 indices) ---------------------- */
 
 /* PointSearch (interpolate_kernel.cu:33-81) fused with the inverse-squared-distance weights of

@@ -48,7 +48,12 @@ def num_threads():
 
 
 def _fp(t):
-    return ctypes.cast(t.data_ptr(), _f32p)
+    return ctypes.cast(t.data_ptr(), ctypes.c_void_p)
+
+
+def _fn(name, t):
+    """the fp32 or fp64 instantiation (the reference dispatches both: AT_DISPATCH_FLOATING_TYPES)"""
+    return getattr(lib(), name + ("_f64" if t.dtype == torch.float64 else ""))
 
 
 def _ip(t):
@@ -58,8 +63,8 @@ def _ip(t):
 def _f32(t, name):
     if t.is_cuda:
         raise RuntimeError(f"{name}: the oracle runs on CPU tensors")
-    if t.dtype != torch.float32:
-        raise RuntimeError(f"{name} must be float32 in the oracle")
+    if t.dtype not in (torch.float32, torch.float64):
+        raise RuntimeError(f"{name} must be float32 or float64 in the oracle")
     return t.contiguous()
 
 
@@ -77,7 +82,7 @@ def farthest_point_sample(points, num_centroids, keyed=False):
     _check(M > 0, "num_centroids <= 0")
     _check(N >= M, "num_points < num_centroids")
     index = torch.zeros(B, M, dtype=torch.int64)
-    fn = lib().pn2o_farthest_point_sample_keyed if keyed else lib().pn2o_farthest_point_sample
+    fn = _fn("pn2o_farthest_point_sample_keyed" if keyed else "pn2o_farthest_point_sample", points)
     fn(_fp(points), _i64(B), _i64(N), _i64(M), _ip(index))
     return index
 
@@ -93,8 +98,10 @@ def ball_query(points, centroids, radius, num_neighbours):
     K = int(num_neighbours)
     index = torch.zeros(B, M, K, dtype=torch.int64)
     count = torch.zeros(B, M, dtype=torch.int64)
-    lib().pn2o_ball_query(_fp(points), _fp(centroids), _i64(B), _i64(N), _i64(M),
-                          ctypes.c_float(radius), _i64(K), _ip(index), _ip(count))
+    # the reference passes its `const float radius` converted to scalar_t (ball_query_kernel.cu:116-127)
+    r = ctypes.c_double(ctypes.c_float(radius).value) if points.dtype == torch.float64 else ctypes.c_float(radius)
+    _fn("pn2o_ball_query", points)(_fp(points), _fp(centroids), _i64(B), _i64(N), _i64(M), r, _i64(K), _ip(index),
+                                   _ip(count))
     return [index, count]
 
 
@@ -107,8 +114,8 @@ def group_points_forward(input, index):
     _check(index.size(0) == input.size(0), "index.size(0) != batch_size")
     B, C, N = input.shape
     _, M, K = index.shape
-    out = torch.empty(B, C, M, K, dtype=torch.float32)
-    lib().pn2o_group_points_forward(_fp(input), _ip(index), _i64(B), _i64(C), _i64(N), _i64(M), _i64(K), _fp(out))
+    out = torch.empty(B, C, M, K, dtype=input.dtype)
+    _fn("pn2o_group_points_forward", input)(_fp(input), _ip(index), _i64(B), _i64(C), _i64(N), _i64(M), _i64(K), _fp(out))
     return out
 
 
@@ -119,8 +126,8 @@ def group_points_backward(grad_output, index, num_points):
     _check(grad_output.dim() == 4, "grad_output.dim() != 4")
     B, C, M, K = grad_output.shape
     _check(tuple(index.shape) == (B, M, K), "index shape mismatch")
-    grad_in = torch.empty(B, C, int(num_points), dtype=torch.float32)
-    lib().pn2o_group_points_backward(_fp(grad_output), _ip(index), _i64(B), _i64(C), _i64(num_points),
+    grad_in = torch.empty(B, C, int(num_points), dtype=grad_output.dtype)
+    _fn("pn2o_group_points_backward", grad_output)(_fp(grad_output), _ip(index), _i64(B), _i64(C), _i64(num_points),
                                      _i64(M), _i64(K), _fp(grad_in))
     return grad_in
 
@@ -136,8 +143,8 @@ def point_search(query_xyz, key_xyz, num_neighbours):
     _check(int(num_neighbours) == 3, "num_neighbours != K")
     _check(Nk >= 3, "num_key < num_neighbours")
     index = torch.zeros(B, Nq, 3, dtype=torch.int64)
-    dist = torch.zeros(B, Nq, 3, dtype=torch.float32)
-    lib().pn2o_point_search(_fp(query_xyz), _fp(key_xyz), _i64(B), _i64(Nq), _i64(Nk), _ip(index), _fp(dist))
+    dist = torch.zeros(B, Nq, 3, dtype=query_xyz.dtype)
+    _fn("pn2o_point_search", query_xyz)(_fp(query_xyz), _fp(key_xyz), _i64(B), _i64(Nq), _i64(Nk), _ip(index), _fp(dist))
     return [index, dist]
 
 
@@ -150,8 +157,8 @@ def interpolate_forward(input, index, weight):
     Nq = index.size(1)
     _check(index.size(0) == B and index.size(2) == 3, "index shape mismatch")
     _check(tuple(weight.shape) == (B, Nq, 3), "weight shape mismatch")
-    out = torch.empty(B, C, Nq, dtype=torch.float32)
-    lib().pn2o_interpolate_forward(_fp(input), _ip(index), _fp(weight), _i64(B), _i64(C), _i64(Nk), _i64(Nq), _fp(out))
+    out = torch.empty(B, C, Nq, dtype=input.dtype)
+    _fn("pn2o_interpolate_forward", input)(_fp(input), _ip(index), _fp(weight), _i64(B), _i64(C), _i64(Nk), _i64(Nq), _fp(out))
     return out
 
 
@@ -163,8 +170,8 @@ def interpolate_backward(grad_output, index, weight, num_inst):
     B, C, Nq = grad_output.shape
     _check(index.size(0) == B and index.size(2) == 3, "index shape mismatch")
     _check(tuple(weight.shape) == (B, Nq, 3), "weight shape mismatch")
-    grad_in = torch.empty(B, C, int(num_inst), dtype=torch.float32)
-    lib().pn2o_interpolate_backward(_fp(grad_output), _ip(index), _fp(weight), _i64(B), _i64(C), _i64(num_inst),
+    grad_in = torch.empty(B, C, int(num_inst), dtype=grad_output.dtype)
+    _fn("pn2o_interpolate_backward", grad_output)(_fp(grad_output), _ip(index), _fp(weight), _i64(B), _i64(C), _i64(num_inst),
                                     _i64(Nq), _fp(grad_in))
     return grad_in
 
@@ -175,6 +182,6 @@ def gather_points(points, index):
     index = index.contiguous()
     B, C, N = points.shape
     M = index.size(1)
-    out = torch.empty(B, C, M, dtype=torch.float32)
-    lib().pn2o_gather_points(_fp(points), _ip(index), _i64(B), _i64(C), _i64(N), _i64(M), _fp(out))
+    out = torch.empty(B, C, M, dtype=points.dtype)
+    _fn("pn2o_gather_points", points)(_fp(points), _ip(index), _i64(B), _i64(C), _i64(N), _i64(M), _fp(out))
     return out

@@ -39,6 +39,14 @@ _SIGNATURES = {
     "s4g_point_search_f32": ([_vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp], _i),
     "s4g_interpolate_forward_f32": ([_vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp], _i),
     "s4g_interpolate_backward_f32": ([_vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp], _i),
+    "s4g_farthest_point_sample_f64_workspace": ([_i, _i], ctypes.c_size_t),
+    "s4g_farthest_point_sample_f64": ([_vp, _i, _i, _i, _vp, _vp, ctypes.c_size_t, _vp], _i),
+    "s4g_ball_query_f64": ([_vp, _vp, _i, _i, _i, _d, _i, _vp, _vp, _vp], _i),
+    "s4g_group_points_forward_f64": ([_vp, _vp, _i, _i, _i, _i, _i, _vp, _vp], _i),
+    "s4g_group_points_backward_f64": ([_vp, _vp, _i, _i, _i, _i, _i, _vp, _vp], _i),
+    "s4g_point_search_f64": ([_vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp], _i),
+    "s4g_interpolate_forward_f64": ([_vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp], _i),
+    "s4g_interpolate_backward_f64": ([_vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp], _i),
     "s4g_three_nn_weights_f32_i32": ([_vp, _vp, _i, _i, _i, _vp, _vp, _vp], _i),
     "s4g_interp_concat_bf16": ([_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp], _i),
     "s4g_gather_xyz_f32_i32": ([_vp, _vp, _i, _i, _i, _vp, _vp], _i),

@@ -157,3 +157,41 @@ def test_post_processing_pinned_to_reference_code():
     ok, _ = model_cpu.collision_filter(g["coll/poses"], g["coll/cloud"])
     assert np.array_equal(ok, np.nonzero(g["coll/ok"])[0])
     assert np.array_equal(model_cpu.importance_sampling(g["samp/scores"], g["samp/u"]), g["samp/picked"])
+
+
+@pytest.mark.parametrize("kind,N,M", [("lattice", 700, 300), ("dup", 900, 400), ("identical", 100, 20), ("uniform", 1500, 200)])
+def test_fp64_oracle_fps_tie_rule(kind, N, M):
+    """the double instantiation (sampling_kernel.cu:21 dispatches float and double): closed-form tie rule == literal
+    block simulation, and on fp32-representable inputs the double FPS of a lattice picks the same points as fp32
+    (all distances exact in both)."""
+    from oracle import pn2_ext_cpu as o
+    gen = {"lattice": lambda: inputs.lattice_cloud(2, N, 3, side=8), "dup": lambda: inputs.duplicated_cloud(2, N, 3),
+           "identical": lambda: inputs.identical_cloud(2, N), "uniform": lambda: inputs.uniform_cloud(2, N, 3)}[kind]
+    p32 = gen()
+    p64 = p32.double()
+    lit = o.farthest_point_sample(p64, M)
+    assert torch.equal(o.farthest_point_sample(p64, M, keyed=True), lit)
+    if kind in ("lattice", "identical"):
+        assert torch.equal(o.farthest_point_sample(p32, M), lit)
+
+
+def test_fp64_oracle_ops_match_torch():
+    from oracle import pn2_ext_cpu as o
+    rs = np.random.RandomState(5)
+    p = torch.from_numpy(rs.rand(2, 3, 400))
+    c = o.gather_points(p, o.farthest_point_sample(p, 40))
+    idx, cnt = o.ball_query(p, c, 0.2, 16)
+    d = ((p[:, :, None, :] - c[:, :, :, None]) ** 2).sum(1)  # (B,M,N)
+    r2 = float(np.float32(0.2)) ** 2
+    assert torch.equal(cnt, (d < r2).sum(-1).clamp(max=16))
+    nn_i, nn_d = o.point_search(p, c, 3)
+    top = torch.topk(((p[:, :, :, None] - c[:, :, None, :]) ** 2).sum(1), 3, dim=-1, largest=False)
+    assert torch.equal(nn_i, top.indices)
+    np.testing.assert_allclose(nn_d.numpy(), top.values.numpy(), rtol=1e-13, atol=1e-15)
+    f = torch.from_numpy(rs.randn(2, 7, 40))
+    w = torch.from_numpy(rs.rand(2, 400, 3))
+    out = o.interpolate_forward(f, nn_i, w)
+    ref = (torch.gather(f[:, :, None, :].expand(-1, -1, 400, -1), 3, nn_i[:, None].expand(-1, 7, -1, -1)) * w[:, None]).sum(-1)
+    np.testing.assert_allclose(out.numpy(), ref.numpy(), rtol=1e-13, atol=1e-14)
+    g = o.group_points_forward(f, idx.clamp(max=39))
+    assert g.dtype == torch.float64 and g.shape == (2, 7, 40, 16)
