@@ -190,6 +190,17 @@ int s4g_grasp_nms(const double* poses, const int* order, int n, double min_dist,
 /* importance sampling: cum = cumsum(exp(5 * scores)); picked[i] = first index with cum >= sorted_uniform[i] * cum[-1]. */
 int s4g_grasp_importance_sample(const double* scores, int n, const double* sorted_uniform, int m, double* cum, int* picked,
                                 void* stream);
+/* The tail of GraspDetector.detect (grasp_detector.py:212-251) for a whole batch with no host round trip
+ * (BASELINE config 5): collision test of every candidate (cloud (B,3,n_points) fp32, NULL = skip), ordered
+ * compaction, optional de-duplication (nms_min_dist <= 0 = off; result in descending score order), importance
+ * sampling with per-scene ascending uniforms [B][m] (device, NULL = first m) when more than m candidates are left,
+ * else all of them.  poses / scores / n_cand as written by s4g_grasp_poses / s4g_grasp_select with max_out = cap.
+ * Outputs: out_index [B][m] candidate indices, out_n [B], out_poses [B][m][16], out_scores [B][m]. */
+size_t s4g_grasp_finish_batch_workspace(int B, int cap);
+int s4g_grasp_finish_batch(const double* poses, const double* scores, const int* n_cand, int B, int cap,
+                           const float* cloud_b3n, int n_points, const float* gripper, double nms_min_dist,
+                           const double* sorted_uniform, int m, void* workspace, size_t workspace_bytes, int* out_index,
+                           int* out_n, double* out_poses, double* out_scores, void* stream);
 
 #ifdef __cplusplus
 }

@@ -67,6 +67,9 @@ _SIGNATURES = {
     "s4g_grasp_collision_f32": ([_vp, _i, _vp, _i, _vp, _vp, _vp, _vp], _i),
     "s4g_grasp_nms": ([_vp, _vp, _i, _d, _vp, _vp, _vp], _i),
     "s4g_grasp_importance_sample": ([_vp, _i, _vp, _i, _vp, _vp, _vp], _i),
+    "s4g_grasp_finish_batch_workspace": ([_i, _i], ctypes.c_size_t),
+    "s4g_grasp_finish_batch": ([_vp, _vp, _vp, _i, _i, _vp, _i, _vp, _d, _vp, _i, _vp, ctypes.c_size_t, _vp, _vp, _vp, _vp,
+                                _vp], _i),
 }
 
 for _name, (_args, _res) in _SIGNATURES.items():

@@ -326,6 +326,172 @@ __global__ void grasp_sample_kernel(const double* __restrict__ scores, int n, co
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// 7. the same tail for a whole batch without a host round trip (BASELINE config 5: thousands of scenes streamed
+//    through one GPU): collision test of every candidate of every scene, then — one block per scene — ordered
+//    compaction of the collision-free candidates, optional translation de-duplication in descending score
+//    order, importance sampling (or "all of them" when at most m are left, grasp_detector.py:235), and the
+//    gather of the selected poses.  Candidate counts stay on the device.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+grasp_collision_batch_kernel(const double* __restrict__ poses, const int* __restrict__ n_cand, int cap,
+                             const float* __restrict__ cloud_b3n, int n_points, const Gripper g,
+                             unsigned char* __restrict__ ok) {
+  const int b = blockIdx.y;
+  const int n = min(n_cand[b], cap);
+  __shared__ float gl[12];
+  __shared__ int s_back, s_finger;
+  const float* X = cloud_b3n + (long long)b * 3 * n_points;
+  const float* Y = X + n_points;
+  const float* Z = Y + n_points;
+  for (int p = blockIdx.x; p < n; p += gridDim.x) {
+    const double* P = poses + ((long long)b * cap + p) * 16;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      float Rm[9], t[3];
+      for (int a = 0; a < 3; ++a) {
+        for (int c = 0; c < 3; ++c) Rm[a * 3 + c] = (float)P[a * 4 + c];
+        t[a] = (float)P[a * 4 + 3];
+      }
+      for (int a = 0; a < 3; ++a) {
+        for (int c = 0; c < 3; ++c) gl[a * 4 + c] = Rm[c * 3 + a];
+        float acc = 0.f;
+        for (int c = 0; c < 3; ++c) acc = __fmaf_rn(-Rm[c * 3 + a], t[c], acc);
+        gl[a * 4 + 3] = acc;
+      }
+      s_back = 0;
+      s_finger = 0;
+    }
+    __syncthreads();
+    int back = 0, finger = 0;
+    for (int i = threadIdx.x; i < n_points; i += blockDim.x) {
+      const float px = X[i], py = Y[i], pz = Z[i];
+      const float lx = gl[0] * px + gl[1] * py + gl[2] * pz + gl[3];
+      if (!(lx < g.finger_length && lx > -g.bottom_length)) continue;
+      const float ly = gl[4] * px + gl[5] * py + gl[6] * pz + gl[7];
+      const float lz = gl[8] * px + gl[9] * py + gl[10] * pz + gl[11];
+      const bool zc = lz < g.half_hand_thickness && lz > -g.half_hand_thickness;
+      if (!zc) continue;
+      if (ly < g.half_bottom_width && ly > -g.half_bottom_width && lx < -g.back_margin) ++back;
+      const bool left = ly < g.half_bottom_width && ly > g.half_bottom_space;
+      const bool right = ly > -g.half_bottom_width && ly < -g.half_bottom_space;
+      if (left || right) ++finger;
+    }
+    back = __reduce_add_sync(0xffffffffu, back);
+    finger = __reduce_add_sync(0xffffffffu, finger);
+    if ((threadIdx.x & 31) == 0) {
+      atomicAdd(&s_back, back);
+      atomicAdd(&s_finger, finger);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0)
+      ok[(long long)b * cap + p] = ((float)s_back > g.back_threshold || (float)s_finger > g.finger_threshold) ? 0 : 1;
+  }
+}
+
+constexpr int kFinishThreads = 1024;
+
+__global__ void __launch_bounds__(kFinishThreads, 1)
+grasp_finish_batch_kernel(const double* __restrict__ poses, const double* __restrict__ scores, const int* __restrict__ n_cand,
+                          int cap, const unsigned char* __restrict__ ok, double nms_min_dist,
+                          const double* __restrict__ sorted_u, int m, int* __restrict__ work,  // [B][3*cap]
+                          double* __restrict__ cum,                                          // [B][cap]
+                          int* __restrict__ out_index, int* __restrict__ out_n, double* __restrict__ out_poses,
+                          double* __restrict__ out_scores) {
+  const int b = blockIdx.x;
+  const int n = min(n_cand[b], cap);
+  const double* P = poses + (long long)b * cap * 16;
+  const double* S = scores + (long long)b * cap;
+  int* list = work + (long long)b * 3 * cap;  // collision-free candidates, candidate order
+  int* order = list + cap;                    // ... in descending score order (stable)
+  int* kept = order + cap;                    // ... surviving the de-duplication
+  __shared__ int s_warp[32];
+  __shared__ int s_base, s_n, s_hit;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  // (a) ordered compaction
+  if (threadIdx.x == 0) s_base = 0;
+  __syncthreads();
+  for (int c0 = 0; c0 < n; c0 += kFinishThreads) {
+    const int i = c0 + threadIdx.x;
+    const bool f = i < n && (ok == nullptr || ok[(long long)b * cap + i] != 0);
+    const unsigned bal = __ballot_sync(0xffffffffu, f);
+    if (lane == 0) s_warp[warp] = __popc(bal);
+    __syncthreads();
+    int before = 0;
+    for (int w = 0; w < warp; ++w) before += s_warp[w];
+    if (f) list[s_base + before + __popc(bal & ((1u << lane) - 1u))] = i;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      int tot = 0;
+      for (int w = 0; w < 32; ++w) tot += s_warp[w];
+      s_base += tot;
+    }
+    __syncthreads();
+  }
+  int L = s_base;
+  const int* seq = list;
+  // (b) translation de-duplication in descending score order (ties: lower index first)
+  if (nms_min_dist > 0.0 && L > 0) {
+    for (int i = threadIdx.x; i < L; i += kFinishThreads) {
+      const double si = S[list[i]];
+      int rank = 0;
+      for (int j = 0; j < L; ++j) {
+        const double sj = S[list[j]];
+        rank += (sj > si || (sj == si && j < i)) ? 1 : 0;
+      }
+      order[rank] = list[i];
+    }
+    if (threadIdx.x == 0) s_n = 0;
+    __syncthreads();
+    for (int i = 0; i < L; ++i) {
+      const int c = order[i];
+      const double cx = P[16LL * c + 3], cy = P[16LL * c + 7], cz = P[16LL * c + 11];
+      if (threadIdx.x == 0) s_hit = 0;
+      __syncthreads();
+      const int nk = s_n;
+      bool hit = false;
+      for (int q = threadIdx.x; q < nk && !hit; q += kFinishThreads) {
+        const int k = kept[q];
+        hit = fabs(P[16LL * k + 3] - cx) + fabs(P[16LL * k + 7] - cy) + fabs(P[16LL * k + 11] - cz) < nms_min_dist;
+      }
+      if (hit) s_hit = 1;
+      __syncthreads();
+      if (threadIdx.x == 0 && !s_hit) kept[s_n++] = c;
+      __syncthreads();
+    }
+    L = s_n;
+    seq = kept;
+  }
+  // (c) importance sampling when more than m are left (grasp_detector.py:235-251), else all of them
+  int n_sel = L < m ? L : m;
+  int* oi = out_index + (long long)b * m;
+  if (L > m && sorted_u != nullptr) {
+    if (threadIdx.x == 0) {
+      double* cm = cum + (long long)b * cap;
+      double acc = 0.0;
+      for (int i = 0; i < L; ++i) {
+        acc += exp(5.0 * S[seq[i]]);
+        cm[i] = acc;
+      }
+      int idx = 0;
+      for (int i = 0; i < m; ++i) {
+        const double target = sorted_u[(long long)b * m + i] * cm[L - 1];
+        while (idx < L - 1 && cm[idx] < target) ++idx;
+        oi[i] = seq[idx];
+      }
+    }
+  } else {
+    for (int i = threadIdx.x; i < n_sel; i += kFinishThreads) oi[i] = seq[i];
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) out_n[b] = n_sel;
+  // (d) gather
+  for (int e = threadIdx.x; e < n_sel * 16; e += kFinishThreads)
+    out_poses[((long long)b * m) * 16 + e] = P[16LL * oi[e >> 4] + (e & 15)];
+  for (int i = threadIdx.x; i < n_sel; i += kFinishThreads) out_scores[(long long)b * m + i] = S[oi[i]];
+}
+
 }  // namespace s4g
 
 // ================================================================================================
@@ -409,5 +575,40 @@ extern "C" int s4g_grasp_importance_sample(const double* scores, int n, const do
   S4G_CHECK_ARG(n > 0 && m >= 0, "grasp_importance_sample: bad shape");
   s4g::grasp_sample_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(scores, n, sorted_uniform, m, cum, picked);
   S4G_LAUNCH_CHECK("grasp_importance_sample");
+  return S4G_OK;
+}
+
+// Batched tail (BASELINE config 5).  poses [B][cap][16] / scores [B][cap] / n_cand [B] as written by s4g_grasp_poses and
+// s4g_grasp_select (cap = their max_out); cloud (B,3,n_points) fp32 channel-first, NULL = no collision test;
+// nms_min_dist <= 0 = no de-duplication; sorted_uniform [B][m] fp64 ascending per scene (device), NULL = keep the first
+// m.  workspace: B * cap * (3 * 4 + 8 + 1) bytes.  Outputs: out_index [B][m] (candidate index), out_n [B],
+// out_poses [B][m][16], out_scores [B][m]; entries past out_n[b] are undefined.
+extern "C" size_t s4g_grasp_finish_batch_workspace(int B, int cap) { return (size_t)B * cap * (3 * 4 + 8 + 1) + 64; }
+
+extern "C" int s4g_grasp_finish_batch(const double* poses, const double* scores, const int* n_cand, int B, int cap,
+                                      const float* cloud_b3n, int n_points, const float* gripper, double nms_min_dist,
+                                      const double* sorted_uniform, int m, void* workspace, size_t workspace_bytes,
+                                      int* out_index, int* out_n, double* out_poses, double* out_scores, void* stream) {
+  S4G_CHECK_ARG(poses && scores && n_cand && workspace && out_index && out_n && out_poses && out_scores,
+                "grasp_finish_batch: null pointer");
+  S4G_CHECK_ARG(B >= 0 && cap > 0 && m > 0, "grasp_finish_batch: bad shape");
+  S4G_CHECK_ARG(workspace_bytes >= s4g_grasp_finish_batch_workspace(B, cap), "grasp_finish_batch: workspace too small");
+  S4G_CHECK_ARG(B <= 65535, "grasp_finish_batch: batch too large for one launch");
+  if (B == 0) return S4G_OK;
+  cudaStream_t s = (cudaStream_t)stream;
+  double* cum = reinterpret_cast<double*>(workspace);
+  int* work = reinterpret_cast<int*>(cum + (size_t)B * cap);
+  unsigned char* ok = reinterpret_cast<unsigned char*>(work + (size_t)B * cap * 3);
+  if (cloud_b3n) {
+    S4G_CHECK_ARG(gripper && n_points > 0, "grasp_finish_batch: collision test needs the gripper and a cloud");
+    s4g::Gripper g = {gripper[0], gripper[1], gripper[2], gripper[3], gripper[4], gripper[5], gripper[6], gripper[7]};
+    dim3 grid((unsigned)(cap < 128 ? cap : 128), (unsigned)B);
+    s4g::grasp_collision_batch_kernel<<<grid, 256, 0, s>>>(poses, n_cand, cap, cloud_b3n, n_points, g, ok);
+    S4G_LAUNCH_CHECK("grasp_collision_batch");
+  }
+  s4g::grasp_finish_batch_kernel<<<B, s4g::kFinishThreads, 0, s>>>(poses, scores, n_cand, cap, cloud_b3n ? ok : nullptr,
+                                                                  nms_min_dist, sorted_uniform, m, work, cum, out_index,
+                                                                  out_n, out_poses, out_scores);
+  S4G_LAUNCH_CHECK("grasp_finish_batch");
   return S4G_OK;
 }

@@ -59,7 +59,8 @@ class GraspPostProcessor:
             check(lib.s4g_grasp_scores_f32(ptr(x), B, C, N, ptr(out), stream_ptr(x.device)), "grasp_scores")
         return out
 
-    def select_and_decode(self, points, predictions, score_threshold=0.7, vertical_degree_threshold=0.2):
+    def select_and_decode(self, points, predictions, score_threshold=0.7, vertical_degree_threshold=0.2,
+                          check_overflow=True):
         """All scenes at once.  points (B,3,N) fp32.  Returns dict with ``n`` (B,) int32 candidate counts,
         ``poses`` (B, cap, 4, 4) fp64, ``scores`` (B, cap) fp64, ``point_index`` (the cloud point each pose is anchored at) / ``rotation_index`` (the rank whose rotation block
         the reference's reshape pairs with it) (B, cap) int32,
@@ -83,6 +84,8 @@ class GraspPostProcessor:
                                            float(vertical_degree_threshold), _dptr(self._approach_row), ptr(work), cap,
                                            ptr(out_point), ptr(out_rot), ptr(n_out), ptr(n_high), stream_ptr(dev)),
                       "grasp_select")
+                if not check_overflow:  # streaming use: no host round trip; candidates past `cap` are dropped
+                    break
                 need = int(n_out.max().item()) if B else 0
                 if need <= cap:
                     break
@@ -151,6 +154,44 @@ class GraspPostProcessor:
                                    vertical_degree_threshold)
         n = int(r["n"][0].item())
         return r["poses"][0, :n], r["scores"][0, :n]
+
+    def detect_batch_device(self, points, predictions, clouds=None, num_selected=5, score_threshold=0.7,
+                            verticalness_threshold=0.2, collision_check=True, nms_min_dist=None, sorted_uniform=None):
+        """``detect_batch`` without any host round trip (BASELINE config 5: thousands of scenes streamed through a
+        GPU): five kernel launches for the whole batch.  ``clouds``: (B,3,m) fp32 CUDA tensor for the collision
+        test (default: the network input); ``sorted_uniform``: (B, num_selected) ascending uniforms per scene
+        (np.sort(np.random.rand(k)) in the reference, grasp_detector.py:236) or None to keep the first
+        ``num_selected``.  Scenes with more than ``max_candidates`` candidates are truncated to the first ones.
+        Returns dict of CUDA tensors: ``n`` (B,), ``poses`` (B,k,4,4), ``scores`` (B,k), ``index`` (B,k), ``n_candidates`` (B,)."""
+        r = self.select_and_decode(points, predictions, score_threshold, verticalness_threshold, check_overflow=False)
+        poses, scores, n_cand = r["poses"], r["scores"], r["n"]
+        B, cap = scores.shape
+        dev = poses.device
+        m = int(num_selected)
+        cloud = None
+        if collision_check:
+            cloud = (clouds if clouds is not None else points).float().contiguous()
+            self._need_cuda(cloud)
+        u = None
+        if sorted_uniform is not None:
+            u = torch.as_tensor(np.asarray(sorted_uniform, dtype=np.float64) if not torch.is_tensor(sorted_uniform)
+                                else sorted_uniform, dtype=torch.float64).to(dev).contiguous()
+            assert u.shape == (B, m)
+        ws_bytes = int(lib.s4g_grasp_finish_batch_workspace(B, cap))
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+        out_index = torch.empty((B, m), dtype=torch.int32, device=dev)
+        out_n = torch.empty(B, dtype=torch.int32, device=dev)
+        out_poses = torch.empty((B, m, 4, 4), dtype=torch.float64, device=dev)
+        out_scores = torch.empty((B, m), dtype=torch.float64, device=dev)
+        with torch.cuda.device(dev):
+            check(lib.s4g_grasp_finish_batch(ptr(poses), ptr(scores), ptr(n_cand), B, cap,
+                                             ptr(cloud) if cloud is not None else None,
+                                             cloud.shape[2] if cloud is not None else 0, _dptr(self._gripper),
+                                             float(nms_min_dist) if nms_min_dist else 0.0,
+                                             ptr(u) if u is not None else None, m, ptr(ws), ws_bytes, ptr(out_index),
+                                             ptr(out_n), ptr(out_poses), ptr(out_scores), stream_ptr(dev)),
+                  "grasp_finish_batch")
+        return {"n": out_n, "poses": out_poses, "scores": out_scores, "index": out_index, "n_candidates": n_cand}
 
     def detect_batch(self, points, predictions, clouds=None, num_selected=5, score_threshold=0.7,
                      verticalness_threshold=0.2, collision_check=True, nms_min_dist=None, rng=None):

@@ -136,6 +136,48 @@ def test_detect_batch_runs_end_to_end():
             assert torch.allclose(R @ R.transpose(1, 2), eye.expand_as(R), atol=1e-5)
 
 
+@pytest.mark.parametrize("collision,nms,sample", [(True, 0.01, True), (True, None, True), (False, 0.02, False),
+                                                  (False, None, True), (True, 0.5, False)])
+def test_detect_batch_device_matches_oracle_composition(collision, nms, sample):
+    """The sync-free batched tail (s4g_grasp_finish_batch) == the per-scene composition of the oracle's collision
+    filter, de-duplication and importance sampling on the device's own candidate poses (exact indices)."""
+    from oracle import model_cpu as ora
+    from s4g_release_b200.postprocess import GraspPostProcessor
+    B, N, m = 5, 3000, 6
+    points, pred = _predictions(B, N, seed=33)
+    pred["score"][4] = -5.0 * torch.ones_like(pred["score"][4])  # a scene without candidates
+    pred["score"][4, 0] += 10.0
+    post = GraspPostProcessor()
+    cp, cpred = points.cuda(), {k: v.cuda() for k, v in pred.items()}
+    u = np.sort(np.random.RandomState(2).rand(B, m), axis=1)
+    r = post.detect_batch_device(cp, cpred, num_selected=m, score_threshold=0.6, collision_check=collision,
+                                 nms_min_dist=nms, sorted_uniform=u if sample else None)
+    cand = post.select_and_decode(cp, cpred, 0.6, 0.2)
+    torch.cuda.synchronize()
+    assert torch.equal(r["n_candidates"], cand["n"])
+    for b in range(B):
+        n = int(cand["n"][b])
+        poses = cand["poses"][b, :n].cpu().numpy()
+        scores = cand["scores"][b, :n].cpu().numpy()
+        idx = np.arange(n)
+        if collision and n:
+            # decide with the DEVICE's point counts where a point sits within rounding of a gripper plane
+            ok = post.collision_free(cand["poses"][b, :n], cp[b].t().contiguous()).cpu().numpy()
+            want_ok, _ = ora.collision_filter(poses, points[b].t().numpy())
+            assert len(set(np.nonzero(ok)[0]) ^ set(want_ok)) <= max(2, n // 100)
+            idx = idx[ok]
+        if nms and len(idx):
+            idx = idx[ora.translation_nms(poses[idx], scores[idx], nms)]
+        if len(idx) > m:
+            idx = idx[ora.importance_sampling(scores[idx], u[b])] if sample else idx[:m]
+        k = int(r["n"][b])
+        assert k == len(idx), (b, k, len(idx))
+        assert np.array_equal(r["index"][b, :k].cpu().numpy(), idx)
+        np.testing.assert_array_equal(r["poses"][b, :k].cpu().numpy(), poses[idx])
+        np.testing.assert_array_equal(r["scores"][b, :k].cpu().numpy(), scores[idx])
+    assert int(r["n"][4]) <= 1
+
+
 def test_against_reference_golden():
     """Device path vs the outputs of the reference's own code (tests/golden/postprocess_ref.npz)."""
     import os
