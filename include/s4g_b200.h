@@ -152,6 +152,12 @@ int s4g_chain_describe(const s4g_chain* chain, char* buf, int cap);
 int s4g_chain_pack_weights(const s4g_chain* chain, int layer, const float* w_host, int cout_real, int cin_real,
                            void* packed_host);
 int s4g_chain_set_params(s4g_chain* chain, const void* weights_dev, const float* const* bias_dev);
+/* Chains created with in_mode 5 (gathered input without features, e.g. the first set-abstraction level): their
+ * cin[0] is the OUTPUT width (multiple of 16, <= 128) of a 3 -> cin[0] layer on the relative coordinates
+ * (conv + BN + ReLU of SharedMLP block 0, nn_utils/mlp.py:95-106) that the kernel evaluates in fp32 on the CUDA
+ * cores while it stages the tile, instead of as a K = 3 tensor-core layer.  w4_host: [cin[0]][4] fp32 table in HOST
+ * memory (w_x, w_y, w_z, shift), BN folded; copied into the chain. */
+int s4g_chain_set_xyz_layer(s4g_chain* chain, const float* w4_host, int relu);
 int s4g_chain_run_rows(const s4g_chain* chain, const void* in_rows, int in_stride, long long P, void* out,
                        int n_points, void* stream);
 int s4g_chain_run_gather(const s4g_chain* chain, const void* feat, const float* xyz, const float* ctr, const int* nbr,

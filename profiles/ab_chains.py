@@ -20,7 +20,7 @@ for i, chain in enumerate(eng.sa_chains):
     Nn, M, K = lv_n[i], lv_n[i + 1], cfg["num_neighbours"][i]
     xyz = torch.rand(B, 3, Nn, device="cuda", generator=g); ctr = xyz[:, :, :M].contiguous()
     nbr = torch.randint(0, Nn, (B, M, K), device="cuda", dtype=torch.int32, generator=g)
-    fc = chain.cin[0] - 3
+    fc = chain.all_cin[0] - 3
     feat = torch.randn(B * Nn, fc, device="cuda", generator=g).to(torch.bfloat16) if fc else None
     out.append(("sa%d"%i, timed(lambda: chain.run_gather(feat, xyz, ctr, nbr))))
 for i, chains in enumerate(eng.fp_chains):

@@ -66,7 +66,7 @@ for i, chain in enumerate(eng.sa_chains):
     xyz = torch.rand(B, 3, Nn, device=dev, generator=g)
     ctr = xyz[:, :, :M].contiguous()
     nbr = torch.randint(0, Nn, (B, M, K), device=dev, dtype=torch.int32, generator=g)
-    fc = chain.cin[0] - 3
+    fc = chain.all_cin[0] - 3
     feat = torch.randn(B * Nn, fc, device=dev, generator=g).to(torch.bfloat16) if fc else None
     timed("sa%d" % i, chain, lambda: chain.run_gather(feat, xyz, ctr, nbr), B * M * K)
 for i, chains in enumerate(eng.fp_chains):

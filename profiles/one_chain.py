@@ -23,7 +23,7 @@ if name.startswith("sa"):
     xyz = torch.rand(B, 3, Nn, device="cuda", generator=g)
     ctr = xyz[:, :, :M].contiguous()
     nbr = torch.randint(0, Nn, (B, M, K), device="cuda", dtype=torch.int32, generator=g)
-    fc = ch.cin[0] - 3
+    fc = ch.all_cin[0] - 3
     feat = torch.randn(B * Nn, fc, device="cuda", generator=g).to(torch.bfloat16) if fc else None
     run = lambda: ch.run_gather(feat, xyz, ctr, nbr)
 elif name.startswith("fp"):

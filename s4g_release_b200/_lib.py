@@ -59,6 +59,7 @@ _SIGNATURES = {
     "s4g_chain_set_profile": ([_vp, _vp], _i),
     "s4g_chain_pack_weights": ([_vp, _i, _vp, _i, _i, _vp], _i),
     "s4g_chain_set_params": ([_vp, _vp, _vp], _i),
+    "s4g_chain_set_xyz_layer": ([_vp, _vp, _i], _i),
     "s4g_chain_run_rows": ([_vp, _vp, _i, ctypes.c_longlong, _vp, _i, _vp], _i),
     "s4g_chain_run_gather": ([_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp], _i),
     "s4g_grasp_scores_f32": ([_vp, _i, _i, _i, _vp, _vp], _i),

@@ -7,7 +7,7 @@ import torch
 
 from ._lib import check, lib, ptr, stream_ptr
 
-IN_ROWS, IN_GATHER = 0, 1
+IN_ROWS, IN_GATHER, IN_XYZ_MLP = 0, 1, 5
 OUT_ROWS, OUT_MAXPOOL, OUT_LOGITS = 2, 3, 4
 
 
@@ -16,10 +16,27 @@ def _int_array(values):
 
 
 class MlpChain:
-    """layers: list of (W fp32 [cout, cin] BN-folded, shift fp32 [cout], relu: bool)."""
+    """layers: list of (W fp32 [cout, cin] BN-folded, shift fp32 [cout], relu: bool).
+    ``xyz_layer_on_cuda_cores=True`` plans a gathered chain without features (in_mode IN_GATHER, feat_c 0, first
+    layer 3 -> <= 128 channels, more layers behind it) as IN_XYZ_MLP: the kernel evaluates that first layer in fp32 on
+    the CUDA cores while it stages the tile.  Off by default — measured on the first set-abstraction level
+    (64 x 5120 x 64 rows, 3 -> 128 -> 128 -> 256): 5.57 ms against 4.27 ms with the K = 16 tensor-core layer; the two
+    loader warps cannot issue the 49 k FMAs of a tile as fast as the rest of the tile runs."""
 
-    def __init__(self, layers, device, in_mode=IN_ROWS, feat_c=0, out_mode=OUT_ROWS, group=1, sigmoid=False):
+    def __init__(self, layers, device, in_mode=IN_ROWS, feat_c=0, out_mode=OUT_ROWS, group=1, sigmoid=False,
+                 xyz_layer_on_cuda_cores=False):
         self.device = torch.device(device)
+        self.all_cin = [int(w.shape[1]) for w, _, _ in layers]
+        self.all_cout = [int(w.shape[0]) for w, _, _ in layers]
+        self._xyz_table = None
+        if (xyz_layer_on_cuda_cores and in_mode == IN_GATHER and feat_c == 0 and len(layers) > 1
+                and layers[0][0].shape[0] % 16 == 0 and layers[0][0].shape[0] <= 128):
+            w0, b0, relu0 = layers[0]
+            table = torch.cat([w0.detach().float().reshape(-1, 3), b0.detach().float().reshape(-1, 1)], dim=1)
+            self._xyz_table = np.ascontiguousarray(table.cpu().numpy(), dtype=np.float32)
+            self._xyz_relu = bool(relu0)
+            layers = layers[1:]
+            in_mode = IN_XYZ_MLP
         self.n_layers = len(layers)
         self.cin = [int(w.shape[1]) for w, _, _ in layers]
         self.cout = [int(w.shape[0]) for w, _, _ in layers]
@@ -46,6 +63,10 @@ class MlpChain:
         self._bias_ptrs = (ctypes.c_void_p * self.n_layers)(*[t.data_ptr() for t in self.bias])
         check(lib.s4g_chain_set_params(self._h, ptr(self.weights), ctypes.cast(self._bias_ptrs, ctypes.c_void_p)),
               "chain_set_params")
+        if self._xyz_table is not None:
+            check(lib.s4g_chain_set_xyz_layer(self._h, self._xyz_table.ctypes.data_as(ctypes.c_void_p),
+                                              1 if self._xyz_relu else 0),
+                  "chain_set_xyz_layer")
 
     def info(self):
         vals = [ctypes.c_int() for _ in range(7)]
@@ -64,7 +85,7 @@ class MlpChain:
         check(lib.s4g_chain_set_profile(self._h, ptr(counters) if counters is not None else None), "chain_set_profile")
 
     def flops(self, rows):
-        return 2.0 * rows * sum(ci * co for ci, co in zip(self.cin, self.cout))
+        return 2.0 * rows * sum(ci * co for ci, co in zip(self.all_cin, self.all_cout))
 
     def run_rows(self, x, n_points=0):
         """x: bf16 [P, stride] channel-last (stride >= cin).  Returns bf16 [P, out_c] or fp32 (B, out_c, n_points)."""

@@ -26,7 +26,7 @@ constexpr double kIssuePerMma = 20.0;
 
 struct Block { int kind, c_begin, c_count, layer; };
 struct HMma { int blk, acc, k16, koff, n_rows, flags, layer, n_begin, k_begin, n_mma; };
-struct HEpi { int kind, acc, blk, layer, relu, c_begin, c_count, aux, pred, same, min_it; };
+struct HEpi { int kind, acc, blk, layer, relu, c_begin, c_count, aux, pred, same, min_it, coop; };
 struct HLoad { int kind, blk, c_begin, c_count, pred, same, min_it; };
 
 struct Draft {
@@ -39,11 +39,24 @@ struct Draft {
 
 int round_up(int x, int m) { return (x + m - 1) / m * m; }
 
+// which row-oriented epilogue jobs all 16 warps share: 0 none, 1 all, 2 those whose accumulator is not half of an
+// N = 256 pair (a pair is already drained by both groups at once), 3 (default) = 2, but only in chains whose hidden
+// layers are all at most 128 wide.  Measured (profiles/ab_chains.py, policy 0 -> 2): the chain that is bound by the
+// latency of single-accumulator layers gains (sa0 4.73 -> 4.27 ms); in wide chains the tile tail already overlaps the
+// next tile's first layer and the extra barrier traffic of a shared job costs more than the earlier hand-off
+// (head chain 1.635 -> 1.72 ms).
+int coop_policy() {
+  const char* e = getenv("S4G_EPI_COOP");
+  return e ? atoi(e) : 3;
+}
+
 bool build_draft(const s4g_chain* ch, const int* relu, int feat_c, int S, bool pair_ok, Draft& d) {
   const int L = ch->n_layers;
   std::vector<Block> in_desc;
   if (ch->in_mode == IN_ROWS) {
     for (int c = 0; c < ch->cin_pad[0]; c += 128) in_desc.push_back({WK_LOAD_ROWS, c, std::min(128, ch->cin_pad[0] - c), -1});
+  } else if (ch->in_mode == IN_XYZ_MLP) {
+    in_desc.push_back({WK_LOAD_XYZ, 0, ch->cin_pad[0], -1});
   } else {
     for (int c = 0; c < feat_c; c += 128) in_desc.push_back({WK_LOAD_FEAT, c, std::min(128, feat_c - c), -1});
     in_desc.push_back({WK_LOAD_XYZ, feat_c, 16, -1});
@@ -123,16 +136,27 @@ bool build_draft(const s4g_chain* ch, const int* relu, int feat_c, int S, bool p
         for (int kb = 0; kb < nk; ++kb)
           for (size_t gi = 0; gi < grps.size(); ++gi) emit(gi, kb);
       }
+      std::vector<int> in_pair(nn, 0);
+      for (const Grp& g : grps)
+        if (g.cnt == 2) in_pair[g.nb] = in_pair[g.nb + 1] = 1;
+      int policy = coop_policy();
+      if (policy == 3) {
+        policy = 2;
+        for (int h = 0; h + 1 < L; ++h)
+          if (ch->cout_pad[h] > 128) policy = 0;
+      }
       for (int nb = nb0; nb < nb1; ++nb) {
         const int acc = acc0 + nb - nb0;
+        const int coop = policy == 1 || (policy == 2 && !in_pair[nb]);
         if (!last) {
           const int idx = (int)d.blocks.size();
           d.blocks.push_back({WK_EPI_HIDDEN, nbs[nb].first, nbs[nb].second, l});
           produced.push_back(idx);
-          d.epi.push_back({WK_EPI_HIDDEN, acc, idx, l, relu[l], nbs[nb].first, nbs[nb].second, 0, 0, 0, 0});
+          d.epi.push_back({WK_EPI_HIDDEN, acc, idx, l, relu[l], nbs[nb].first, nbs[nb].second, 0, 0, 0, 0, coop});
         } else {
           const int kind = ch->out_mode == OUT_ROWS ? WK_EPI_ROWS : ch->out_mode == OUT_MAXPOOL ? WK_EPI_MAXPOOL : WK_EPI_LOGITS;
-          d.epi.push_back({kind, acc, -1, l, relu[l], nbs[nb].first, nbs[nb].second, (n_maxpool++) & 1, 0, 0, 0});
+          d.epi.push_back({kind, acc, -1, l, relu[l], nbs[nb].first, nbs[nb].second, (n_maxpool++) & 1, 0, 0, 0,
+                           kind == WK_EPI_ROWS ? coop : 0});
         }
       }
     }
@@ -159,9 +183,10 @@ bool build_draft(const s4g_chain* ch, const int* relu, int feat_c, int S, bool p
 }
 
 double epi_cost(const HEpi& e) {
+  const double cols = e.coop ? 0.5 * e.c_count : e.c_count;  // columns per lane quadrant
   switch (e.kind) {
-    case WK_EPI_HIDDEN: return 700.0 + 6.0 * e.c_count;  // per group of 8 warps (profiles/chain_prof.py)
-    case WK_EPI_ROWS: return 700.0 + 6.5 * e.c_count;
+    case WK_EPI_HIDDEN: return 700.0 + 6.0 * cols;  // per group of 8 warps (profiles/chain_prof.py)
+    case WK_EPI_ROWS: return 700.0 + 6.5 * cols;
     case WK_EPI_MAXPOOL: return 500.0;
     default: return 500.0;
   }
@@ -281,7 +306,7 @@ struct Sim {
         if (f < 0) break;
       }
       if (l.kind == WK_LOAD_XYZ) {
-        t_ld = std::max(t_ld, f) + kXyzCost;
+        t_ld = std::max(t_ld, f) + kXyzCost + (l.c_count > 16 ? 12.0 * l.c_count : 0.0);  // + the xyz layer itself
         act_ready[p] = t_ld;
       } else {
         t_ld = std::max(t_ld, f) + 30 + 8.0 * l.c_count / 8;
@@ -303,9 +328,13 @@ struct Sim {
         const int tile = pc_ep[g] / nE;
         const HEpi& e = d.epi[pc_ep[g] % nE];
         const int q = tile * nA + e.acc;
-        if ((q & 1) != g) { ++pc_ep[g]; prog = true; continue; }
+        if (e.coop) {  // both groups work on it: processed once, when both have arrived
+          if (pc_ep[g ^ 1] != pc_ep[g]) break;
+          if (g == 1) break;  // group 0 runs it for both
+        } else if ((q & 1) != g) { ++pc_ep[g]; prog = true; continue; }
         if (tm_full[q] < 0) break;
         double t = std::max(t_ep[g], tm_full[q]);
+        if (e.coop) t = std::max(t, t_ep[1]);
         int p = -1;
         if (e.kind == WK_EPI_HIDDEN) {
           p = tile * nB + e.blk;
@@ -318,6 +347,7 @@ struct Sim {
         if (p >= 0) act_ready[p] = t_ep[g];
         if (pc_ep[g] % nE == nE - 1) tile_end[tile] = t_ep[g];
         ++pc_ep[g];
+        if (e.coop) { t_ep[1] = t_ep[0]; ++pc_ep[1]; }
         prog = true;
       }
     }
@@ -359,7 +389,7 @@ int plan_chain(s4g_chain* ch, int n_layers, const int* cin, const int* cout, con
                int out_mode, int out_c, int group, int sigmoid) {
   memset(ch, 0, sizeof(*ch));
   S4G_CHECK_ARG(n_layers >= 1 && n_layers <= kMaxLayers, "mlp_chain: 1..%d layers supported", kMaxLayers);
-  S4G_CHECK_ARG(in_mode == IN_ROWS || in_mode == IN_GATHER, "mlp_chain: bad in_mode");
+  S4G_CHECK_ARG(in_mode == IN_ROWS || in_mode == IN_GATHER || in_mode == IN_XYZ_MLP, "mlp_chain: bad in_mode");
   S4G_CHECK_ARG(out_mode >= OUT_ROWS && out_mode <= OUT_LOGITS, "mlp_chain: bad out_mode");
   ch->n_layers = n_layers;
   ch->in_mode = in_mode;
@@ -374,6 +404,9 @@ int plan_chain(s4g_chain* ch, int n_layers, const int* cin, const int* cout, con
   if (in_mode == IN_GATHER) {
     S4G_CHECK_ARG(feat_c % 16 == 0 && cin[0] == feat_c + 3, "mlp_chain: gather input must be feat_c(%%16==0) + 3 xyz");
     ch->cin_pad[0] = feat_c + 16;
+  } else if (in_mode == IN_XYZ_MLP) {
+    S4G_CHECK_ARG(feat_c == 0 && cin[0] % 16 == 0 && cin[0] <= 128,
+                  "mlp_chain: the CUDA-core xyz layer needs feat_c == 0 and an output width that is a multiple of 16, <= 128");
   } else {
     S4G_CHECK_ARG(cin[0] % 8 == 0, "mlp_chain: row input width must be a multiple of 8");
   }
@@ -426,7 +459,7 @@ int plan_chain(s4g_chain* ch, int n_layers, const int* cin, const int* cout, con
   for (int j = 0; j < p.n_ld; ++j) {
     const HLoad& l = d.loads[j];
     p.ld[j] = {(uint8_t)l.kind, (uint8_t)l.same, (uint8_t)(l.blk % S), (uint8_t)(l.blk / S), 0, 0, 0, (uint8_t)l.pred,
-               (uint16_t)l.c_begin, (uint16_t)l.c_count, (uint8_t)l.min_it, {0, 0, 0}};
+               (uint16_t)l.c_begin, (uint16_t)l.c_count, (uint8_t)l.min_it, 0, {0, 0}};
   }
   p.load_depth = std::max(1, d.depth);
   p.n_ep = (int)d.epi.size();
@@ -434,7 +467,8 @@ int plan_chain(s4g_chain* ch, int n_layers, const int* cin, const int* cout, con
     const HEpi& e = d.epi[j];
     const int blk = e.blk < 0 ? 0 : e.blk;
     p.ep[j] = {(uint8_t)e.kind, (uint8_t)e.same, (uint8_t)(blk % S), (uint8_t)(blk / S), (uint8_t)e.acc, (uint8_t)e.layer,
-               (uint8_t)e.relu, (uint8_t)e.pred, (uint16_t)e.c_begin, (uint16_t)e.c_count, (uint8_t)e.min_it, {0, 0, 0}};
+               (uint8_t)e.relu, (uint8_t)e.pred, (uint16_t)e.c_begin, (uint16_t)e.c_count, (uint8_t)e.min_it,
+               (uint8_t)e.coop, {0, 0}};
   }
   const int nB = (int)d.blocks.size();
   p.n_act_mod = nB % S;

@@ -13,7 +13,9 @@
 //     ahead of the MMA warp by as many blocks as the slot ring allows, i.e. they prefetch the next tile;
 //   * 16 epilogue warps in two groups of 8 (two per TMEM lane quadrant, 64 columns each); group g drains the
 //     accumulators with q % 2 == g, so the two blocks of an N = 256 pair are drained concurrently: + shift, ReLU, bf16 ->
-//     the next layer's K-block slot, or the chain's output (rows / max-pooled groups / logits).
+//     the next layer's K-block slot, or the chain's output (rows / max-pooled groups / logits).  Jobs marked `coop`
+//     are drained by all 16 warps (four per lane quadrant, 32 columns each): the block is ready in half the time,
+//     which is what the next layer's first MMA waits for.
 // Activation blocks and accumulators live in RINGS indexed by their production order, so the streams are
 // identical for every tile and every wait is "the n-th completion of barrier b":
 //   activation block p (p-th produced, across tiles)  -> slot p % S, use p / S
@@ -55,7 +57,10 @@ constexpr int kMaxEpiJobs = 32;
 constexpr int kMaxLayers = 6;
 constexpr int kMaxBlocks = 32;  // activation blocks per tile
 
-enum InMode { IN_ROWS = 0, IN_GATHER = 1 };
+// IN_XYZ_MLP: gathered input without features whose 3 -> cin[0] first layer (K = 3: 81 % of a K = 16 MMA step
+// would be padding, and its epilogue a whole MMA -> epilogue -> MMA round trip) is computed by the loader warps
+// on the CUDA cores in fp32, straight into the activation block the chain's layer 0 reads
+enum InMode { IN_ROWS = 0, IN_GATHER = 1, IN_XYZ_MLP = 5 };
 enum OutMode { OUT_ROWS = 2, OUT_MAXPOOL = 3, OUT_LOGITS = 4 };
 
 // MF_PAIR: the job's MMAs are N = 256 wide and fill accumulators acc and acc + 1 (adjacent TMEM blocks)
@@ -75,7 +80,8 @@ struct MmaJob {      // one weight chunk x one activation K-block (part) -> one 
 enum WorkerKind {
   WK_LOAD_ROWS = 0,   // loader: cp.async a K-block of contiguous input rows (published once landed)
   WK_LOAD_FEAT = 1,   // loader: cp.async a K-block of gathered neighbour feature rows
-  WK_LOAD_XYZ = 3,    // loader: build and publish the 16-channel relative-xyz block (synchronous)
+  WK_LOAD_XYZ = 3,    // loader: build and publish the 16-channel relative-xyz block (synchronous); IN_XYZ_MLP: the
+                      //         c_count-channel output of the xyz layer, ReLU(W (x - c) + shift), instead
   WK_EPI_HIDDEN = 5,  // epilogue: accumulator -> +shift, ReLU, bf16 -> activation block
   WK_EPI_ROWS = 6,    // epilogue: accumulator -> bf16 rows in global memory
   WK_EPI_MAXPOOL = 7, // epilogue: transposed accumulator -> max over each group of columns -> bf16 [group][channel]
@@ -94,7 +100,8 @@ struct WorkerJob {
   uint16_t c_begin;  // loads: first input channel; epilogues: first output channel of the block
   uint16_t c_count;  // channels / columns in the block (multiple of 8 for loads, of 16 for epilogues)
   uint8_t min_it;    // producers, same == 0: first tile iteration of the CTA at which a previous block exists
-  uint8_t pad[3];
+  uint8_t coop;      // EPI_HIDDEN / EPI_ROWS: 1 = all 16 epilogue warps drain this accumulator (32 columns each)
+  uint8_t pad[2];
 };
 
 struct ChainParams {
@@ -115,6 +122,9 @@ struct ChainParams {
   int in_stride;
   const void* feat;          // IN_GATHER: bf16 [B*N][feat_c] (null when feat_c == 0)
   int feat_c;
+  float xyz_w[128 * 4];      // IN_XYZ_MLP: [cin[0]][4] fp32 = (w_x, w_y, w_z, shift) of the xyz layer (BN folded);
+  int xyz_relu;              //   in kernel-parameter space: every lane reads the same entry (constant-bank broadcast)
+  int xyz_set;
   const float* xyz;          // (B,3,N)
   const float* ctr;          // (B,3,M)
   const int* nbr;            // (B,M,K)

@@ -71,9 +71,16 @@ __global__ void __launch_bounds__(kFpsThreads, 1)
 fps_kernel(const float* __restrict__ points, int N, int M, int L, IndexT* __restrict__ index) {
   extern __shared__ float s_xyz[];  // [3][kFpsThreads * P]: this CTA's slice of the cloud
   constexpr int kLocal = kFpsThreads * P;
-  constexpr int kEntries = kFpsWarps * CLUSTER;
-  // one 32-byte record per warp of the cluster and iteration parity: {distance bits, tie-break key, x, y | z}
+  // Clusters of 4+ CTAs reduce inside the CTA first and exchange ONE record per CTA: the receiving CTA retires
+  // remote stores one at a time, and 16 x CLUSTER x 2 of them per iteration cost more than the distance pass
+  // (measured per iteration at N = 25 600: cluster 8, 1.85 -> 1.07 us; cluster 4, 0.90 -> 0.86 us; cluster 2 is
+  // faster with the direct per-warp exchange, 1.04 vs 1.12 us: profiles/r01/fps_probe.txt).
+  constexpr bool kHier = CLUSTER >= 4;
+  constexpr int kEntries = kHier ? CLUSTER : kFpsWarps * CLUSTER;
+  // one 32-byte record per warp (per CTA when kHier) of the cluster and iteration parity:
+  // {distance bits, tie-break key, x, y | z}
   __shared__ __align__(16) uint4 s_rec[2][kEntries][2];
+  __shared__ __align__(16) uint4 s_wrec[kHier ? 2 : 1][kHier ? kFpsWarps : 1][2];  // kHier: this CTA's warp records
   __shared__ __align__(8) unsigned long long s_bar[2];  // clusters: records of parity b have all landed
 
   const int t = threadIdx.x;
@@ -149,6 +156,34 @@ fps_kernel(const float* __restrict__ points, int N, int M, int L, IndexT* __rest
     const unsigned tb = (db == wmax) ? (__brev(j & bmask) | (j >> L)) : 0xffffffffu;
     const unsigned wtb = __reduce_min_sync(0xffffffffu, tb);
     constexpr unsigned kRecBytes = 20;  // 16-byte + 4-byte remote store per record
+    if constexpr (kHier) {
+      if (tb == wtb) {  // exactly one lane: keys are distinct per point
+        const int lp = bi * kFpsThreads + t;
+        s_wrec[buf][warp][0] = make_uint4(wmax, wtb, __float_as_uint(sx[lp]), __float_as_uint(sy[lp]));
+        s_wrec[buf][warp][1].x = __float_as_uint(sz[lp]);
+      }
+      __syncthreads();
+      if (warp == 0) {
+        // (a record that lands before the barrier is armed just makes the transaction count negative for a moment)
+        if (lane == 0) fps_mbar_expect_tx(&s_bar[buf], CLUSTER * kRecBytes);
+        uint2 kv = make_uint2(0u, 0xffffffffu);
+        if (lane < kFpsWarps) kv = *reinterpret_cast<const uint2*>(&s_wrec[buf][lane][0]);
+        const unsigned cmax = __reduce_max_sync(0xffffffffu, kv.x);
+        const unsigned ck = __reduce_min_sync(0xffffffffu, (kv.x == cmax) ? kv.y : 0xffffffffu);
+        if (lane < kFpsWarps && kv.x == cmax && kv.y == ck) {
+          const uint4 lo = s_wrec[buf][lane][0];
+          const unsigned zb = s_wrec[buf][lane][1].x;
+          const unsigned rec = fps_smem_u32(&s_rec[buf][rank][0]);
+          const unsigned bar = fps_smem_u32(&s_bar[buf]);
+#pragma unroll
+          for (int q = 0; q < CLUSTER; ++q) {
+            const unsigned rrec = fps_mapa(rec, q), rbar = fps_mapa(bar, q);
+            fps_st_async_v4(rrec, lo, rbar);
+            fps_st_async_b32(rrec + 16, zb, rbar);
+          }
+        }
+      }
+    } else {
     if constexpr (CLUSTER > 1) {
       // arm this parity's barrier for the kEntries records of this iteration (a record that lands first just
       // makes the transaction count negative for a moment: the phase cannot complete before this arrival)
@@ -175,13 +210,14 @@ fps_kernel(const float* __restrict__ points, int N, int M, int L, IndexT* __rest
         s_rec[buf][e][1] = make_uint4(zb, 0u, 0u, 0u);
       }
     }
+    }
     if constexpr (CLUSTER > 1) fps_mbar_wait(&s_bar[buf], (unsigned)((i - 1) >> 1) & 1u);  // ((i-1)/2)-th use of this parity
     else __syncthreads();
     // ---- every warp reduces the cluster's records redundantly ----
     unsigned d = 0u, k = 0xffffffffu;
     int e = 0;
 #pragma unroll
-    for (int q = lane; q < kEntries; q += 32) {
+    for (int q = lane; q < kEntries; q += 32) {  // (kHier: at most 16 records, one per CTA)
       const uint2 kv = *reinterpret_cast<const uint2*>(&s_rec[buf][q][0]);
       if (kv.x > d || (kv.x == d && kv.y < k)) { d = kv.x; k = kv.y; e = q; }
     }

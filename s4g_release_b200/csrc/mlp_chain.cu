@@ -209,7 +209,9 @@ __device__ __forceinline__ void ring_at(const Ring& base, const ChainParams& p, 
 // PROF = true adds the per-role cycle counters of s4g_chain_set_profile (clock reads cost the MMA warp ~150 cycles
 // per job, so the product path is compiled without them).
 // ------------------------------------------------------------------------------------------------
-template <bool PROF>
+// XYZ_MLP: the IN_XYZ_MLP loader code lives in an instantiation of its own — the kernel is ~60 KB of SASS shared by
+// five roles, and every extra block of rarely-run code costs the other chains instruction-cache misses.
+template <bool PROF, bool XYZ_MLP>
 __global__ void __launch_bounds__(kChainThreads, 1) mlp_chain_kernel(const __grid_constant__ ChainParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* slots = smem;
@@ -229,10 +231,11 @@ __global__ void __launch_bounds__(kChainThreads, 1) mlp_chain_kernel(const __gri
   const int n_my = ((int)blockIdx.x < n_tiles) ? (n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
 
   if (threadIdx.x == 0) {
-    // one arrival per WARP (per-thread arrivals on one mbarrier serialise for hundreds of cycles); a block
-    // is published by the 8 warps of one epilogue group or by the 2 loader warps arriving with count 4
-    for (int s = 0; s < kMaxSlots; ++s) mbar_init(&act_ready[s], kEpiGroupWarps);
-    for (int s = 0; s < kAccBlocks; ++s) { mbar_init(&tm_full[s], 1); mbar_init(&tm_empty[s], kEpiGroupWarps); }
+    // one arrival per WARP (per-thread arrivals on one mbarrier serialise for hundreds of cycles).  Blocks and
+    // accumulators count 16: the 16 epilogue warps of a cooperative job arrive once, the 8 warps of one
+    // epilogue group with weight 2, the 2 loader warps with weight 8
+    for (int s = 0; s < kMaxSlots; ++s) mbar_init(&act_ready[s], kEpiWarps);
+    for (int s = 0; s < kAccBlocks; ++s) { mbar_init(&tm_full[s], 1); mbar_init(&tm_empty[s], kEpiWarps); }
     for (int s = 0; s < kMaxStages; ++s) { mbar_init(&w_full[s], 1); mbar_init(&w_empty[s], 1); }
     for (int s = 0; s < kMaxBlocks; ++s) mbar_init(&blk_free[s], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -407,19 +410,19 @@ __global__ void __launch_bounds__(kChainThreads, 1) mlp_chain_kernel(const __gri
       const long long row = tile_row(jt, h);
       return row < p.P ? __ldg(p.nbr + row) : 0;
     };
-    if (p.in_mode == IN_GATHER) { jn_next[0] = load_nbr(0, 0); jn_next[1] = load_nbr(0, 1); }
+    if (p.in_mode != IN_ROWS) { jn_next[0] = load_nbr(0, 0); jn_next[1] = load_nbr(0, 1); }
     // slots of the cp.async blocks issued and not yet published, oldest first (one commit group each)
     int pend0 = 0, pend1 = 0, pend2 = 0, npend = 0;
     auto publish_oldest = [&]() {
       fence_proxy_async();
       __syncwarp();
-      if (lane == 0) mbar_arrive_n(&act_ready[pend0], kEpiGroupWarps / kLoadWarps);
+      if (lane == 0) mbar_arrive_n(&act_ready[pend0], kEpiWarps / kLoadWarps);
       pend0 = pend1; pend1 = pend2; --npend;
     };
     long long c_free = 0, c_cp = 0;
     const long long t_begin = tick<PROF>();
     for (int it = 0; it < n_my; ++it) {
-      if (p.in_mode == IN_GATHER) {
+      if (p.in_mode != IN_ROWS) {
         jn[0] = jn_next[0]; jn[1] = jn_next[1];
         jn_next[0] = load_nbr(it + 1, 0); jn_next[1] = load_nbr(it + 1, 1);
       }
@@ -447,6 +450,52 @@ __global__ void __launch_bounds__(kChainThreads, 1) mlp_chain_kernel(const __gri
           }
           mbar_wait(fbar, fpar);
           c_free += tick<PROF>() - t0;
+        }
+        if (XYZ_MLP && job.kind == WK_LOAD_XYZ) {
+          // the xyz layer on the CUDA cores: ReLU(W (x_j - c_m) + shift) in fp32 for this thread's two rows
+          float dx[2], dy[2], dz[2];
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            const long long row = tile_row(it, h);
+            dx[h] = dy[h] = dz[h] = 0.f;
+            if (row < p.P) {
+              const int b = (int)(row / per_b);
+              const int m = (int)((row - (long long)b * per_b) / p.K);
+              const float* X = p.xyz + (long long)b * 3 * p.N;
+              const float* C = p.ctr + (long long)b * 3 * p.M;
+              dx[h] = __fsub_rn(__ldg(X + jn[h]), __ldg(C + m));
+              dy[h] = __fsub_rn(__ldg(X + p.N + jn[h]), __ldg(C + p.M + m));
+              dz[h] = __fsub_rn(__ldg(X + 2 * p.N + jn[h]), __ldg(C + 2 * p.M + m));
+            }
+          }
+          uint8_t* sb = slots + (size_t)slot * kSlotBytes + (size_t)r * 16;
+          const bool relu = p.xyz_relu != 0;
+          const int pieces = job.c_count >> 3;
+#pragma unroll 2
+          for (int g = 0; g < pieces; ++g) {
+            float4 w[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e)  // constant bank, warp-uniform index
+              w[e] = make_float4(p.xyz_w[(g * 8 + e) * 4], p.xyz_w[(g * 8 + e) * 4 + 1], p.xyz_w[(g * 8 + e) * 4 + 2],
+                                 p.xyz_w[(g * 8 + e) * 4 + 3]);
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+              uint32_t pk[4];
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const float4 wa = w[2 * e], wb = w[2 * e + 1];
+                const float va = fmaf(wa.z, dz[h], fmaf(wa.y, dy[h], fmaf(wa.x, dx[h], wa.w)));
+                const float vb = fmaf(wb.z, dz[h], fmaf(wb.y, dy[h], fmaf(wb.x, dx[h], wb.w)));
+                pk[e] = bias_act_pack(va, vb, 0.f, 0.f, relu);
+              }
+              *reinterpret_cast<uint4*>(sb + (size_t)g * (kTileRows * 16) + (size_t)h * (64 * 16)) =
+                  make_uint4(pk[0], pk[1], pk[2], pk[3]);
+            }
+          }
+          fence_proxy_async();
+          __syncwarp();
+          if (lane == 0) mbar_arrive_n(&act_ready[slot], kEpiWarps / kLoadWarps);
+          continue;
         }
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
@@ -485,7 +534,7 @@ __global__ void __launch_bounds__(kChainThreads, 1) mlp_chain_kernel(const __gri
         if (job.kind == WK_LOAD_XYZ) {
           fence_proxy_async();
           __syncwarp();
-          if (lane == 0) mbar_arrive_n(&act_ready[slot], kEpiGroupWarps / kLoadWarps);
+          if (lane == 0) mbar_arrive_n(&act_ready[slot], kEpiWarps / kLoadWarps);
         } else {
           cp_async_commit();
           if (npend == 0) pend0 = slot; else if (npend == 1) pend1 = slot; else pend2 = slot;
@@ -509,8 +558,7 @@ __global__ void __launch_bounds__(kChainThreads, 1) mlp_chain_kernel(const __gri
     const int qd = warp & 3;              // TMEM lane quadrant this warp may read
     const int half = (warp >> 2) & 1;     // columns [64 half, 64 half + 64) of an accumulator block
     const int erow = qd * 32 + lane;      // tile row (= TMEM lane) in row-oriented epilogues
-    const int c0 = 64 * half;
-    const uint32_t lane_base = tmem_base + ((uint32_t)(qd * 32) << 16) + (uint32_t)c0;
+    const uint32_t lane_base = tmem_base + ((uint32_t)(qd * 32) << 16);
     Ring base = {0, 0u};
     unsigned base_q = 0;
     long long c_full = 0, c_free = 0, c_epi = 0;
@@ -520,13 +568,15 @@ __global__ void __launch_bounds__(kChainThreads, 1) mlp_chain_kernel(const __gri
       for (int j = 0; j < p.n_ep; ++j) {
         const WorkerJob job = p.ep[j];
         const unsigned q = base_q + job.acc;
-        if ((int)(q & 1u) != grp) continue;
+        const bool coop = job.coop != 0;  // all 16 warps: 32 columns each; else the 8 warps of group q % 2: 64 each
+        if (!coop && (int)(q & 1u) != grp) continue;
         const unsigned tb = q & (kAccBlocks - 1);
-        const uint32_t t_addr = lane_base + tb * 128u;
+        const int c0 = coop ? 32 * (warp >> 2) : 64 * half;
+        const uint32_t t_addr = lane_base + tb * 128u + (uint32_t)c0;
         const bool relu = job.relu != 0;
         if (job.kind == WK_EPI_HIDDEN || job.kind == WK_EPI_ROWS) {
           const bool hidden = job.kind == WK_EPI_HIDDEN;
-          const int ncol = min(64, (int)job.c_count - c0);  // columns of this warp: 64, 48, 32, 16 or <= 0
+          const int ncol = min(coop ? 32 : 64, (int)job.c_count - c0);  // columns of this warp: 64, 48, 32, 16 or <= 0
           const float* bias = p.bias[job.layer] + job.c_begin + c0;
           // the shifts of the first 32 columns travel while this warp waits for the accumulator
           float4 bv[8];  // the shift vectors are padded to a multiple of 128 floats: always in bounds
@@ -604,8 +654,9 @@ __global__ void __launch_bounds__(kChainThreads, 1) mlp_chain_kernel(const __gri
           if (hidden) fence_proxy_async();
           __syncwarp();
           if (lane == 0) {
-            if (hidden) mbar_arrive(&act_ready[slot]);
-            mbar_arrive(&tm_empty[tb]);
+            const unsigned weight = coop ? 1u : 2u;
+            if (hidden) mbar_arrive_n(&act_ready[slot], weight);
+            mbar_arrive_n(&tm_empty[tb], weight);
           }
           c_epi += tick<PROF>() - t1;
           if (PROF && p.prof && blockIdx.x == 0 && it == 2 && (threadIdx.x & 255) == 0) {
@@ -691,7 +742,7 @@ __global__ void __launch_bounds__(kChainThreads, 1) mlp_chain_kernel(const __gri
         }
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&tm_empty[tb]);
+        if (lane == 0) mbar_arrive_n(&tm_empty[tb], 2u);
         c_epi += tick<PROF>() - t1;
         if (PROF && p.prof && blockIdx.x == 0 && it == 2 && (threadIdx.x & 255) == 0) {
           long long* tr = p.prof + 148 * 16 + 4 * kMaxMmaJobs + j * 4;
@@ -797,6 +848,17 @@ extern "C" int s4g_chain_set_params(s4g_chain* ch, const void* weights_dev, cons
   return S4G_OK;
 }
 
+// IN_XYZ_MLP chains: the BN-folded 3 -> cin[0] layer the loader warps evaluate in fp32.  w4_host: [cin[0]][4] fp32
+// (w_x, w_y, w_z, shift) in HOST memory; it is copied into the kernel parameters.
+extern "C" int s4g_chain_set_xyz_layer(s4g_chain* ch, const float* w4_host, int relu) {
+  S4G_CHECK_ARG(ch && w4_host, "mlp_chain: null pointer");
+  S4G_CHECK_ARG(ch->in_mode == s4g::IN_XYZ_MLP, "mlp_chain: chain was not planned with IN_XYZ_MLP");
+  memcpy(ch->prm.xyz_w, w4_host, sizeof(float) * 4 * (size_t)ch->cin_pad[0]);
+  ch->prm.xyz_relu = relu ? 1 : 0;
+  ch->prm.xyz_set = 1;
+  return S4G_OK;
+}
+
 // Optional per-CTA cycle counters (16 x int64 per CTA, >= 148 CTAs): [0] producer total, [1] producer
 // waiting for a free stage; [2] MMA warp total, [3..5] waiting for activations / TMEM / weights;
 // [6] epilogue warps total, [7] waiting for an accumulator, [12] for a free slot, [10] epilogue work;
@@ -812,14 +874,16 @@ static int s4g_chain_launch(const s4g_chain* ch, s4g::ChainParams& p, cudaStream
   if (p.P <= 0) return S4G_OK;
   static bool attr_set = false;
   if (!attr_set) {
-    S4G_CUDA(cudaFuncSetAttribute(s4g::mlp_chain_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    S4G_CUDA(cudaFuncSetAttribute(s4g::mlp_chain_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    S4G_CUDA(cudaFuncSetAttribute(s4g::mlp_chain_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    S4G_CUDA(cudaFuncSetAttribute(s4g::mlp_chain_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    S4G_CUDA(cudaFuncSetAttribute(s4g::mlp_chain_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr_set = true;
   }
   const int tiles = (p.P + s4g::kTileRows - 1) / s4g::kTileRows;
   const int grid = tiles < s4g::num_sms() ? tiles : s4g::num_sms();
-  if (p.prof) s4g::mlp_chain_kernel<true><<<grid, s4g::kChainThreads, ch->smem_bytes, stream>>>(p);
-  else s4g::mlp_chain_kernel<false><<<grid, s4g::kChainThreads, ch->smem_bytes, stream>>>(p);
+  if (p.in_mode == s4g::IN_XYZ_MLP) s4g::mlp_chain_kernel<false, true><<<grid, s4g::kChainThreads, ch->smem_bytes, stream>>>(p);
+  else if (p.prof) s4g::mlp_chain_kernel<true, false><<<grid, s4g::kChainThreads, ch->smem_bytes, stream>>>(p);
+  else s4g::mlp_chain_kernel<false, false><<<grid, s4g::kChainThreads, ch->smem_bytes, stream>>>(p);
   S4G_LAUNCH_CHECK("mlp_chain");
   return S4G_OK;
 }
@@ -849,7 +913,8 @@ extern "C" int s4g_chain_run_rows(const s4g_chain* ch, const void* in_rows, int 
 extern "C" int s4g_chain_run_gather(const s4g_chain* ch, const void* feat, const float* xyz, const float* ctr,
                                     const int* nbr, int B, int N, int M, int K, void* out, void* stream) {
   S4G_CHECK_ARG(ch && xyz && ctr && nbr && out, "mlp_chain: null pointer");
-  S4G_CHECK_ARG(ch->in_mode == s4g::IN_GATHER, "mlp_chain: chain was planned for row input");
+  S4G_CHECK_ARG(ch->in_mode != s4g::IN_ROWS, "mlp_chain: chain was planned for row input");
+  S4G_CHECK_ARG(ch->in_mode != s4g::IN_XYZ_MLP || ch->prm.xyz_set, "mlp_chain: s4g_chain_set_xyz_layer was not called");
   S4G_CHECK_ARG(ch->prm.feat_c == 0 || (feat != nullptr && ((uintptr_t)feat & 15) == 0), "mlp_chain: bad feature table");
   S4G_CHECK_ARG((long long)B * M * K < (1ll << 31), "mlp_chain: too many rows");
   if (ch->out_mode == s4g::OUT_MAXPOOL) S4G_CHECK_ARG(K == ch->prm.group, "mlp_chain: K != planned max-pool group");

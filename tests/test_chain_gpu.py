@@ -84,10 +84,12 @@ def test_logits_head(dims, n_out, B, n_points, sigmoid):
     _check(got, want)
 
 
+@pytest.mark.parametrize("xyz_cuda", [False, True])
 @pytest.mark.parametrize("feat_c,dims,B,N,M,K", [(0, [128, 128, 256], 2, 2048, 256, 64), (64, [64, 64, 128], 2, 1024, 64, 16),
                                                   (256, [256, 256, 512], 1, 2048, 128, 64), (512, [512, 512, 1024], 1, 512, 64, 64),
-                                                  (32, [32, 64], 3, 300, 50, 8), (0, [16, 32], 1, 100, 7, 32)])
-def test_set_abstraction_gather_maxpool(feat_c, dims, B, N, M, K):
+                                                  (32, [32, 64], 3, 300, 50, 8), (0, [16, 32], 1, 100, 7, 32),
+                                                  (0, [64, 128], 2, 700, 33, 16), (0, [256, 128], 1, 400, 20, 8), (0, [48], 1, 90, 9, 8)])
+def test_set_abstraction_gather_maxpool(feat_c, dims, B, N, M, K, xyz_cuda):
     """gather + centroid subtraction + concat + chain + max over K, vs torch fp32 on the same operands."""
     from s4g_release_b200.chain import IN_GATHER, OUT_MAXPOOL, MlpChain
     g = torch.Generator().manual_seed(feat_c + M)
@@ -97,18 +99,27 @@ def test_set_abstraction_gather_maxpool(feat_c, dims, B, N, M, K):
     ctr = torch.gather(xyz, 2, sel.unsqueeze(1).expand(-1, 3, -1)).contiguous()
     nbr = torch.randint(0, N, (B, M, K), generator=g, dtype=torch.int32)
     feat = _bf(torch.randn(B * N, feat_c, generator=g)) if feat_c else None
-    ch = MlpChain(layers, "cuda", IN_GATHER, feat_c, OUT_MAXPOOL, group=K)
+    if xyz_cuda and feat_c:
+        pytest.skip("the CUDA-core xyz layer only exists for chains without gathered features")
+    ch = MlpChain(layers, "cuda", IN_GATHER, feat_c, OUT_MAXPOOL, group=K, xyz_layer_on_cuda_cores=xyz_cuda)
     got = ch.run_gather(feat.cuda().to(torch.bfloat16) if feat_c else None, xyz.cuda(), ctr.cuda(), nbr.cuda())
     torch.cuda.synchronize()
     # reference: reference channel order [rel_xyz | features] (modules.py:48)
     idx = nbr.long().reshape(B, M * K)
     gx = torch.gather(xyz.transpose(1, 2), 1, idx.unsqueeze(-1).expand(-1, -1, 3)).reshape(B, M, K, 3)
-    rel = _bf(gx - ctr.transpose(1, 2).unsqueeze(2))
+    rel32 = gx - ctr.transpose(1, 2).unsqueeze(2)
+    rel = _bf(rel32)
     x = rel
     if feat_c:
         gf = torch.gather(feat.reshape(B, N, feat_c), 1, idx.unsqueeze(-1).expand(-1, -1, feat_c)).reshape(B, M, K, feat_c)
         x = torch.cat([rel, gf], dim=-1)
-    want = _ref_chain(x.reshape(-1, feat_c + 3), layers).reshape(B * M, K, -1).max(dim=1)[0]
+    if ch.in_mode == 5:
+        # IN_XYZ_MLP: the 3 -> C layer runs in fp32 on the CUDA cores (unrounded coordinates and weights)
+        w0, b0, _ = layers[0]
+        h = _bf(torch.relu(rel32.reshape(-1, 3) @ w0.t() + b0))
+        want = _ref_chain(h, layers[1:]).reshape(B * M, K, -1).max(dim=1)[0]
+    else:
+        want = _ref_chain(x.reshape(-1, feat_c + 3), layers).reshape(B * M, K, -1).max(dim=1)[0]
     assert tuple(got.shape) == (B * M, dims[-1])
     _check(got, _bf(want))
 

@@ -30,6 +30,8 @@ FPS_CASES = [
     ("lattice", 3, 2000, 600), ("lattice", 2, 700, 700), ("lattice", 2, 200, 150), ("lattice", 2, 40, 40),
     ("lattice", 2, 30000, 2000), ("dup", 2, 3000, 1500), ("dup", 1, 26000, 3000), ("identical", 2, 600, 50),
     ("uniform", 1, 60000, 512), ("lattice", 1, 100000, 600),
+    # batches that fill the GPU: two clouds interleaved per cluster (odd batches leave a cluster one cloud)
+    ("lattice", 75, 2048, 200), ("dup", 39, 5120, 300), ("uniform", 65, 25600, 80), ("identical", 41, 4000, 20),
 ]
 
 
@@ -67,7 +69,7 @@ def test_fps_noncontiguous_and_errors(ext, ora):
     with pytest.raises(RuntimeError):
         ext.farthest_point_sample(base[:, :2].cuda(), 10)
     with pytest.raises(RuntimeError):
-        ext.farthest_point_sample(base.double().cuda(), 10)
+        ext.farthest_point_sample(base.half().cuda(), 10)  # float32 / float64 only, like AT_DISPATCH_FLOATING_TYPES
 
 
 def test_fps_full_batch_properties(ext):
