@@ -211,7 +211,9 @@ __device__ __forceinline__ void ring_at(const Ring& base, const ChainParams& p, 
 // ------------------------------------------------------------------------------------------------
 // XYZ_MLP: the IN_XYZ_MLP loader code lives in an instantiation of its own — the kernel is ~60 KB of SASS shared by
 // five roles, and every extra block of rarely-run code costs the other chains instruction-cache misses.
-template <bool PROF, bool XYZ_MLP>
+// OUT (the chain's output mode) and GATHER (gathered vs row input) are compile-time for the same reason: a chain only
+// carries the loader and the final epilogue it uses.
+template <bool PROF, bool XYZ_MLP, int OUT, bool GATHER>
 __global__ void __launch_bounds__(kChainThreads, 1) mlp_chain_kernel(const __grid_constant__ ChainParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* slots = smem;
@@ -342,7 +344,7 @@ __global__ void __launch_bounds__(kChainThreads, 1) mlp_chain_kernel(const __gri
         // work for the NEXT job is done between this job's MMAs, while the tensor pipe is busy: all but the
         // last MMA, then fetch + probe the next job, then the last MMA and the commits.
         const uint32_t n = (uint32_t)job.n8 * 8u;
-        const bool transposed = (job.flags & MF_TRANSPOSED) != 0;
+        const bool transposed = OUT == OUT_MAXPOOL && (job.flags & MF_TRANSPOSED) != 0;
         const uint32_t idesc = make_idesc(128, transposed ? kTileRows : (int)n);
         const uint32_t a_lo = (slots16 + (uint32_t)slot * (kSlotBytes >> 4) + (uint32_t)job.koff * (2u * a_lbo16)) | (a_lbo16 << 16);
         const uint32_t w_lo = (ring16 + (uint32_t)cur.s * (kStageBytes >> 4)) | (n << 16);  // LBO = n rows * 16 B
@@ -410,7 +412,7 @@ __global__ void __launch_bounds__(kChainThreads, 1) mlp_chain_kernel(const __gri
       const long long row = tile_row(jt, h);
       return row < p.P ? __ldg(p.nbr + row) : 0;
     };
-    if (p.in_mode != IN_ROWS) { jn_next[0] = load_nbr(0, 0); jn_next[1] = load_nbr(0, 1); }
+    if constexpr (GATHER) { jn_next[0] = load_nbr(0, 0); jn_next[1] = load_nbr(0, 1); }
     // slots of the cp.async blocks issued and not yet published, oldest first (one commit group each)
     int pend0 = 0, pend1 = 0, pend2 = 0, npend = 0;
     auto publish_oldest = [&]() {
@@ -422,7 +424,7 @@ __global__ void __launch_bounds__(kChainThreads, 1) mlp_chain_kernel(const __gri
     long long c_free = 0, c_cp = 0;
     const long long t_begin = tick<PROF>();
     for (int it = 0; it < n_my; ++it) {
-      if (p.in_mode != IN_ROWS) {
+      if constexpr (GATHER) {
         jn[0] = jn_next[0]; jn[1] = jn_next[1];
         jn_next[0] = load_nbr(it + 1, 0); jn_next[1] = load_nbr(it + 1, 1);
       }
@@ -431,7 +433,7 @@ __global__ void __launch_bounds__(kChainThreads, 1) mlp_chain_kernel(const __gri
         int slot;
         unsigned use;
         ring_at(base, p, job.blk_mod, job.blk_div, slot, use);
-        if (job.kind != WK_LOAD_XYZ && npend == D) {  // pipeline full: the oldest block must land first
+        if ((!GATHER || job.kind != WK_LOAD_XYZ) && npend == D) {  // pipeline full: the oldest block must land first
           const long long t0 = tick<PROF>();
           cp_async_wait(D - 1);
           c_cp += tick<PROF>() - t0;
@@ -503,7 +505,7 @@ __global__ void __launch_bounds__(kChainThreads, 1) mlp_chain_kernel(const __gri
           const bool valid = row < p.P;
           const long long rr = valid ? row : 0;
           uint8_t* sbase = slots + (size_t)slot * kSlotBytes + (size_t)(r + 64 * h) * 16;
-          if (job.kind == WK_LOAD_XYZ) {
+          if (GATHER && job.kind == WK_LOAD_XYZ) {
             float xa = 0.f, xb = 0.f, xc = 0.f;
             if (valid) {
               const int b = (int)(rr / per_b);
@@ -520,7 +522,7 @@ __global__ void __launch_bounds__(kChainThreads, 1) mlp_chain_kernel(const __gri
             *reinterpret_cast<uint4*>(sbase + kTileRows * 16) = make_uint4(0u, 0u, 0u, 0u);
           } else {
             const __nv_bfloat16* src;
-            if (job.kind == WK_LOAD_ROWS) {
+            if constexpr (!GATHER) {
               src = reinterpret_cast<const __nv_bfloat16*>(p.in_rows) + rr * (long long)p.in_stride + job.c_begin;
             } else {
               const int b = (int)(rr / per_b);
@@ -531,7 +533,7 @@ __global__ void __launch_bounds__(kChainThreads, 1) mlp_chain_kernel(const __gri
             for (int c = 0; c < pieces; ++c) cp_async16(sbase + (size_t)c * (kTileRows * 16), src + c * 8, valid);
           }
         }
-        if (job.kind == WK_LOAD_XYZ) {
+        if (GATHER && job.kind == WK_LOAD_XYZ) {
           fence_proxy_async();
           __syncwarp();
           if (lane == 0) mbar_arrive_n(&act_ready[slot], kEpiWarps / kLoadWarps);
@@ -574,8 +576,8 @@ __global__ void __launch_bounds__(kChainThreads, 1) mlp_chain_kernel(const __gri
         const int c0 = coop ? 32 * (warp >> 2) : 64 * half;
         const uint32_t t_addr = lane_base + tb * 128u + (uint32_t)c0;
         const bool relu = job.relu != 0;
-        if (job.kind == WK_EPI_HIDDEN || job.kind == WK_EPI_ROWS) {
-          const bool hidden = job.kind == WK_EPI_HIDDEN;
+        if (job.kind == WK_EPI_HIDDEN || (OUT == OUT_ROWS && job.kind == WK_EPI_ROWS)) {
+          const bool hidden = OUT != OUT_ROWS || job.kind == WK_EPI_HIDDEN;
           const int ncol = min(coop ? 32 : 64, (int)job.c_count - c0);  // columns of this warp: 64, 48, 32, 16 or <= 0
           const float* bias = p.bias[job.layer] + job.c_begin + c0;
           // the shifts of the first 32 columns travel while this warp waits for the accumulator
@@ -594,10 +596,10 @@ __global__ void __launch_bounds__(kChainThreads, 1) mlp_chain_kernel(const __gri
           const unsigned fpar = (unsigned)(job.same ? it : it - 1) & 1u;
           uint8_t* dst = slots + (size_t)slot * kSlotBytes + ((size_t)(c0 >> 3) * kTileRows + erow) * 16;
           __nv_bfloat16* orow = reinterpret_cast<__nv_bfloat16*>(p.out) + row * (long long)p.out_c + job.c_begin + c0;
-          // slab A: columns [0, 32) or [0, 16) of the warp's range; slab B: the rest
-          const int na = ncol >= 32 ? 32 : (ncol > 0 ? 16 : 0);
-          const int nb = ncol - na > 0 ? ncol - na : 0;  // 32, 16 or 0
-          if (na == 32) {
+          // full-width warps (64 columns, or 32 in a cooperative job): 32-column slabs, the second slab's shifts
+          // travelling under its TMEM load.  Narrow layers (a multiple of 16 columns left): a compact 16-column
+          // loop — the kernel's instruction footprint is what the common path pays for.
+          if (ncol == 64 || ncol == 32) {
             float va[32];
             tmem_ld32_issue(t_addr, va);
             if (need_free) {
@@ -611,43 +613,34 @@ __global__ void __launch_bounds__(kChainThreads, 1) mlp_chain_kernel(const __gri
               if (hidden) *reinterpret_cast<uint4*>(dst + (size_t)g * (kTileRows * 16)) = pk;
               else if (row < p.P) *reinterpret_cast<uint4*>(orow + g * 8) = pk;
             }
+            if (ncol == 64) {
+              tmem_ld32_issue(t_addr + 32u, va);
+#pragma unroll
+              for (int g = 0; g < 8; ++g) bv[g] = __ldg(reinterpret_cast<const float4*>(bias + 32) + g);
+              tmem_wait();
+#pragma unroll
+              for (int g = 0; g < 4; ++g) {
+                const uint4 pk = epi_piece_r(va + g * 8, bv[2 * g], bv[2 * g + 1], relu);
+                if (hidden) *reinterpret_cast<uint4*>(dst + (size_t)(4 + g) * (kTileRows * 16)) = pk;
+                else if (row < p.P) *reinterpret_cast<uint4*>(orow + 32 + g * 8) = pk;
+              }
+            }
           } else {
             if (need_free) mbar_wait(&blk_free[job.pred], fpar);
-            if (na == 16) {
+#pragma unroll 1
+            for (int c = 0; c < ncol; c += 16) {
               float vh[16];
-              tmem_ld16_issue(t_addr, vh);
+              tmem_ld16_issue(t_addr + (uint32_t)c, vh);
+              float4 bw[4];
+#pragma unroll
+              for (int g = 0; g < 4; ++g) bw[g] = __ldg(reinterpret_cast<const float4*>(bias + c) + g);
               tmem_wait();
 #pragma unroll
               for (int g = 0; g < 2; ++g) {
-                const uint4 pk = epi_piece_r(vh + g * 8, bv[2 * g], bv[2 * g + 1], relu);
-                if (hidden) *reinterpret_cast<uint4*>(dst + (size_t)g * (kTileRows * 16)) = pk;
-                else if (row < p.P) *reinterpret_cast<uint4*>(orow + g * 8) = pk;
+                const uint4 pk = epi_piece_r(vh + g * 8, bw[2 * g], bw[2 * g + 1], relu);
+                if (hidden) *reinterpret_cast<uint4*>(dst + (size_t)((c >> 3) + g) * (kTileRows * 16)) = pk;
+                else if (row < p.P) *reinterpret_cast<uint4*>(orow + c + g * 8) = pk;
               }
-            }
-          }
-          if (nb == 32) {
-            float va[32];
-            tmem_ld32_issue(t_addr + 32u, va);
-#pragma unroll
-            for (int g = 0; g < 8; ++g) bv[g] = __ldg(reinterpret_cast<const float4*>(bias + 32) + g);
-            tmem_wait();
-#pragma unroll
-            for (int g = 0; g < 4; ++g) {
-              const uint4 pk = epi_piece_r(va + g * 8, bv[2 * g], bv[2 * g + 1], relu);
-              if (hidden) *reinterpret_cast<uint4*>(dst + (size_t)(4 + g) * (kTileRows * 16)) = pk;
-              else if (row < p.P) *reinterpret_cast<uint4*>(orow + 32 + g * 8) = pk;
-            }
-          } else if (nb == 16) {
-            float vh[16];
-            tmem_ld16_issue(t_addr + 32u, vh);
-#pragma unroll
-            for (int g = 0; g < 4; ++g) bv[g] = __ldg(reinterpret_cast<const float4*>(bias + 32) + g);
-            tmem_wait();
-#pragma unroll
-            for (int g = 0; g < 2; ++g) {
-              const uint4 pk = epi_piece_r(vh + g * 8, bv[2 * g], bv[2 * g + 1], relu);
-              if (hidden) *reinterpret_cast<uint4*>(dst + (size_t)(4 + g) * (kTileRows * 16)) = pk;
-              else if (row < p.P) *reinterpret_cast<uint4*>(orow + 32 + g * 8) = pk;
             }
           }
           tc_fence_before();
@@ -670,7 +663,7 @@ __global__ void __launch_bounds__(kChainThreads, 1) mlp_chain_kernel(const __gri
         const long long t1 = tick<PROF>();
         c_full += t1 - t0;
         tc_fence_after();
-        if (job.kind == WK_EPI_MAXPOOL) {
+        if (OUT == OUT_MAXPOOL && job.kind == WK_EPI_MAXPOOL) {
           // transposed: TMEM lane = output channel, columns = the tile's 128 positions; a group of G
           // adjacent columns is one centroid's neighbourhood (max commutes with +shift and ReLU).
           const int G = p.group;
@@ -695,32 +688,19 @@ __global__ void __launch_bounds__(kChainThreads, 1) mlp_chain_kernel(const __gri
 #pragma unroll
             for (int e = 1; e < 32; ++e) m = fmaxf(m, fmaxf(v0[e], v1[e]));
             emit(m, c0);
-          } else if (G == 32) {
-            float m0 = v0[0], m1 = v1[0];
+          } else {  // G = 32, 16 or 8: 64 / G groups in this warp's columns (compact code: the PN2_CLS levels use 64)
+#pragma unroll 1
+            for (int g0 = 0; g0 < 64; g0 += G) {
+              float m = -3.4e38f;
 #pragma unroll
-            for (int e = 1; e < 32; ++e) { m0 = fmaxf(m0, v0[e]); m1 = fmaxf(m1, v1[e]); }
-            emit(m0, c0);
-            emit(m1, c0 + 32);
-          } else if (G == 16) {
-#pragma unroll
-            for (int g = 0; g < 32; g += 16) {
-              float m0 = v0[g], m1 = v1[g];
-#pragma unroll
-              for (int e = 1; e < 16; ++e) { m0 = fmaxf(m0, v0[g + e]); m1 = fmaxf(m1, v1[g + e]); }
-              emit(m0, c0 + g);
-              emit(m1, c0 + 32 + g);
-            }
-          } else {  // G == 8
-#pragma unroll
-            for (int g = 0; g < 32; g += 8) {
-              float m0 = v0[g], m1 = v1[g];
-#pragma unroll
-              for (int e = 1; e < 8; ++e) { m0 = fmaxf(m0, v0[g + e]); m1 = fmaxf(m1, v1[g + e]); }
-              emit(m0, c0 + g);
-              emit(m1, c0 + 32 + g);
+              for (int e = 0; e < 32; ++e) {
+                if (e >= g0 && e < g0 + G) m = fmaxf(m, v0[e]);
+                if (e + 32 >= g0 && e + 32 < g0 + G) m = fmaxf(m, v1[e]);
+              }
+              emit(m, c0 + g0);
             }
           }
-        } else if (half == 0) {  // WK_EPI_LOGITS: fp32, channel-first (B, out_c, n_points), bias, optional sigmoid
+        } else if (OUT == OUT_LOGITS && half == 0) {  // WK_EPI_LOGITS: fp32, channel-first (B, out_c, n_points), bias, optional sigmoid
           const float* bias = p.bias[job.layer] + job.c_begin;
           float v[16];
           tmem_ld16_issue(t_addr, v);
@@ -869,21 +849,48 @@ extern "C" int s4g_chain_set_profile(s4g_chain* ch, void* counters_dev) {
   return S4G_OK;
 }
 
+namespace s4g {
+template <bool PROF, bool XYZ_MLP, int OUT, bool GATHER>
+static int launch_chain(const ChainParams& p, int grid, size_t smem, cudaStream_t stream) {
+  auto kern = mlp_chain_kernel<PROF, XYZ_MLP, OUT, GATHER>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    S4G_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    attr_set = true;
+  }
+  kern<<<grid, kChainThreads, smem, stream>>>(p);
+  return S4G_OK;
+}
+}  // namespace s4g
+
 static int s4g_chain_launch(const s4g_chain* ch, s4g::ChainParams& p, cudaStream_t stream) {
   S4G_CHECK_ARG(p.weights != nullptr, "mlp_chain: s4g_chain_set_params was not called");
   if (p.P <= 0) return S4G_OK;
-  static bool attr_set = false;
-  if (!attr_set) {
-    S4G_CUDA(cudaFuncSetAttribute(s4g::mlp_chain_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    S4G_CUDA(cudaFuncSetAttribute(s4g::mlp_chain_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    S4G_CUDA(cudaFuncSetAttribute(s4g::mlp_chain_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    attr_set = true;
-  }
   const int tiles = (p.P + s4g::kTileRows - 1) / s4g::kTileRows;
   const int grid = tiles < s4g::num_sms() ? tiles : s4g::num_sms();
-  if (p.in_mode == s4g::IN_XYZ_MLP) s4g::mlp_chain_kernel<false, true><<<grid, s4g::kChainThreads, ch->smem_bytes, stream>>>(p);
-  else if (p.prof) s4g::mlp_chain_kernel<true, false><<<grid, s4g::kChainThreads, ch->smem_bytes, stream>>>(p);
-  else s4g::mlp_chain_kernel<false, false><<<grid, s4g::kChainThreads, ch->smem_bytes, stream>>>(p);
+  const bool gather = p.in_mode != s4g::IN_ROWS, xyz = p.in_mode == s4g::IN_XYZ_MLP, prof = p.prof != nullptr;
+  S4G_CHECK_ARG(!(xyz && prof), "mlp_chain: the cycle counters are not built for IN_XYZ_MLP chains");
+  int rc = S4G_E_UNSUPPORTED;
+#define S4G_CHAIN_CASE(PROF_, XYZ_, OUT_, GATHER_)                                                                     \
+  if (prof == PROF_ && xyz == XYZ_ && ch->out_mode == s4g::OUT_ && gather == GATHER_)                                  \
+    rc = s4g::launch_chain<PROF_, XYZ_, s4g::OUT_, GATHER_>(p, grid, ch->smem_bytes, stream);
+  S4G_CHAIN_CASE(false, false, OUT_ROWS, false)
+  S4G_CHAIN_CASE(false, false, OUT_LOGITS, false)
+  S4G_CHAIN_CASE(false, false, OUT_MAXPOOL, false)
+  S4G_CHAIN_CASE(false, false, OUT_ROWS, true)
+  S4G_CHAIN_CASE(false, false, OUT_LOGITS, true)
+  S4G_CHAIN_CASE(false, false, OUT_MAXPOOL, true)
+  S4G_CHAIN_CASE(true, false, OUT_ROWS, false)
+  S4G_CHAIN_CASE(true, false, OUT_LOGITS, false)
+  S4G_CHAIN_CASE(true, false, OUT_MAXPOOL, false)
+  S4G_CHAIN_CASE(true, false, OUT_ROWS, true)
+  S4G_CHAIN_CASE(true, false, OUT_LOGITS, true)
+  S4G_CHAIN_CASE(true, false, OUT_MAXPOOL, true)
+  S4G_CHAIN_CASE(false, true, OUT_ROWS, true)
+  S4G_CHAIN_CASE(false, true, OUT_LOGITS, true)
+  S4G_CHAIN_CASE(false, true, OUT_MAXPOOL, true)
+#undef S4G_CHAIN_CASE
+  if (rc != S4G_OK) return rc == S4G_E_UNSUPPORTED ? s4g::set_error(rc, "mlp_chain: no kernel for this chain type") : rc;
   S4G_LAUNCH_CHECK("mlp_chain");
   return S4G_OK;
 }
