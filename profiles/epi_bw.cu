@@ -223,7 +223,7 @@ static void run(int active, const float* bias, long long* d_out, int load = 0, c
   fflush(stdout);
 }
 
-int main() {
+int main(int argc, char** argv) {
   float* bias;
   long long* d_out;
   cudaMalloc(&bias, 4096);
@@ -241,7 +241,8 @@ int main() {
   run<2>(16, bias, d_out);
   run<3>(16, bias, d_out);
   run<5>(16, bias, d_out);
-  for (int load = 1; load <= 3; ++load) {
+  // concurrent tensor-core / bulk-copy load: EXPERIMENTAL (hangs on the B200 it was tried on) — ./epi_bw load
+  for (int load = 1; load <= 3 && argc > 1; ++load) {
     run<0>(8, bias, d_out, load, wsrc);
     run<0>(16, bias, d_out, load, wsrc);
     run<1>(16, bias, d_out, load, wsrc);
