@@ -706,16 +706,23 @@ __global__ void __launch_bounds__(kChainThreads, 1) mlp_chain_kernel(const __gri
           tmem_ld16_issue(t_addr, v);
           tmem_wait();
           if (row < p.P) {
-            float* out = reinterpret_cast<float*>(p.out);
+            // (compact on purpose: index arithmetic hoisted, fast reciprocal — this loop is unrolled 16 times and
+            // the kernel's instruction footprint is paid by every role)
             const long long bb = row / p.n_points;
             const long long n = row - bb * p.n_points;
+            float* o = reinterpret_cast<float*>(p.out) + (bb * p.out_c) * p.n_points + n;
+            const size_t stride = (size_t)p.n_points;
+            const float4* b4 = reinterpret_cast<const float4*>(bias);
+            const float4 b0 = __ldg(b4), b1 = __ldg(b4 + 1), b2 = __ldg(b4 + 2), b3 = __ldg(b4 + 3);
+            const float bs[16] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w, b2.x, b2.y, b2.z, b2.w, b3.x, b3.y, b3.z, b3.w};
+            const bool sig = p.sigmoid != 0;
 #pragma unroll
             for (int c = 0; c < 16; ++c) {
               if (c < p.out_c) {
-                float t = v[c] + __ldg(bias + c);
+                float t = v[c] + bs[c];
                 if (relu) t = fmaxf(t, 0.f);
-                if (p.sigmoid) t = 1.f / (1.f + __expf(-t));
-                out[(bb * p.out_c + c) * p.n_points + n] = t;
+                if (sig) t = __fdividef(1.f, 1.f + __expf(-t));
+                o[c * stride] = t;
               }
             }
           }
