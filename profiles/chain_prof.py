@@ -22,7 +22,7 @@ NAMES = ["prod_total", "prod_wait_stage", "mma_total", "mma_wait_act", "mma_wait
 
 
 def timed(name, chain, fn, rows):
-    cnt = torch.zeros(148 * 16 + 4 * 128 + 4 * 32, dtype=torch.int64, device=dev)
+    cnt = torch.zeros(148 * 16 + 4 * 128 + 4 * 32 + 2 * 4 * 64, dtype=torch.int64, device=dev)
     chain.set_profile(cnt)
     fn()
     torch.cuda.synchronize()
@@ -56,6 +56,13 @@ def timed(name, chain, fn, rows):
             r = trace[4 * 128 + 4 * j: 4 * 128 + 4 * j + 3]
             if r[0] > 0:
                 print("     epi %2d: %6d %6d %6d   (waited %5d, work %5d)" % (j, r[0] - t0, r[1] - t0, r[2] - t0, r[1] - r[0], r[2] - r[1]))
+        print("   loader jobs of the 3rd and 4th tile (same clock): begin slot_free issued")
+        for k in range(2):
+            for j in range(64):
+                r = trace[4 * 128 + 4 * 32 + 4 * (64 * k + j): 4 * 128 + 4 * 32 + 4 * (64 * k + j) + 3]
+                if r[0] > 0:
+                    print("     tile %d load %2d: %6d %6d %6d   (waited %5d for the slot, issue %5d)" %
+                          (3 + k, j, r[0] - t0, r[1] - t0, r[2] - t0, r[1] - r[0], r[2] - r[1]))
 
 
 N = cfg["num_points"] if "num_points" in cfg else 25600

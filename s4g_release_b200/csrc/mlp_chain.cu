@@ -439,6 +439,7 @@ __global__ void __launch_bounds__(kChainThreads, 1) mlp_chain_kernel(const __gri
           c_cp += tick<PROF>() - t0;
           publish_oldest();
         }
+        const long long tl0 = tick<PROF>();
         // slot free?  wait for the release of the block that last held it (chain_plan.cuh)
         uint64_t* fbar = &blk_free[job.pred];
         const bool need = job.same || it >= (int)job.min_it;
@@ -499,6 +500,10 @@ __global__ void __launch_bounds__(kChainThreads, 1) mlp_chain_kernel(const __gri
           if (lane == 0) mbar_arrive_n(&act_ready[slot], kEpiWarps / kLoadWarps);
           continue;
         }
+        const long long tl1 = tick<PROF>();
+        // (lane = row: an instruction touches 32 cache lines.  8 rows x 4 pieces per instruction — 8 lines, the
+        // quarter-warps still conflict-free in shared memory — was measured 5 % SLOWER on the head chain, and an
+        // L2 bulk prefetch of the next tile's rows changed nothing: the stall at a tile start is slot-bound.)
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
           const long long row = tile_row(it, h);
@@ -532,6 +537,10 @@ __global__ void __launch_bounds__(kChainThreads, 1) mlp_chain_kernel(const __gri
 #pragma unroll 4
             for (int c = 0; c < pieces; ++c) cp_async16(sbase + (size_t)c * (kTileRows * 16), src + c * 8, valid);
           }
+        }
+        if (PROF && p.prof && blockIdx.x == 0 && (it == 2 || it == 3) && r == 0) {  // loader timeline (chain_prof.py)
+          long long* tr = p.prof + 148 * 16 + 4 * kMaxMmaJobs + 4 * kMaxEpiJobs + ((it - 2) * kMaxLoadJobs + j) * 4;
+          tr[0] = tl0; tr[1] = tl1; tr[2] = tick<PROF>();
         }
         if (GATHER && job.kind == WK_LOAD_XYZ) {
           fence_proxy_async();
