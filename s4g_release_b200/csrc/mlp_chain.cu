@@ -547,6 +547,13 @@ __global__ void __launch_bounds__(kChainThreads, 1) mlp_chain_kernel(const __gri
           __syncwarp();
           if (lane == 0) mbar_arrive_n(&act_ready[slot], kEpiWarps / kLoadWarps);
         } else {
+          // the blocks committed before this one had this block's whole issue loop to land: publish them now,
+          // not when the pipeline is full — the MMA warp starts a tile on its FIRST input block
+          // (cp.async.wait_group only counts committed groups, so this does not wait for the copies just issued)
+          if (npend) {
+            cp_async_wait(0);
+            while (npend) publish_oldest();
+          }
           cp_async_commit();
           if (npend == 0) pend0 = slot; else if (npend == 1) pend1 = slot; else pend2 = slot;
           ++npend;
