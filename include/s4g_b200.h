@@ -164,6 +164,25 @@ int s4g_chain_run_gather(const s4g_chain* chain, const void* feat, const float* 
                          int B, int N, int M, int K, void* out, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * Device-side cloud pre-processing (csrc/preprocess.cu) — GraspDetector._pre_processing / sample_single_cloud
+ * (grasp_detector.py:82-105) over transform_numpy_points (utils/math_utils.py:20-24).  The reference's voxelize() and
+ * remove_outliers() discard the clouds open3d returns, so what it observably does is the axis change _REAL2TRAIN
+ * and a random sub-sample: s4g_cloud_transform_select_f32, for a batch, with caller-supplied indices.
+ * ------------------------------------------------------------------------------------------------ */
+/* out[b,:,i] = (mat44 [cloud[b,:,index[b,i]]; 1])[:3].  cloud (B,3,n), index (B,m) int64 or NULL (identity, m == n),
+ * mat44: 16 floats in HOST memory, row-major -> out (B,3,m). */
+int s4g_cloud_transform_select_f32(const float* cloud, int B, int n, const int64_t* index, int m, const float* mat44,
+                                   float* out, void* stream);
+/* The intended (but inert in the reference) voxel filter, OUR definition: cell keys ((cz*ny + cy)*nx + cx) of a
+ * (3,n) cloud on a grid of side `voxel` anchored at origin3 (host), and the per-voxel means given the sorted keys,
+ * the sort permutation and the exclusive scan of the segment-start flags.  The radius-outlier filter is
+ * s4g_ball_query_f32 with K = nb_points + 1 (count > nb_points keeps the point). */
+int s4g_voxel_keys_f32(const float* cloud_3n, int n, const float* origin3, float voxel, const int* dims3, int64_t* key,
+                       void* stream);
+int s4g_voxel_means_f32(const float* cloud_3n, int n, const int64_t* sorted_key, const int64_t* order, const int* seg_rank,
+                        float* out_3cap, int cap, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
  * Device-side grasp post-processing (csrc/postprocess.cu) — replaces the numpy / python tail of
  * GraspDetector: post_processing + orthogonalization (grasp_detector.py:124-185), the per-pose collision loop
  * (:214-232 over cloud_processor/view_collision_checker.py:37-65), importance sampling (:235-251), and adds

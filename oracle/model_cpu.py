@@ -268,3 +268,50 @@ def translation_nms(poses, scores, min_dist):
         if all(np.abs(poses[k, :3, 3] - t).sum() >= min_dist for k in kept):
             kept.append(int(c))
     return np.array(kept, dtype=np.int64)
+
+
+# --------------------------------------------------------------------------- #
+# Pre-processing (CPU restatement; test infrastructure only)
+# --------------------------------------------------------------------------- #
+def transform_numpy_points(cloud_array, transformation_matrix):
+    """utils/math_utils.py:20-24."""
+    homo = np.concatenate([cloud_array, np.ones([1, cloud_array.shape[1]])], axis=0)
+    return (transformation_matrix @ homo)[:3, :]
+
+
+def pre_processing(cloud_array, random_index):
+    """grasp_detector.py:92-105 as it BEHAVES: voxelize() / remove_outliers() discard open3d's return values
+    (cloud_processor.py:31-42), so the cloud goes straight to _REAL2TRAIN and the random sub-sample (:86-91);
+    the result is what eval() turns into the float32 network input (:113)."""
+    points = transform_numpy_points(np.asarray(cloud_array), REAL2TRAIN.astype(np.int64))
+    return points[:, np.asarray(random_index)].astype(np.float32)
+
+
+def voxel_down_sample(cloud_3n, voxel_size):
+    """OUR definition of the intended voxel filter (csrc/preprocess.cu): per-voxel mean, ascending (z,y,x) cell order,
+    grid anchored at min - voxel/2 like open3d."""
+    p = np.asarray(cloud_3n, dtype=np.float32)
+    origin = (p.min(axis=1) - np.float32(0.5 * voxel_size)).astype(np.float32)
+    extent = p.max(axis=1) - origin
+    dims = np.maximum(np.floor(extent / voxel_size).astype(np.int64) + 1, 1)
+    inv = np.float32(1.0) / np.float32(voxel_size)
+    cell = np.floor((p - origin[:, None]) * inv).astype(np.int64)
+    cell = np.minimum(np.maximum(cell, 0), (dims - 1)[:, None])
+    key = (cell[2] * dims[1] + cell[1]) * dims[0] + cell[0]
+    order = np.argsort(key, kind="stable")
+    uniq, start = np.unique(key[order], return_index=True)
+    out = np.zeros((3, len(uniq)), dtype=np.float32)
+    bounds = list(start) + [len(key)]
+    for v in range(len(uniq)):
+        sel = order[bounds[v]:bounds[v + 1]]
+        out[:, v] = (p[:, sel].astype(np.float64).sum(axis=1) / len(sel)).astype(np.float32)
+    return out
+
+
+def radius_outlier_mask(cloud_3n, nb_points, radius):
+    """Keep points with more than nb_points points (itself included) within radius — fp32 squared distances in the
+    ops' rounding order, strict '<' against radius^2 (the ball-query rule)."""
+    from oracle import pn2_ext_cpu
+    p = torch.as_tensor(np.asarray(cloud_3n, dtype=np.float32)).unsqueeze(0)
+    _, count = pn2_ext_cpu.ball_query(p, p, radius, nb_points + 1)
+    return (count[0] > nb_points).numpy()

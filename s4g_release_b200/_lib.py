@@ -62,6 +62,9 @@ _SIGNATURES = {
     "s4g_chain_set_xyz_layer": ([_vp, _vp, _i], _i),
     "s4g_chain_run_rows": ([_vp, _vp, _i, ctypes.c_longlong, _vp, _i, _vp], _i),
     "s4g_chain_run_gather": ([_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp], _i),
+    "s4g_cloud_transform_select_f32": ([_vp, _i, _i, _vp, _i, _vp, _vp, _vp], _i),
+    "s4g_voxel_keys_f32": ([_vp, _i, _vp, _f, _vp, _vp, _vp], _i),
+    "s4g_voxel_means_f32": ([_vp, _i, _vp, _vp, _vp, _vp, _i, _vp], _i),
     "s4g_grasp_scores_f32": ([_vp, _i, _i, _i, _vp, _vp], _i),
     "s4g_grasp_select": ([_vp, _vp, _i, _i, _d, _d, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp], _i),
     "s4g_grasp_poses": ([_vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp], _i),

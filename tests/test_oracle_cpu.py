@@ -195,3 +195,17 @@ def test_fp64_oracle_ops_match_torch():
     np.testing.assert_allclose(out.numpy(), ref.numpy(), rtol=1e-13, atol=1e-14)
     g = o.group_points_forward(f, idx.clamp(max=39))
     assert g.dtype == torch.float64 and g.shape == (2, 7, 40, 16)
+
+
+def test_preprocess_oracle_pinned_to_reference_golden():
+    """oracle/model_cpu.py::pre_processing == the reference's own transform_numpy_points + sample_single_cloud
+    replay (tests/golden/preprocess_ref.npz, made by tests/golden/make_preprocess_golden.py); the seeded index draw is
+    reproduced too."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "preprocess_ref.npz"))
+    for name in ("large", "small"):
+        cloud, index = g[name + "/cloud"], g[name + "/index"]
+        assert np.array_equal(model_cpu.pre_processing(cloud, index), g[name + "/points_f32"])
+        rs = np.random.RandomState(17)
+        n, m = cloud.shape[1], len(index)
+        assert np.array_equal(rs.choice(np.arange(n), m, replace=not (n > m)), index)
