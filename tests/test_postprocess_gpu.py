@@ -196,3 +196,42 @@ def test_against_reference_golden():
     assert np.array_equal(ok.cpu().numpy(), g["coll/ok"])
     picked = post.importance_sample(torch.from_numpy(g["samp/scores"]).cuda(), g["samp/u"])
     assert np.array_equal(picked.cpu().numpy(), g["samp/picked"])
+
+
+def test_grasp_detector_detect_flow():
+    """s4g_release_b200.detector.GraspDetector.detect == the oracle's restatement of the reference flow
+    (pre-processing -> forward -> post-processing -> collision filter -> importance sampling), with the random draws
+    replayed from the same seed.  The network is replaced by seeded random predictions: random-init heads give
+    thousands of EXACTLY tied scores, and the reference's ranking of ties is whatever numpy's unstable argsort does
+    (grasp_detector.py:149), which no other implementation can be asked to reproduce."""
+    from oracle import model_cpu as ora
+    from s4g_release_b200.detector import GraspDetector
+    import bench
+    rs = np.random.RandomState(4)
+    n_in = 6000
+    cloud = (rs.rand(3, 9000).astype(np.float32) * np.array([[0.5], [0.5], [0.05]], dtype=np.float32)
+             + np.array([[-0.25], [-0.25], [0.8]], dtype=np.float32))
+    det = GraspDetector(model=bench.seeded_model(), num_input=n_in)
+    real_pred = det.eval(cloud, rng=np.random.RandomState(1))  # the real network runs end to end
+    assert tuple(real_pred["frame_R"].shape) == (1, 9, n_in)
+    _, pred = _predictions(1, n_in, seed=77)
+    cuda_pred = {k: v.cuda() for k, v in pred.items()}
+    det.model = lambda batch: cuda_pred
+    poses, scores = det.detect(cloud.T, num_selected=5, score_threshold=0.6, verticalness_threshold=0.2,
+                               collision_check=True, rng=np.random.RandomState(9))
+    assert poses.dtype == np.float64 and poses.shape[1:] == (4, 4) and scores.shape[0] == poses.shape[0] <= 5
+    rng = np.random.RandomState(9)
+    idx = det.pre.sample_index(cloud.shape[1], rng)
+    points = ora.pre_processing(cloud, idx)
+    dev_scores = det.post.scores(cuda_pred["score"])[0].cpu().numpy()
+    p, s = ora.post_processing(points, pred, 0.6, 0.2, all_scores=dev_scores)
+    ok = det.post.collision_free(torch.from_numpy(p).cuda(), torch.from_numpy(cloud.T.copy()).cuda()).cpu().numpy()
+    want_ok, _ = ora.collision_filter(p, cloud.T)
+    assert len(set(np.nonzero(ok)[0]) ^ set(want_ok)) <= max(2, len(p) // 100)
+    p, s = p[ok], s[ok]
+    if p.shape[0] > 5:
+        pick = ora.importance_sampling(s, np.sort(rng.rand(5)))
+        p, s = p[pick], s[pick]
+    assert p.shape == poses.shape
+    np.testing.assert_allclose(scores, s, atol=1e-6)
+    np.testing.assert_allclose(poses, p, atol=1e-5)
