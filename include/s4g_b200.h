@@ -45,6 +45,9 @@ unsigned long long s4g_launch_count(void);
  * (block tree reduction, sampling_kernel.cu:100-113) exactly.  Requires N >= M > 0. */
 int s4g_farthest_point_sample_f32(const float* points, int B, int N, int M, int64_t* index, void* stream);
 int s4g_farthest_point_sample_f32_i32(const float* points, int B, int N, int M, int32_t* index, void* stream);
+/* Experimental: route clouds of 4 096 .. 55 000 points through the exact bucket-pruned FPS kernel (same results; slower
+ * than the default kernels on the measured workloads, see csrc/fps.cu).  Returns the previous setting. */
+int s4g_fps_set_bucket_mode(int on);
 
 /* gather_points — pointnet2_utils/functions.py:10-25.  out[b,c,m] = points[b,c,index[b,m]]. */
 int s4g_gather_points_f32(const float* points, const int64_t* index, int B, int C, int N, int M, float* out,

@@ -31,6 +31,7 @@ _SIGNATURES = {
     "s4g_launch_count": ([], ctypes.c_ulonglong),
     "s4g_farthest_point_sample_f32": ([_vp, _i, _i, _i, _vp, _vp], _i),
     "s4g_farthest_point_sample_f32_i32": ([_vp, _i, _i, _i, _vp, _vp], _i),
+    "s4g_fps_set_bucket_mode": ([_i], _i),
     "s4g_gather_points_f32": ([_vp, _vp, _i, _i, _i, _i, _vp, _vp], _i),
     "s4g_ball_query_f32": ([_vp, _vp, _i, _i, _i, _f, _i, _vp, _vp, _vp], _i),
     "s4g_ball_query_f32_i32": ([_vp, _vp, _i, _i, _i, _f, _i, _vp, _vp, _vp], _i),

@@ -232,3 +232,19 @@ def test_fps_large_clouds_bit_exact(ext, ora, kind, B, N, M):
     assert torch.equal(got.cpu(), ora.farthest_point_sample(pts, M))
     with pytest.raises(RuntimeError):
         ext.farthest_point_sample(torch.zeros(1, 3, 262145, device="cuda"), 4)
+
+
+@pytest.mark.parametrize("kind,B,N,M", [("uniform", 2, 5120, 1024), ("lattice", 2, 30000, 800), ("dup", 1, 26000, 1200),
+                                        ("identical", 2, 6000, 70), ("uniform", 3, 4097, 4097)])
+def test_fps_bucket_kernel_bit_exact(ext, ora, kind, B, N, M):
+    """the experimental bucket-pruned FPS kernel (s4g_fps_set_bucket_mode) gives the reference's indices too"""
+    from s4g_release_b200._lib import lib
+    pts = _gen(kind, B, N, seed=21)
+    want = ora.farthest_point_sample(pts, M)
+    old = lib.s4g_fps_set_bucket_mode(1)
+    try:
+        got = ext.farthest_point_sample(pts.cuda(), M)
+        torch.cuda.synchronize()
+    finally:
+        lib.s4g_fps_set_bucket_mode(old)
+    assert torch.equal(got.cpu(), want)
