@@ -136,6 +136,10 @@ int s4g_gather_xyz_f32_i32(const float* xyz, const int* index, int B, int N, int
 typedef struct s4g_chain s4g_chain;
 s4g_chain* s4g_chain_create(int n_layers, const int* cin, const int* cout, const int* relu, int in_mode, int feat_c,
                             int out_mode, int out_c, int group, int sigmoid);
+/* s4g_chain_create with the number of 32 KB activation slots pinned (0 = the planner's choice; the rest of shared
+ * memory becomes weight stages).  NULL if no deadlock-free plan exists with that count.  For host-side autotuning. */
+s4g_chain* s4g_chain_create_slots(int n_layers, const int* cin, const int* cout, const int* relu, int in_mode, int feat_c,
+                                  int out_mode, int out_c, int group, int sigmoid, int slots);
 void s4g_chain_destroy(s4g_chain* chain);
 size_t s4g_chain_weight_bytes(const s4g_chain* chain);
 int s4g_chain_cout_pad(const s4g_chain* chain, int layer);

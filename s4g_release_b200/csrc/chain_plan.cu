@@ -386,7 +386,7 @@ void evaluate(Candidate& c) {
 }  // namespace
 
 int plan_chain(s4g_chain* ch, int n_layers, const int* cin, const int* cout, const int* relu, int in_mode, int feat_c,
-               int out_mode, int out_c, int group, int sigmoid) {
+               int out_mode, int out_c, int group, int sigmoid, int force_slots) {
   memset(ch, 0, sizeof(*ch));
   S4G_CHECK_ARG(n_layers >= 1 && n_layers <= kMaxLayers, "mlp_chain: 1..%d layers supported", kMaxLayers);
   S4G_CHECK_ARG(in_mode == IN_ROWS || in_mode == IN_GATHER || in_mode == IN_XYZ_MLP, "mlp_chain: bad in_mode");
@@ -425,7 +425,11 @@ int plan_chain(s4g_chain* ch, int n_layers, const int* cin, const int* cout, con
 
   const int kSmemBudget = 227 * 1024 - 1024;  // barriers + TMEM slot live in the last KB
   Candidate best;
+  // force_slots > 0 restricts the search to that many activation slots (the rest of shared memory goes to weight
+  // stages): the simulation ranks slot counts imperfectly — the set-abstraction level 2 chain runs 23 % faster with 5
+  // slots than with the 3 it prefers — so the host can time the alternatives and pin the best (engine.py autotune)
   for (int S = kMaxSlots; S >= 2; --S) {
+    if (force_slots > 0 && S != force_slots) continue;
     int stages = (kSmemBudget - S * kSlotBytes) / kStageBytes;
     if (stages < 2) continue;
     stages = std::min(stages, kMaxStages);

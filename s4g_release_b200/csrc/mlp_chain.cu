@@ -783,6 +783,18 @@ extern "C" s4g_chain* s4g_chain_create(int n_layers, const int* cin, const int* 
   return ch;
 }
 
+// Same with the number of activation slots pinned (0 = the planner's choice); NULL when no plan exists with it.
+extern "C" s4g_chain* s4g_chain_create_slots(int n_layers, const int* cin, const int* cout, const int* relu, int in_mode,
+                                             int feat_c, int out_mode, int out_c, int group, int sigmoid, int slots) {
+  s4g_chain* ch = new (std::nothrow) s4g_chain;
+  if (!ch) return nullptr;
+  if (s4g::plan_chain(ch, n_layers, cin, cout, relu, in_mode, feat_c, out_mode, out_c, group, sigmoid, slots) != S4G_OK) {
+    delete ch;
+    return nullptr;
+  }
+  return ch;
+}
+
 extern "C" void s4g_chain_destroy(s4g_chain* ch) { delete ch; }
 
 extern "C" size_t s4g_chain_weight_bytes(const s4g_chain* ch) { return ch ? ch->w_bytes : 0; }
