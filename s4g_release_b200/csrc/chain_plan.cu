@@ -45,7 +45,9 @@ int round_up(int x, int m) { return (x + m - 1) / m * m; }
 // latency of single-accumulator layers gains (sa0 4.73 -> 4.27 ms); in wide chains the tile tail already overlaps the
 // next tile's first layer and the extra barrier traffic of a shared job costs more than the earlier hand-off
 // (head chain 1.635 -> 1.72 ms).
+thread_local int g_force_coop = -1;  // set by plan_chain for the duration of one planning call (host autotuning)
 int coop_policy() {
+  if (g_force_coop >= 0) return g_force_coop;
   const char* e = getenv("S4G_EPI_COOP");
   return e ? atoi(e) : 3;
 }
@@ -386,7 +388,11 @@ void evaluate(Candidate& c) {
 }  // namespace
 
 int plan_chain(s4g_chain* ch, int n_layers, const int* cin, const int* cout, const int* relu, int in_mode, int feat_c,
-               int out_mode, int out_c, int group, int sigmoid, int force_slots) {
+               int out_mode, int out_c, int group, int sigmoid, int force_slots, int force_pairs, int force_coop) {
+  struct CoopScope {  // force_coop: -1 = default policy, 0..2 = see coop_policy()
+    explicit CoopScope(int v) { g_force_coop = v; }
+    ~CoopScope() { g_force_coop = -1; }
+  } coop_scope(force_coop);
   memset(ch, 0, sizeof(*ch));
   S4G_CHECK_ARG(n_layers >= 1 && n_layers <= kMaxLayers, "mlp_chain: 1..%d layers supported", kMaxLayers);
   S4G_CHECK_ARG(in_mode == IN_ROWS || in_mode == IN_GATHER || in_mode == IN_XYZ_MLP, "mlp_chain: bad in_mode");
@@ -434,6 +440,7 @@ int plan_chain(s4g_chain* ch, int n_layers, const int* cin, const int* cout, con
     if (stages < 2) continue;
     stages = std::min(stages, kMaxStages);
     for (int pair_ok = 1; pair_ok >= 0; --pair_ok) {
+      if (force_pairs >= 0 && pair_ok != force_pairs) continue;  // -1 = both, 0 = N <= 128 only, 1 = N = 256 pairs
       for (int depth = 3; depth >= 1; --depth) {
         Candidate c;
         if (!build_draft(ch, relu, feat_c, S, pair_ok != 0, c.d)) continue;

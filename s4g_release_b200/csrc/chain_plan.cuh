@@ -158,5 +158,6 @@ struct s4g_chain {
 namespace s4g {
 // Plans the chain: fills ch->prm job streams, ring sizes, chunk sources.  Returns S4G_OK or sets the error.
 int plan_chain(s4g_chain* ch, int n_layers, const int* cin, const int* cout, const int* relu, int in_mode, int feat_c,
-               int out_mode, int out_c, int group, int sigmoid, int force_slots = 0);
+               int out_mode, int out_c, int group, int sigmoid, int force_slots = 0, int force_pairs = -1,
+               int force_coop = -1);
 }  // namespace s4g

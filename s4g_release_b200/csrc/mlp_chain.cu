@@ -783,16 +783,25 @@ extern "C" s4g_chain* s4g_chain_create(int n_layers, const int* cin, const int* 
   return ch;
 }
 
-// Same with the number of activation slots pinned (0 = the planner's choice); NULL when no plan exists with it.
-extern "C" s4g_chain* s4g_chain_create_slots(int n_layers, const int* cin, const int* cout, const int* relu, int in_mode,
-                                             int feat_c, int out_mode, int out_c, int group, int sigmoid, int slots) {
+// Same with planner decisions pinned, for host-side autotuning: slots = activation slots (0 = planner's choice),
+// pairs = -1 planner's choice / 0 no N = 256 accumulator pairs / 1 pairs only, coop = -1 default policy / 0 none /
+// 1 every row epilogue shared by all 16 warps / 2 the unpaired ones.  NULL when no plan exists under the constraints.
+extern "C" s4g_chain* s4g_chain_create_tuned(int n_layers, const int* cin, const int* cout, const int* relu, int in_mode,
+                                             int feat_c, int out_mode, int out_c, int group, int sigmoid, int slots,
+                                             int pairs, int coop) {
   s4g_chain* ch = new (std::nothrow) s4g_chain;
   if (!ch) return nullptr;
-  if (s4g::plan_chain(ch, n_layers, cin, cout, relu, in_mode, feat_c, out_mode, out_c, group, sigmoid, slots) != S4G_OK) {
+  if (s4g::plan_chain(ch, n_layers, cin, cout, relu, in_mode, feat_c, out_mode, out_c, group, sigmoid, slots, pairs,
+                      coop) != S4G_OK) {
     delete ch;
     return nullptr;
   }
   return ch;
+}
+
+extern "C" s4g_chain* s4g_chain_create_slots(int n_layers, const int* cin, const int* cout, const int* relu, int in_mode,
+                                             int feat_c, int out_mode, int out_c, int group, int sigmoid, int slots) {
+  return s4g_chain_create_tuned(n_layers, cin, cout, relu, in_mode, feat_c, out_mode, out_c, group, sigmoid, slots, -1, -1);
 }
 
 extern "C" void s4g_chain_destroy(s4g_chain* ch) { delete ch; }

@@ -104,18 +104,20 @@ class FusedPointNet2:
 
     def _make_chain(self, layers, in_mode, feat_c, out_mode, group=1, sigmoid=False):
         """Builds one chain.  The planner ranks the shared-memory splits (activation slots vs weight stages) with a
-        simulation that is only roughly calibrated, so with ``autotune`` the alternatives (3 / 4 / 5 slots) are timed
+        simulation that is only roughly calibrated, so with ``autotune`` the alternatives (3 / 4 / 5 slots, accumulator
+        pairs on / off, cooperative epilogues on / off) are timed
         once per chain shape on synthetic rows and the fastest is pinned (set-abstraction level 2: 3.6 -> 2.8 ms)."""
         sig = _chain_signature(layers, in_mode, feat_c, out_mode, group)
         if self.autotune and sig not in _TUNED_SLOTS:
             _TUNED_SLOTS[sig] = self._tune_slots(layers, in_mode, feat_c, out_mode, group, sigmoid)
-        return MlpChain(layers, self.device, in_mode, feat_c, out_mode, group=group, sigmoid=sigmoid,
-                        slots=_TUNED_SLOTS.get(sig, 0))
+        slots, pairs, coop = _TUNED_SLOTS.get(sig, (0, -1, -1))
+        return MlpChain(layers, self.device, in_mode, feat_c, out_mode, group=group, sigmoid=sigmoid, slots=slots,
+                        pairs=pairs, coop=coop)
 
     def _tune_slots(self, layers, in_mode, feat_c, out_mode, group, sigmoid):
         dev = self.device
         g = torch.Generator(device=dev).manual_seed(0)
-        tiles = 148 * 12  # 12 tiles per SM: steady state dominates
+        tiles = 148 * 48  # 48 tiles per SM: steady state dominates
         rows = tiles * 128
         if in_mode == IN_GATHER:
             K = group
@@ -123,21 +125,28 @@ class FusedPointNet2:
             N = 4 * M
             xyz = torch.rand(1, 3, N, device=dev, generator=g)
             ctr = xyz[:, :, :M].contiguous()
-            nbr = torch.randint(0, N, (1, M, K), device=dev, dtype=torch.int32, generator=g)
+            # neighbours are LOCAL in a real scene (ball query): indices near the centroid's own, not uniform over the cloud
+            near = torch.randint(0, 512, (1, M, K), device=dev, dtype=torch.int64, generator=g)
+            nbr = ((torch.arange(M, device=dev).view(1, M, 1) * (N // M) + near) % N).to(torch.int32)
             feat = torch.randn(N, feat_c, device=dev, generator=g).to(torch.bfloat16) if feat_c else None
             run = lambda ch: ch.run_gather(feat, xyz, ctr, nbr)
         else:
             x = torch.randn(rows, layers[0][0].shape[1], device=dev, generator=g).to(torch.bfloat16)
             n_points = rows if out_mode == OUT_LOGITS else 0
             run = lambda ch: ch.run_rows(x, n_points=n_points)
-        best, best_ms = 0, None
-        for slots in (0, 3, 4, 5):
+        best, best_ms = (0, -1, -1), None
+        seen = set()
+        candidates = [(0, -1, -1)] + [(sl, pr, co) for sl in (3, 4, 5) for pr in (1, 0) for co in (-1, 0, 2)]
+        for slots, pairs, coop in candidates:
             try:
-                ch = MlpChain(layers, dev, in_mode, feat_c, out_mode, group=group, sigmoid=sigmoid, slots=slots)
+                ch = MlpChain(layers, dev, in_mode, feat_c, out_mode, group=group, sigmoid=sigmoid, slots=slots,
+                              pairs=pairs, coop=coop)
             except RuntimeError:
-                continue  # no deadlock-free plan with that many slots
-            if slots and ch.info()["slots"] != slots:
+                continue  # no deadlock-free plan under these constraints
+            plan = ch.describe()
+            if plan in seen:  # different constraints, same job streams
                 continue
+            seen.add(plan)
             run(ch)
             ts = []
             for _ in range(3):
@@ -149,7 +158,7 @@ class FusedPointNet2:
                 ts.append(a.elapsed_time(b))
             ms = min(ts)
             if best_ms is None or ms < best_ms * 0.985:  # keep the planner's choice unless another is clearly faster
-                best, best_ms = slots, ms
+                best, best_ms = (slots, pairs, coop), ms
             del ch
         return best
 
