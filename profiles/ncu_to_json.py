@@ -1,6 +1,6 @@
 """ncu launch-list CSV -> JSON summary (the profiles/r01/ncu_launches_*.json files).
 
-    S4G_PROFILE_ITERS=2 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum,\
+    ncu --profile-from-start off --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum,\
 sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active,launch__registers_per_thread,launch__grid_size,\
 launch__block_size --clock-control none --csv --log-file gpurun_out/launches.csv python profiles/one_forward.py
     python profiles/ncu_to_json.py gpurun_out/launches.csv profiles/r01/ncu_launches_vN.json [launches per forward = 46]

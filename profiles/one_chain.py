@@ -1,5 +1,5 @@
 """One fused MLP chain of PN2_CLS at the BASELINE config[1] shape, for ncu captures:
-    ncu --set full --clock-control none --import-source on -k regex:mlp_chain -s 2 -c 1 -o gpurun_out/prof \
+    ncu --profile-from-start off --set full --clock-control none --import-source on -k regex:mlp_chain -c 1 -o gpurun_out/prof \
         python profiles/one_chain.py head0        (names: sa0 sa1 sa2 fp1 fp2 head0)"""
 import os
 import sys
@@ -38,4 +38,8 @@ else:
 for _ in range(3):
     run()
 torch.cuda.synchronize()
+torch.cuda.profiler.start()  # ncu --profile-from-start off: skip the autotuner's candidate launches
+run()
+torch.cuda.synchronize()
+torch.cuda.profiler.stop()
 print(name, ch.info())

@@ -1,7 +1,7 @@
 """One fused PN2_CLS forward at the BASELINE config[1] shape (64 scenes x 25 600 points) for ncu captures.
 
-    ncu --set full --clock-control none --import-source on -k regex:'mlp_chain|fps_kernel|ball_query|three_nn' \
-        -c 20 -o gpurun_out/prof python profiles/one_forward.py
+    ncu --profile-from-start off --metrics gpu__time_duration.sum,... --clock-control none --csv \
+        --log-file gpurun_out/launches.csv python profiles/one_forward.py          (see profiles/ncu_to_json.py)
 """
 import os
 import sys
@@ -20,4 +20,10 @@ scenes = base.repeat((B + base.shape[0] - 1) // base.shape[0], 1, 1)[:B].contigu
 for _ in range(int(os.environ.get("S4G_PROFILE_ITERS", "1"))):
     out = eng.forward(scenes)
 torch.cuda.synchronize()
+# the engine's autotuner launches hundreds of candidate chains while it is built: profile only this forward
+# (ncu --profile-from-start off)
+torch.cuda.profiler.start()
+out = eng.forward(scenes)
+torch.cuda.synchronize()
+torch.cuda.profiler.stop()
 print({k: tuple(v.shape) for k, v in out.items()})

@@ -149,7 +149,7 @@ class FusedPointNet2:
             seen.add(plan)
             run(ch)
             ts = []
-            for _ in range(3):
+            for _ in range(5):
                 a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 a.record()
                 run(ch)
@@ -157,7 +157,7 @@ class FusedPointNet2:
                 torch.cuda.synchronize(dev)
                 ts.append(a.elapsed_time(b))
             ms = min(ts)
-            if best_ms is None or ms < best_ms * 0.985:  # keep the planner's choice unless another is clearly faster
+            if best_ms is None or ms < best_ms * 0.97:  # keep the planner's choice unless another is clearly faster
                 best, best_ms = (slots, pairs, coop), ms
             del ch
         return best
