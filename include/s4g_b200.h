@@ -141,9 +141,11 @@ s4g_chain* s4g_chain_create(int n_layers, const int* cin, const int* cout, const
 s4g_chain* s4g_chain_create_slots(int n_layers, const int* cin, const int* cout, const int* relu, int in_mode, int feat_c,
                                   int out_mode, int out_c, int group, int sigmoid, int slots);
 /* ... and with the accumulator pairing (pairs: -1 planner's choice, 0 off, 1 on) and the cooperative-epilogue policy
- * (coop: -1 default, 0 none, 1 all row epilogues, 2 the unpaired ones) pinned as well. */
+ * (coop: -1 default, 0 none, 1 all row epilogues, 2 the unpaired ones) pinned as well; subs = row blocks of 128 rows
+ * per tile (1, or 2: two tiles interleaved layer by layer so one's MMAs overlap the other's epilogue — narrow chains). */
 s4g_chain* s4g_chain_create_tuned(int n_layers, const int* cin, const int* cout, const int* relu, int in_mode, int feat_c,
-                                  int out_mode, int out_c, int group, int sigmoid, int slots, int pairs, int coop);
+                                  int out_mode, int out_c, int group, int sigmoid, int slots, int pairs, int coop,
+                                  int subs);
 void s4g_chain_destroy(s4g_chain* chain);
 size_t s4g_chain_weight_bytes(const s4g_chain* chain);
 int s4g_chain_cout_pad(const s4g_chain* chain, int layer);

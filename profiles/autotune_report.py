@@ -9,4 +9,4 @@ eng = engine.FusedPointNet2(bench.seeded_model().cuda())
 torch.cuda.synchronize()
 print("engine build + autotune: %.2f s" % (time.time() - t0))
 for k, v in engine._TUNED_SLOTS.items():
-    print(" ", [c for c in k[0]], "in_mode", k[1], "feat_c", k[2], "out_mode", k[3], "-> (slots, pairs, coop) =", v)
+    print(" ", [c for c in k[0]], "in_mode", k[1], "feat_c", k[2], "out_mode", k[3], "-> (slots, pairs, coop, subs) =", v)

@@ -14,6 +14,17 @@ B = int(sys.argv[1]) if len(sys.argv) > 1 else 64
 TRACE = sys.argv[2].split(",") if len(sys.argv) > 2 else []
 net = seeded_model().cuda()
 eng = FusedPointNet2(net)
+if os.environ.get("S4G_PROF_PLAN"):  # "slots,pairs,coop,subs": rebuild the set-abstraction chains under these constraints
+    from s4g_release_b200.chain import IN_GATHER, OUT_MAXPOOL, MlpChain
+    sl, pr, co, su = [int(v) for v in os.environ["S4G_PROF_PLAN"].split(",")]
+    fc = 0
+    for i, layers in enumerate(eng.sa):
+        try:
+            eng.sa_chains[i] = MlpChain([(w, b, True) for w, b in layers], "cuda", IN_GATHER, fc, OUT_MAXPOOL,
+                                        group=eng.cfg["num_neighbours"][i], slots=sl, pairs=pr, coop=co, subs=su)
+        except RuntimeError:
+            pass
+        fc = layers[-1][0].shape[0]
 cfg = eng.cfg
 dev = "cuda"
 g = torch.Generator(device=dev).manual_seed(0)

@@ -24,7 +24,7 @@ class MlpChain:
     loader warps cannot issue the 49 k FMAs of a tile as fast as the rest of the tile runs."""
 
     def __init__(self, layers, device, in_mode=IN_ROWS, feat_c=0, out_mode=OUT_ROWS, group=1, sigmoid=False,
-                 xyz_layer_on_cuda_cores=False, slots=0, pairs=-1, coop=-1):
+                 xyz_layer_on_cuda_cores=False, slots=0, pairs=-1, coop=-1, subs=1):
         self.device = torch.device(device)
         self.all_cin = [int(w.shape[1]) for w, _, _ in layers]
         self.all_cout = [int(w.shape[0]) for w, _, _ in layers]
@@ -45,7 +45,7 @@ class MlpChain:
         relu = [1 if r else 0 for _, _, r in layers]
         self._h = lib.s4g_chain_create_tuned(self.n_layers, _int_array(self.cin), _int_array(self.cout), _int_array(relu),
                                              in_mode, feat_c, out_mode, self.out_c, group, 1 if sigmoid else 0, int(slots),
-                                             int(pairs), int(coop))
+                                             int(pairs), int(coop), int(subs))
         if not self._h:
             raise RuntimeError("s4g_chain_create failed: " + lib.s4g_last_error().decode())
         nbytes = lib.s4g_chain_weight_bytes(self._h)

@@ -26,8 +26,8 @@ constexpr double kIssuePerMma = 20.0;
 
 struct Block { int kind, c_begin, c_count, layer; };
 struct HMma { int blk, acc, k16, koff, n_rows, flags, layer, n_begin, k_begin, n_mma; };
-struct HEpi { int kind, acc, blk, layer, relu, c_begin, c_count, aux, pred, same, min_it, coop; };
-struct HLoad { int kind, blk, c_begin, c_count, pred, same, min_it; };
+struct HEpi { int kind, acc, blk, layer, relu, c_begin, c_count, aux, pred, same, min_it, coop, sub; };
+struct HLoad { int kind, blk, c_begin, c_count, pred, same, min_it, sub; };
 
 struct Draft {
   int S = 0, stages = 0, n_acc = 0, depth = 0;
@@ -52,7 +52,10 @@ int coop_policy() {
   return e ? atoi(e) : 3;
 }
 
-bool build_draft(const s4g_chain* ch, const int* relu, int feat_c, int S, bool pair_ok, Draft& d) {
+// R = row blocks (sub-tiles of 128 rows) per tile.  With R = 2 every layer is emitted for sub-tile 0, then for sub-tile
+// 1: the job streams of two 128-row tiles interleaved layer by layer, so that the MMAs of one run while the epilogue
+// of the other drains — for narrow chains, whose tile is otherwise a strict MMA -> epilogue -> MMA ping-pong.
+bool build_draft(const s4g_chain* ch, const int* relu, int feat_c, int S, bool pair_ok, int R, Draft& d) {
   const int L = ch->n_layers;
   std::vector<Block> in_desc;
   if (ch->in_mode == IN_ROWS) {
@@ -63,7 +66,7 @@ bool build_draft(const s4g_chain* ch, const int* relu, int feat_c, int S, bool p
     for (int c = 0; c < feat_c; c += 128) in_desc.push_back({WK_LOAD_FEAT, c, std::min(128, feat_c - c), -1});
     in_desc.push_back({WK_LOAD_XYZ, feat_c, 16, -1});
   }
-  std::vector<int> cur;
+  std::vector<int> cur_sub[2];
   int n_maxpool = 0;
   for (int l = 0; l < L; ++l) {
     const bool last = (l == L - 1);
@@ -72,7 +75,7 @@ bool build_draft(const s4g_chain* ch, const int* relu, int feat_c, int S, bool p
     std::vector<std::pair<int, int>> nbs;
     for (int n = 0; n < width; n += 128) nbs.push_back({n, std::min(128, width - n)});
     const int nn = (int)nbs.size();
-    const int nk = (l == 0) ? (int)in_desc.size() : (int)cur.size();
+    const int nk = (l == 0) ? (int)in_desc.size() : (int)cur_sub[0].size();
     // N-outer (one output block after the other, each over all K-blocks; the epilogue of block n overlaps
     // the MMAs of block n+1) needs every K-block and all but the last output block resident at once;
     // otherwise K-outer: up to 4 accumulators filled K-block by K-block, inputs released as they go.
@@ -84,16 +87,36 @@ bool build_draft(const s4g_chain* ch, const int* relu, int feat_c, int S, bool p
     if (!n_outer && l > 0 && nn > kAccBlocks) return false;  // a hidden layer cannot be re-read in passes
     if (!n_outer && !last && nn > S) return false;
     const int passes = n_outer ? 1 : (nn + kAccBlocks - 1) / kAccBlocks;
+    // With two row blocks the input blocks of BOTH come first in the block order.  The slot protocol waits with a
+    // one-bit phase ("the release of block pred in the previous tile"), which is only unambiguous if block pred of the
+    // CURRENT tile cannot be released before that wait is made; an epilogue-produced block whose slot predecessor
+    // is a loader-produced block of higher index would break that (the loader and the MMA warp run ahead of the
+    // epilogue).  Inputs first + S <= blocks per tile rules it out, as in the single-block order.
+    std::vector<int> kin_pre[2];
+    if (l == 0 && R > 1) {
+      if (passes != 1) return false;
+      for (int sub = 0; sub < R; ++sub)
+        for (const Block& b : in_desc) {
+          const int idx = (int)d.blocks.size();
+          d.blocks.push_back(b);
+          d.loads.push_back({b.kind, idx, b.c_begin, b.c_count, 0, 0, 0, sub});
+          kin_pre[sub].push_back(idx);
+        }
+    }
+    for (int sub = 0; sub < R; ++sub) {
+    std::vector<int>& cur = cur_sub[sub];
     std::vector<int> produced;
     for (int pass = 0; pass < passes; ++pass) {
       const int nb0 = n_outer ? 0 : pass * kAccBlocks;
       const int nb1 = n_outer ? nn : std::min(nn, nb0 + kAccBlocks);
       std::vector<int> kin;
-      if (l == 0) {
+      if (l == 0 && R > 1) {
+        kin = kin_pre[sub];
+      } else if (l == 0) {
         for (const Block& b : in_desc) {
           const int idx = (int)d.blocks.size();
           d.blocks.push_back(b);
-          d.loads.push_back({b.kind, idx, b.c_begin, b.c_count, 0, 0, 0});
+          d.loads.push_back({b.kind, idx, b.c_begin, b.c_count, 0, 0, 0, sub});
           kin.push_back(idx);
         }
       } else {
@@ -154,15 +177,16 @@ bool build_draft(const s4g_chain* ch, const int* relu, int feat_c, int S, bool p
           const int idx = (int)d.blocks.size();
           d.blocks.push_back({WK_EPI_HIDDEN, nbs[nb].first, nbs[nb].second, l});
           produced.push_back(idx);
-          d.epi.push_back({WK_EPI_HIDDEN, acc, idx, l, relu[l], nbs[nb].first, nbs[nb].second, 0, 0, 0, 0, coop});
+          d.epi.push_back({WK_EPI_HIDDEN, acc, idx, l, relu[l], nbs[nb].first, nbs[nb].second, 0, 0, 0, 0, coop, sub});
         } else {
           const int kind = ch->out_mode == OUT_ROWS ? WK_EPI_ROWS : ch->out_mode == OUT_MAXPOOL ? WK_EPI_MAXPOOL : WK_EPI_LOGITS;
           d.epi.push_back({kind, acc, -1, l, relu[l], nbs[nb].first, nbs[nb].second, (n_maxpool++) & 1, 0, 0, 0,
-                           kind == WK_EPI_ROWS ? coop : 0});
+                           kind == WK_EPI_ROWS ? coop : 0, sub});
         }
       }
     }
     cur = produced;
+    }
   }
   d.S = S;
   // slot re-use: block b of tile t inherits the slot of block (t * nB + b - S); see chain_plan.cuh
@@ -388,7 +412,8 @@ void evaluate(Candidate& c) {
 }  // namespace
 
 int plan_chain(s4g_chain* ch, int n_layers, const int* cin, const int* cout, const int* relu, int in_mode, int feat_c,
-               int out_mode, int out_c, int group, int sigmoid, int force_slots, int force_pairs, int force_coop) {
+               int out_mode, int out_c, int group, int sigmoid, int force_slots, int force_pairs, int force_coop, int subs) {
+  S4G_CHECK_ARG(subs == 1 || subs == 2, "mlp_chain: 1 or 2 row blocks per tile");
   struct CoopScope {  // force_coop: -1 = default policy, 0..2 = see coop_policy()
     explicit CoopScope(int v) { g_force_coop = v; }
     ~CoopScope() { g_force_coop = -1; }
@@ -443,7 +468,7 @@ int plan_chain(s4g_chain* ch, int n_layers, const int* cin, const int* cout, con
       if (force_pairs >= 0 && pair_ok != force_pairs) continue;  // -1 = both, 0 = N <= 128 only, 1 = N = 256 pairs
       for (int depth = 3; depth >= 1; --depth) {
         Candidate c;
-        if (!build_draft(ch, relu, feat_c, S, pair_ok != 0, c.d)) continue;
+        if (!build_draft(ch, relu, feat_c, S, pair_ok != 0, subs, c.d)) continue;
         if (pair_ok && (c.d.n_acc & 1)) continue;  // pairs need tile-invariant accumulator parity
         c.d.stages = stages;
         c.d.depth = depth;
@@ -470,7 +495,7 @@ int plan_chain(s4g_chain* ch, int n_layers, const int* cin, const int* cout, con
   for (int j = 0; j < p.n_ld; ++j) {
     const HLoad& l = d.loads[j];
     p.ld[j] = {(uint8_t)l.kind, (uint8_t)l.same, (uint8_t)(l.blk % S), (uint8_t)(l.blk / S), 0, 0, 0, (uint8_t)l.pred,
-               (uint16_t)l.c_begin, (uint16_t)l.c_count, (uint8_t)l.min_it, 0, {0, 0}};
+               (uint16_t)l.c_begin, (uint16_t)l.c_count, (uint8_t)l.min_it, 0, (uint8_t)l.sub, {0}};
   }
   p.load_depth = std::max(1, d.depth);
   p.n_ep = (int)d.epi.size();
@@ -479,7 +504,7 @@ int plan_chain(s4g_chain* ch, int n_layers, const int* cin, const int* cout, con
     const int blk = e.blk < 0 ? 0 : e.blk;
     p.ep[j] = {(uint8_t)e.kind, (uint8_t)e.same, (uint8_t)(blk % S), (uint8_t)(blk / S), (uint8_t)e.acc, (uint8_t)e.layer,
                (uint8_t)e.relu, (uint8_t)e.pred, (uint16_t)e.c_begin, (uint16_t)e.c_count, (uint8_t)e.min_it,
-               (uint8_t)e.coop, {0, 0}};
+               (uint8_t)e.coop, (uint8_t)e.sub, {0}};
   }
   const int nB = (int)d.blocks.size();
   p.n_act_mod = nB % S;
@@ -488,6 +513,7 @@ int plan_chain(s4g_chain* ch, int n_layers, const int* cin, const int* cout, con
   p.slots = S;
   p.stages = d.stages;
   p.in_mode = in_mode;
+  p.subs = subs;
   p.feat_c = feat_c;
   p.out_c = out_c;
   p.group = group > 0 ? group : 1;

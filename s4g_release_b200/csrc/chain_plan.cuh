@@ -101,7 +101,8 @@ struct WorkerJob {
   uint16_t c_count;  // channels / columns in the block (multiple of 8 for loads, of 16 for epilogues)
   uint8_t min_it;    // producers, same == 0: first tile iteration of the CTA at which a previous block exists
   uint8_t coop;      // EPI_HIDDEN / EPI_ROWS: 1 = all 16 epilogue warps drain this accumulator (32 columns each)
-  uint8_t pad[2];
+  uint8_t sub;       // row block (sub-tile of 128 rows) of the tile this job works on: 0, or 1 when the tile has two
+  uint8_t pad[1];
 };
 
 struct ChainParams {
@@ -113,6 +114,7 @@ struct ChainParams {
   int n_acc;                 // accumulators per tile
   int slots, stages;
   int load_depth;            // cp.async input blocks a loader thread keeps in flight (1..3)
+  int subs;                  // row blocks per tile (1 or 2): a tile is 128 * subs rows
   const void* weights;       // packed chunk stream of one tile, in MMA-job order
   const float* bias[kMaxLayers];
   int P;                     // rows (positions)
@@ -159,5 +161,5 @@ namespace s4g {
 // Plans the chain: fills ch->prm job streams, ring sizes, chunk sources.  Returns S4G_OK or sets the error.
 int plan_chain(s4g_chain* ch, int n_layers, const int* cin, const int* cout, const int* relu, int in_mode, int feat_c,
                int out_mode, int out_c, int group, int sigmoid, int force_slots = 0, int force_pairs = -1,
-               int force_coop = -1);
+               int force_coop = -1, int subs = 1);
 }  // namespace s4g

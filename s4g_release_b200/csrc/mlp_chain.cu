@@ -229,7 +229,8 @@ __global__ void __launch_bounds__(kChainThreads, 1) mlp_chain_kernel(const __gri
 
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);  // warp-uniform for the compiler
   const int lane = threadIdx.x & 31;
-  const int n_tiles = (p.P + kTileRows - 1) / kTileRows;
+  const int tile_rows = kTileRows * p.subs;  // a tile = 1 or 2 row blocks of 128 rows (WorkerJob::sub)
+  const int n_tiles = (p.P + tile_rows - 1) / tile_rows;
   const int n_my = ((int)blockIdx.x < n_tiles) ? (n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
 
   if (threadIdx.x == 0) {
@@ -403,16 +404,20 @@ __global__ void __launch_bounds__(kChainThreads, 1) mlp_chain_kernel(const __gri
     const int per_b = p.M * p.K;
     const int D = p.load_depth;
     Ring base = {0, 0u};
-    int jn[2] = {0, 0}, jn_next[2] = {0, 0};  // neighbour index of the two rows in the current / next tile (gather mode)
-    auto tile_row = [&](int jt, int h) -> long long {
-      return ((long long)blockIdx.x + (long long)jt * gridDim.x) * kTileRows + r + 64 * h;
+    // neighbour index of this thread's two rows of each row block, current / next tile (gather mode): [2 * sub + h]
+    int jn[4] = {0, 0, 0, 0}, jn_next[4] = {0, 0, 0, 0};
+    auto tile_row = [&](int jt, int h, int sub) -> long long {
+      return ((long long)blockIdx.x + (long long)jt * gridDim.x) * tile_rows + sub * kTileRows + r + 64 * h;
     };
-    auto load_nbr = [&](int jt, int h) -> int {
-      if (jt >= n_my) return 0;
-      const long long row = tile_row(jt, h);
+    auto load_nbr = [&](int jt, int h, int sub) -> int {
+      if (jt >= n_my || sub >= p.subs) return 0;
+      const long long row = tile_row(jt, h, sub);
       return row < p.P ? __ldg(p.nbr + row) : 0;
     };
-    if constexpr (GATHER) { jn_next[0] = load_nbr(0, 0); jn_next[1] = load_nbr(0, 1); }
+    if constexpr (GATHER) {
+#pragma unroll
+      for (int q = 0; q < 4; ++q) jn_next[q] = load_nbr(0, q & 1, q >> 1);
+    }
     // slots of the cp.async blocks issued and not yet published, oldest first (one commit group each)
     int pend0 = 0, pend1 = 0, pend2 = 0, npend = 0;
     auto publish_oldest = [&]() {
@@ -425,8 +430,8 @@ __global__ void __launch_bounds__(kChainThreads, 1) mlp_chain_kernel(const __gri
     const long long t_begin = tick<PROF>();
     for (int it = 0; it < n_my; ++it) {
       if constexpr (GATHER) {
-        jn[0] = jn_next[0]; jn[1] = jn_next[1];
-        jn_next[0] = load_nbr(it + 1, 0); jn_next[1] = load_nbr(it + 1, 1);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) { jn[q] = jn_next[q]; jn_next[q] = load_nbr(it + 1, q & 1, q >> 1); }
       }
       for (int j = 0; j < p.n_ld; ++j) {
         const WorkerJob job = p.ld[j];
@@ -459,16 +464,17 @@ __global__ void __launch_bounds__(kChainThreads, 1) mlp_chain_kernel(const __gri
           float dx[2], dy[2], dz[2];
 #pragma unroll
           for (int h = 0; h < 2; ++h) {
-            const long long row = tile_row(it, h);
+            const long long row = tile_row(it, h, job.sub);
             dx[h] = dy[h] = dz[h] = 0.f;
             if (row < p.P) {
               const int b = (int)(row / per_b);
               const int m = (int)((row - (long long)b * per_b) / p.K);
               const float* X = p.xyz + (long long)b * 3 * p.N;
               const float* C = p.ctr + (long long)b * 3 * p.M;
-              dx[h] = __fsub_rn(__ldg(X + jn[h]), __ldg(C + m));
-              dy[h] = __fsub_rn(__ldg(X + p.N + jn[h]), __ldg(C + p.M + m));
-              dz[h] = __fsub_rn(__ldg(X + 2 * p.N + jn[h]), __ldg(C + 2 * p.M + m));
+              const int jq = job.sub ? jn[2 + h] : jn[h];
+              dx[h] = __fsub_rn(__ldg(X + jq), __ldg(C + m));
+              dy[h] = __fsub_rn(__ldg(X + p.N + jq), __ldg(C + p.M + m));
+              dz[h] = __fsub_rn(__ldg(X + 2 * p.N + jq), __ldg(C + 2 * p.M + m));
             }
           }
           uint8_t* sb = slots + (size_t)slot * kSlotBytes + (size_t)r * 16;
@@ -506,9 +512,10 @@ __global__ void __launch_bounds__(kChainThreads, 1) mlp_chain_kernel(const __gri
         // L2 bulk prefetch of the next tile's rows changed nothing: the stall at a tile start is slot-bound.)
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
-          const long long row = tile_row(it, h);
+          const long long row = tile_row(it, h, job.sub);
           const bool valid = row < p.P;
           const long long rr = valid ? row : 0;
+          const int jq = job.sub ? jn[2 + h] : jn[h];
           uint8_t* sbase = slots + (size_t)slot * kSlotBytes + (size_t)(r + 64 * h) * 16;
           if (GATHER && job.kind == WK_LOAD_XYZ) {
             float xa = 0.f, xb = 0.f, xc = 0.f;
@@ -517,9 +524,9 @@ __global__ void __launch_bounds__(kChainThreads, 1) mlp_chain_kernel(const __gri
               const int m = (int)((rr - (long long)b * per_b) / p.K);
               const float* X = p.xyz + (long long)b * 3 * p.N;
               const float* C = p.ctr + (long long)b * 3 * p.M;
-              xa = __fsub_rn(__ldg(X + jn[h]), __ldg(C + m));
-              xb = __fsub_rn(__ldg(X + p.N + jn[h]), __ldg(C + p.M + m));
-              xc = __fsub_rn(__ldg(X + 2 * p.N + jn[h]), __ldg(C + 2 * p.M + m));
+              xa = __fsub_rn(__ldg(X + jq), __ldg(C + m));
+              xb = __fsub_rn(__ldg(X + p.N + jq), __ldg(C + p.M + m));
+              xc = __fsub_rn(__ldg(X + 2 * p.N + jq), __ldg(C + 2 * p.M + m));
             }
             __nv_bfloat162 h0 = __floats2bfloat162_rn(xa, xb), h1 = __floats2bfloat162_rn(xc, 0.f);
             *reinterpret_cast<uint4*>(sbase) =
@@ -531,7 +538,7 @@ __global__ void __launch_bounds__(kChainThreads, 1) mlp_chain_kernel(const __gri
               src = reinterpret_cast<const __nv_bfloat16*>(p.in_rows) + rr * (long long)p.in_stride + job.c_begin;
             } else {
               const int b = (int)(rr / per_b);
-              src = reinterpret_cast<const __nv_bfloat16*>(p.feat) + ((long long)b * p.N + jn[h]) * p.feat_c + job.c_begin;
+              src = reinterpret_cast<const __nv_bfloat16*>(p.feat) + ((long long)b * p.N + jq) * p.feat_c + job.c_begin;
             }
             const int pieces = job.c_count >> 3;
 #pragma unroll 4
@@ -582,9 +589,10 @@ __global__ void __launch_bounds__(kChainThreads, 1) mlp_chain_kernel(const __gri
     long long c_full = 0, c_free = 0, c_epi = 0;
     const long long t_begin = tick<PROF>();
     for (int it = 0; it < n_my; ++it) {
-      const long long row = ((long long)blockIdx.x + (long long)it * gridDim.x) * kTileRows + erow;
+      const long long row0 = ((long long)blockIdx.x + (long long)it * gridDim.x) * tile_rows + erow;
       for (int j = 0; j < p.n_ep; ++j) {
         const WorkerJob job = p.ep[j];
+        const long long row = row0 + (long long)job.sub * kTileRows;
         const unsigned q = base_q + job.acc;
         const bool coop = job.coop != 0;  // all 16 warps: 32 columns each; else the 8 warps of group q % 2: 64 each
         if (!coop && (int)(q & 1u) != grp) continue;
@@ -687,7 +695,7 @@ __global__ void __launch_bounds__(kChainThreads, 1) mlp_chain_kernel(const __gri
           const float b = ch < p.out_c ? __ldg(p.bias[job.layer] + ch) : 0.f;
           __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(p.out);
           const long long n_groups = p.P / G;
-          const long long tile_g0 = (((long long)blockIdx.x + (long long)it * gridDim.x) * kTileRows) / G;
+          const long long tile_g0 = (((long long)blockIdx.x + (long long)it * gridDim.x) * tile_rows + job.sub * kTileRows) / G;
           float v0[32], v1[32];
           tmem_ld32_issue(t_addr, v0);
           tmem_ld32_issue(t_addr + 32u, v1);
@@ -785,14 +793,15 @@ extern "C" s4g_chain* s4g_chain_create(int n_layers, const int* cin, const int* 
 
 // Same with planner decisions pinned, for host-side autotuning: slots = activation slots (0 = planner's choice),
 // pairs = -1 planner's choice / 0 no N = 256 accumulator pairs / 1 pairs only, coop = -1 default policy / 0 none /
-// 1 every row epilogue shared by all 16 warps / 2 the unpaired ones.  NULL when no plan exists under the constraints.
+// 1 every row epilogue shared by all 16 warps / 2 the unpaired ones, subs = row blocks (128 rows) per tile: 1, or 2 =
+// two tiles interleaved layer by layer.  NULL when no plan exists under the constraints.
 extern "C" s4g_chain* s4g_chain_create_tuned(int n_layers, const int* cin, const int* cout, const int* relu, int in_mode,
                                              int feat_c, int out_mode, int out_c, int group, int sigmoid, int slots,
-                                             int pairs, int coop) {
+                                             int pairs, int coop, int subs) {
   s4g_chain* ch = new (std::nothrow) s4g_chain;
   if (!ch) return nullptr;
   if (s4g::plan_chain(ch, n_layers, cin, cout, relu, in_mode, feat_c, out_mode, out_c, group, sigmoid, slots, pairs,
-                      coop) != S4G_OK) {
+                      coop, subs) != S4G_OK) {
     delete ch;
     return nullptr;
   }
@@ -801,7 +810,7 @@ extern "C" s4g_chain* s4g_chain_create_tuned(int n_layers, const int* cin, const
 
 extern "C" s4g_chain* s4g_chain_create_slots(int n_layers, const int* cin, const int* cout, const int* relu, int in_mode,
                                              int feat_c, int out_mode, int out_c, int group, int sigmoid, int slots) {
-  return s4g_chain_create_tuned(n_layers, cin, cout, relu, in_mode, feat_c, out_mode, out_c, group, sigmoid, slots, -1, -1);
+  return s4g_chain_create_tuned(n_layers, cin, cout, relu, in_mode, feat_c, out_mode, out_c, group, sigmoid, slots, -1, -1, 1);
 }
 
 extern "C" void s4g_chain_destroy(s4g_chain* ch) { delete ch; }
@@ -910,7 +919,8 @@ static int launch_chain(const ChainParams& p, int grid, size_t smem, cudaStream_
 static int s4g_chain_launch(const s4g_chain* ch, s4g::ChainParams& p, cudaStream_t stream) {
   S4G_CHECK_ARG(p.weights != nullptr, "mlp_chain: s4g_chain_set_params was not called");
   if (p.P <= 0) return S4G_OK;
-  const int tiles = (p.P + s4g::kTileRows - 1) / s4g::kTileRows;
+  const int tile_rows = s4g::kTileRows * p.subs;
+  const int tiles = (p.P + tile_rows - 1) / tile_rows;
   const int grid = tiles < s4g::num_sms() ? tiles : s4g::num_sms();
   const bool gather = p.in_mode != s4g::IN_ROWS, xyz = p.in_mode == s4g::IN_XYZ_MLP, prof = p.prof != nullptr;
   S4G_CHECK_ARG(!(xyz && prof), "mlp_chain: the cycle counters are not built for IN_XYZ_MLP chains");

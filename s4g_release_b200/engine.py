@@ -105,14 +105,14 @@ class FusedPointNet2:
     def _make_chain(self, layers, in_mode, feat_c, out_mode, group=1, sigmoid=False):
         """Builds one chain.  The planner ranks the shared-memory splits (activation slots vs weight stages) with a
         simulation that is only roughly calibrated, so with ``autotune`` the alternatives (3 / 4 / 5 slots, accumulator
-        pairs on / off, cooperative epilogues on / off) are timed
+        pairs on / off, cooperative epilogues on / off, one or two row blocks per tile) are timed
         once per chain shape on synthetic rows and the fastest is pinned (set-abstraction level 2: 3.6 -> 2.8 ms)."""
         sig = _chain_signature(layers, in_mode, feat_c, out_mode, group)
         if self.autotune and sig not in _TUNED_SLOTS:
             _TUNED_SLOTS[sig] = self._tune_slots(layers, in_mode, feat_c, out_mode, group, sigmoid)
-        slots, pairs, coop = _TUNED_SLOTS.get(sig, (0, -1, -1))
+        slots, pairs, coop, subs = _TUNED_SLOTS.get(sig, (0, -1, -1, 1))
         return MlpChain(layers, self.device, in_mode, feat_c, out_mode, group=group, sigmoid=sigmoid, slots=slots,
-                        pairs=pairs, coop=coop)
+                        pairs=pairs, coop=coop, subs=subs)
 
     def _tune_slots(self, layers, in_mode, feat_c, out_mode, group, sigmoid):
         dev = self.device
@@ -134,13 +134,16 @@ class FusedPointNet2:
             x = torch.randn(rows, layers[0][0].shape[1], device=dev, generator=g).to(torch.bfloat16)
             n_points = rows if out_mode == OUT_LOGITS else 0
             run = lambda ch: ch.run_rows(x, n_points=n_points)
-        best, best_ms = (0, -1, -1), None
+        best, best_ms = (0, -1, -1, 1), None
         seen = set()
-        candidates = [(0, -1, -1)] + [(sl, pr, co) for sl in (3, 4, 5) for pr in (1, 0) for co in (-1, 0, 2)]
-        for slots, pairs, coop in candidates:
+        candidates = [(0, -1, -1, 1)] + [(sl, pr, co, 1) for sl in (3, 4, 5) for pr in (1, 0) for co in (-1, 0, 2)]
+        # two row blocks per tile (two 128-row tiles interleaved layer by layer): only narrow chains have the shared
+        # memory for it; the planner refuses the others
+        candidates += [(sl, -1, co, 2) for sl in (0, 3, 4, 5) for co in (-1, 0, 1)]
+        for slots, pairs, coop, subs in candidates:
             try:
                 ch = MlpChain(layers, dev, in_mode, feat_c, out_mode, group=group, sigmoid=sigmoid, slots=slots,
-                              pairs=pairs, coop=coop)
+                              pairs=pairs, coop=coop, subs=subs)
             except RuntimeError:
                 continue  # no deadlock-free plan under these constraints
             plan = ch.describe()
@@ -158,7 +161,7 @@ class FusedPointNet2:
                 ts.append(a.elapsed_time(b))
             ms = min(ts)
             if best_ms is None or ms < best_ms * 0.97:  # keep the planner's choice unless another is clearly faster
-                best, best_ms = (slots, pairs, coop), ms
+                best, best_ms = (slots, pairs, coop, subs), ms
             del ch
         return best
 

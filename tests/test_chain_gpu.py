@@ -143,3 +143,63 @@ def test_fp_front_end(Nq, Nk):
     want = ora.interpolate_forward(sparse.reshape(B, Nk, C2).transpose(1, 2).contiguous(), o_idx, w.cpu())
     _check(out[:, :C2], _bf(want.transpose(1, 2).reshape(B * Nq, C2)), tol=1e-2)
     assert torch.equal(out[:, C2:].float().cpu(), dense)
+
+
+def _two_block_chain(*args, **kw):
+    """MlpChain with two row blocks per tile, or None when no plan fits (wide chains)."""
+    from s4g_release_b200.chain import MlpChain
+    try:
+        return MlpChain(*args, subs=2, **kw)
+    except RuntimeError:
+        return None
+
+
+@pytest.mark.parametrize("dims,P", [([64, 64, 64], 256), ([64, 64, 64], 700), ([32, 16, 32], 77), ([128, 128, 128, 64], 1300),
+                                    ([64, 64], 129), ([256, 128, 128], 513)])
+def test_two_row_blocks_per_tile_rows(dims, P):
+    """tiles of 2 x 128 rows, the two blocks interleaved layer by layer (WorkerJob::sub): same results, ragged tails"""
+    layers = _layers(dims, seed=sum(dims) + 3)
+    x = _bf(torch.randn(P, dims[0], generator=torch.Generator().manual_seed(P)))
+    ch = _two_block_chain(layers, "cuda")
+    assert ch is not None
+    got = ch.run_rows(x.cuda().to(torch.bfloat16))
+    torch.cuda.synchronize()
+    _check(got, _bf(_ref_chain(x, layers)))
+
+
+@pytest.mark.parametrize("feat_c,dims,B,N,M,K", [(0, [128, 128, 256], 2, 2048, 256, 64), (0, [128, 128, 256], 1, 3000, 333, 64),
+                                                  (64, [64, 64, 128], 2, 1024, 65, 16), (32, [32, 64], 3, 300, 50, 8)])
+def test_two_row_blocks_per_tile_gather_maxpool(feat_c, dims, B, N, M, K):
+    from s4g_release_b200.chain import IN_GATHER, OUT_MAXPOOL
+    g = torch.Generator().manual_seed(feat_c + M)
+    layers = _layers([feat_c + 3] + dims, seed=M, scale=2.0)
+    xyz = torch.rand(B, 3, N, generator=g)
+    sel = torch.stack([torch.randperm(N, generator=g)[:M] for _ in range(B)])
+    ctr = torch.gather(xyz, 2, sel.unsqueeze(1).expand(-1, 3, -1)).contiguous()
+    nbr = torch.randint(0, N, (B, M, K), generator=g, dtype=torch.int32)
+    feat = _bf(torch.randn(B * N, feat_c, generator=g)) if feat_c else None
+    ch = _two_block_chain(layers, "cuda", IN_GATHER, feat_c, OUT_MAXPOOL, group=K)
+    assert ch is not None
+    got = ch.run_gather(feat.cuda().to(torch.bfloat16) if feat_c else None, xyz.cuda(), ctr.cuda(), nbr.cuda())
+    torch.cuda.synchronize()
+    idx = nbr.long().reshape(B, M * K)
+    gx = torch.gather(xyz.transpose(1, 2), 1, idx.unsqueeze(-1).expand(-1, -1, 3)).reshape(B, M, K, 3)
+    x = _bf(gx - ctr.transpose(1, 2).unsqueeze(2))
+    if feat_c:
+        gf = torch.gather(feat.reshape(B, N, feat_c), 1, idx.unsqueeze(-1).expand(-1, -1, feat_c)).reshape(B, M, K, feat_c)
+        x = torch.cat([x, gf], dim=-1)
+    want = _ref_chain(x.reshape(-1, feat_c + 3), layers).reshape(B * M, K, -1).max(dim=1)[0]
+    _check(got, _bf(want))
+
+
+def test_two_row_blocks_logits_head():
+    from s4g_release_b200.chain import IN_ROWS, OUT_LOGITS
+    dims, n_out, B, n_points = [64, 32], 5, 3, 1000
+    layers = _layers(dims + [n_out], seed=5, relu_last=False)
+    x = _bf(torch.randn(B * n_points, dims[0], generator=torch.Generator().manual_seed(1)))
+    ch = _two_block_chain(layers, "cuda", IN_ROWS, 0, OUT_LOGITS, sigmoid=True)
+    assert ch is not None
+    got = ch.run_rows(x.cuda().to(torch.bfloat16), n_points=n_points)
+    torch.cuda.synchronize()
+    want = torch.sigmoid(_ref_chain(x, layers)).reshape(B, n_points, n_out).transpose(1, 2)
+    _check(got, want)
