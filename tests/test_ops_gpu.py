@@ -248,3 +248,21 @@ def test_fps_bucket_kernel_bit_exact(ext, ora, kind, B, N, M):
     finally:
         lib.s4g_fps_set_bucket_mode(old)
     assert torch.equal(got.cpu(), want)
+
+
+@pytest.mark.parametrize("B,C,N,K,dtype", [(2, 4, 5, 3, torch.float32), (3, 64, 700, 20, torch.float32), (2, 7, 90, 8, torch.float64)])
+def test_gather_knn_like_the_reference_test(B, C, N, K, dtype):
+    """the reference's own test of dgcnn_ext (functions/gather_knn.py:27-56, first case = its sizes and seed): forward
+    and backward against torch.gather"""
+    from s4g_release_b200.network_models.functions.gather_knn import gather_knn
+    torch.manual_seed(1)
+    feature = torch.rand(B, C, N, dtype=dtype).cuda()
+    knn_inds = torch.randint(0, N, [B, N, K]).long().cuda()
+    f_ref = feature.clone().requires_grad_(True)
+    f_ours = feature.clone().requires_grad_(True)
+    want = torch.gather(f_ref.unsqueeze(2).expand(B, C, N, N), 3, knn_inds.unsqueeze(1).expand(B, C, N, K))
+    got = gather_knn(f_ours, knn_inds)
+    assert torch.equal(got, want)
+    want.backward(torch.ones_like(want))
+    got.backward(torch.ones_like(got))
+    assert f_ref.grad.allclose(f_ours.grad)
