@@ -1,0 +1,65 @@
+"""PN2 — the sibling of PN2_CLS with a continuous pose head (reference: network_models/models/PointNet2.py:24-153).
+
+Same encoder / decoder as PointNet2_tcls.PointNet2 (so the same sm_100a operators and, for configurations without a
+global set-abstraction level, the same fused engine); the heads differ: ``frame_R`` is a 6-D rotation representation
+turned into a matrix by ``toRotMatrix`` (functions/functions.py:179-190), ``frame_t`` is a 3-D offset ADDED to the
+input points, the score key is ``scene_score_logits``, and ``t_logit`` starts at zero (:150-152).  The reference's
+default configuration (4 levels, the last one a global group with num_centroids = 0) runs on the module path.
+"""
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from ..functions.functions import toRotMatrix
+from . import PointNet2_tcls as _tcls
+
+
+class PointNet2(_tcls.PointNet2):
+    _R_OUT, _T_OUT = 6, 3
+
+    def __init__(self, *args, **kwargs):
+        super().__init__(*args, **kwargs)
+        self.init_weights()
+
+    def init_weights(self):
+        nn.init.zeros_(self.t_logit.weight)
+        nn.init.zeros_(self.t_logit.bias)
+
+    def _fusable(self):
+        c = self.config
+        return all(n > 0 for n in c["num_centroids"]) and all(k == 3 for k in c["num_fp_neighbours"])
+
+    def forward(self, data_batch, fused=None):
+        points = data_batch["scene_points"]
+        if fused is None:
+            fused = (not self.training) and (not torch.is_grad_enabled()) and points.is_cuda and self._fusable()
+        raw = self.fused_engine().forward(points) if fused else self.forward_modules(points)
+        return {"scene_score_logits": raw["score"], "frame_R": toRotMatrix(raw["frame_R"]),
+                "frame_t": points + raw["frame_t"], "movable_logits": raw["movable_logits"]}
+
+
+class PointNet2Loss(nn.Module):
+    """PointNet2.py:156-213: weighted CE on the score classes, L1 on the movable directions, flip-symmetric rotation
+    MSE weighted by the ground-truth score (x5), squared translation error weighted by the score (x20)."""
+
+    def __init__(self, label_smoothing=0, neg_weight=0.1):
+        super().__init__()
+        if label_smoothing > 0:
+            raise NotImplementedError("smooth_cross_entropy (nn_utils/functional.py) is outside the hot path")
+        self.label_smoothing, self.neg_weight = label_smoothing, neg_weight
+
+    def forward(self, preds, labels):
+        logits = preds["scene_score_logits"]
+        weight = torch.ones(logits.shape[1], device=logits.device)
+        weight[0] = self.neg_weight
+        gt_R = labels["best_frame_R"]
+        n = gt_R.shape[2]
+        pred_R = preds["frame_R"][:, :, :n]
+        flip = gt_R.new_tensor([1, -1, -1, 1, -1, -1, 1, -1, -1]).view(1, 9, 1)
+        R_err = torch.minimum(((pred_R - gt_R) ** 2).mean(1), ((pred_R - gt_R * flip) ** 2).mean(1))
+        gt_score = labels["scene_score"][:, :n]
+        t_err = ((preds["frame_t"][:, :, :n] - labels["best_frame_t"]) ** 2).sum(1)
+        return {"cls_loss": F.cross_entropy(logits, labels["scene_score_labels"], weight),
+                "R_loss": (R_err * gt_score).mean() * 5.0,
+                "t_loss": (t_err * gt_score).mean() * 20.0,
+                "mov_loss": F.l1_loss(preds["movable_logits"], labels["scene_movable_labels"])}

@@ -38,6 +38,7 @@ NUM_INPUT = 25600
 class PointNet2(nn.Module):
     _SA_MODULE = PointNetSAModule
     _FP_MODULE = PointnetFPModule
+    _R_OUT, _T_OUT = 9, 4  # frame_R: flattened 3x3; frame_t: 4 approach-offset classes (the PN2 sibling: 6 and 3)
 
     def __init__(self,
                  score_classes,
@@ -82,9 +83,9 @@ class PointNet2(nn.Module):
         self.mlp_seg = SharedMLP(c, seg_channels, ndim=1, dropout_prob=dropout_prob)
         self.seg_logit = nn.Conv1d(seg_channels[-1], score_classes, 1, bias=True)
         self.mlp_R = SharedMLP(c, seg_channels, ndim=1)
-        self.R_logit = nn.Conv1d(seg_channels[-1], 9, 1, bias=True)
+        self.R_logit = nn.Conv1d(seg_channels[-1], self._R_OUT, 1, bias=True)
         self.mlp_t = SharedMLP(c, seg_channels, ndim=1)
-        self.t_logit = nn.Conv1d(seg_channels[-1], 4, 1, bias=True)
+        self.t_logit = nn.Conv1d(seg_channels[-1], self._T_OUT, 1, bias=True)
         self.mlp_movable = SharedMLP(c, seg_channels, ndim=1, dropout_prob=dropout_prob)
         self.movable_logit = nn.Sequential(nn.Conv1d(seg_channels[-1], num_removal_directions, 1, bias=True),
                                            nn.Sigmoid())
