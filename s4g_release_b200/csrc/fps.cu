@@ -444,11 +444,28 @@ static int fps_entry(const float* points, int B, int N, int M, IndexT* index, cu
     return set_error(S4G_E_UNSUPPORTED, "farthest_point_sample: N=%d exceeds the on-chip capacity (%d points)", N,
                      kFpsThreads * 16 * kBigP);
   }
-  // smallest cluster that holds the cloud in registers, then grow it while the GPU has idle SMs
-  int cluster = 1;
-  while (cluster < 8 && (N + kFpsThreads * cluster - 1) / (kFpsThreads * cluster) > kFpsMaxP) cluster *= 2;
+  // Cluster size from a measured cost model (profiles/r01/fps_probe2.txt): one iteration costs about
+  // a(cluster) + 0.021 us x points per thread, a = 0.29 / 0.50 / 0.63 / 0.64 us for clusters of 1 / 2 / 4 / 8 CTAs
+  // (block barrier vs distributed-shared-memory exchange), times the number of waves the batch needs on the SMs.
+  // A single CTA wins whenever the cloud is small (<= ~10 points per thread); clusters of 8 only pay for a handful
+  // of clouds (16 clouds x 8 CTAs measured 1.5 us per iteration against 0.88 us with clusters of 4).
   const int sms = num_sms();
-  while (cluster < 8 && B * cluster * 2 <= sms && N > kFpsThreads * cluster) cluster *= 2;
+  int cluster = 0;
+  double best_cost = 0.0;
+  for (int c = 1; c <= 8; c *= 2) {
+    const int Pc = (N + kFpsThreads * c - 1) / (kFpsThreads * c);
+    if (Pc > kFpsMaxP || (c == 8 && B > 4 && cluster != 0)) continue;
+    static const double a[9] = {0, 0.29, 0.50, 0, 0.63, 0, 0, 0, 0.64};
+    const long long ctas = (long long)B * c;
+    const double waves = (double)((ctas + sms - 1) / sms);
+    const double cost = waves * (a[c] + 0.021 * Pc);
+    if (cluster == 0 || cost < best_cost) { cluster = c; best_cost = cost; }
+  }
+  if (cluster == 0) cluster = 8;
+  if (const char* e = getenv("S4G_FPS_CLUSTER")) {  // experiments: force the cluster size where the cloud still fits
+    const int c = atoi(e);
+    if ((c == 1 || c == 2 || c == 4 || c == 8) && (N + kFpsThreads * c - 1) / (kFpsThreads * c) <= kFpsMaxP) cluster = c;
+  }
   const int P = (N + kFpsThreads * cluster - 1) / (kFpsThreads * cluster);
   switch (cluster) {
     case 1: return dispatch_p<1, IndexT>(P, points, B, N, M, L, index, stream);
