@@ -8,7 +8,8 @@ A "step" is one pass of the hot path (the whole PN2_CLS forward: FPS, ball query
 MLP chains) over one batch.  `value` = scenes/s with the inputs already resident in HBM, timed with
 CUDA events on the launching stream (per-step event pairs, L2 flushed between steps, max over ranks).
 `e2e` = the same metric through the public module API with HOST buffers: pinned host -> device copy of
-the clouds, forward, device -> pinned host copy of the four prediction tensors, every step.
+the clouds, forward, device -> pinned host copy of the four prediction tensors, every step (the public call takes
+the pinned result buffers — `model(batch, host_out=...)` — so each head's copy overlaps the next head's compute).
 Weak scaling: each rank owns its own 64 scenes, no collective on the data path.
 
 `--impl reference` times the reference model on the box's HOST cores: the oracle restatement of the
@@ -310,12 +311,14 @@ def main():
         t0 = time.perf_counter()
         x = host_scenes.to(dev, non_blocking=True)
         with torch.no_grad():
-            preds = net({"scene_points": x})
-        if out_host is None:
-            out_host = {k: torch.empty(v.shape, dtype=v.dtype).pin_memory() for k, v in preds.items()}
-            d2h = sum(v.numel() * v.element_size() for v in preds.values())
-        for k, v in preds.items():
-            out_host[k].copy_(v, non_blocking=True)
+            if out_host is None:  # first (warm-up) step: learn the output shapes
+                preds = net({"scene_points": x})
+                out_host = {k: torch.empty(v.shape, dtype=v.dtype).pin_memory() for k, v in preds.items()}
+                d2h = sum(v.numel() * v.element_size() for v in preds.values())
+                for k, v in preds.items():
+                    out_host[k].copy_(v, non_blocking=True)
+            else:  # the public call with pinned result buffers: every head's D2H copy overlaps the next head
+                preds = net({"scene_points": x}, host_out=out_host)
         torch.cuda.synchronize()
         if i >= args.warmup:
             e2e_ms.append(1e3 * (time.perf_counter() - t0))

@@ -84,6 +84,7 @@ class FusedPointNet2:
     def __init__(self, model, mlp_backend="tcgen05", autotune=True):
         self.cfg = model.config
         self.autotune = bool(autotune)
+        self._copy_stream = None
         self.device = next(model.parameters()).device
         if self.device.type != "cuda":
             raise RuntimeError("FusedPointNet2 needs the model on a CUDA device (there is no CPU path)")
@@ -289,7 +290,7 @@ class FusedPointNet2:
                                          B, Nk, Nq, C2, C1, ptr(out), stream_ptr(sparse.device)), "interp_concat")
         return out
 
-    def _forward_tcgen05(self, points, return_trace, timer=None):
+    def _forward_tcgen05(self, points, return_trace, timer=None, host_out=None):
         cfg = self.cfg
         xyz = points.float().contiguous()
         B = xyz.shape[0]
@@ -323,9 +324,25 @@ class FusedPointNet2:
                     x = ch.run_rows(x)
             sparse_xyz, sparse = dense_xyz, x
         n = sparse_xyz.shape[2]
+        names = ("score", "frame_R", "frame_t", "movable_logits")
         with _sec(timer, "heads.mlp"):
-            outs = [ch.run_rows(sparse, n_points=n) for ch in self.head_chains]
-        preds = {"score": outs[0], "frame_R": outs[1], "frame_t": outs[2], "movable_logits": outs[3]}
+            outs = []
+            for name, ch in zip(names, self.head_chains):
+                o = ch.run_rows(sparse, n_points=n)
+                outs.append(o)
+                if host_out is not None:
+                    # stream this head's result to the caller's pinned host tensor while the next head computes
+                    if self._copy_stream is None:
+                        self._copy_stream = torch.cuda.Stream(device=o.device)
+                    ev = torch.cuda.Event()
+                    ev.record()
+                    self._copy_stream.wait_event(ev)
+                    with torch.cuda.stream(self._copy_stream):
+                        host_out[name].copy_(o, non_blocking=True)
+                    o.record_stream(self._copy_stream)
+        if host_out is not None:
+            torch.cuda.current_stream().wait_stream(self._copy_stream)  # the caller's synchronize covers the copies
+        preds = dict(zip(names, outs))
         if return_trace:
             trace["point_feature"] = sparse.float().reshape(B, n, -1)
             trace["sa_feature"] = [f.float().reshape(B, -1, f.shape[1]) for f in lv_feat[1:]]
@@ -334,12 +351,16 @@ class FusedPointNet2:
 
     # ---------------------------------------------------------------- forward
     @torch.no_grad()
-    def forward(self, points, return_trace=False, timer=None):
+    def forward(self, points, return_trace=False, timer=None, host_out=None):
+        """points (B,3,N) fp32 CUDA -> the four prediction tensors.  ``host_out``: optional dict of PINNED host tensors
+        (same keys / shapes as the result); each head's output is then copied to it on a side stream as soon as that
+        head finishes, overlapping the device -> host transfer with the remaining heads (the copies are ordered before
+        the current stream's next operation, so one synchronize() after the call makes them visible)."""
         if not points.is_cuda:
             raise RuntimeError("scene_points must be a CUDA tensor (there is no CPU path)")
         if self.mlp_backend == "tcgen05":
             with torch.cuda.device(points.device):
-                return self._forward_tcgen05(points, return_trace, timer)
+                return self._forward_tcgen05(points, return_trace, timer, host_out)
         cfg = self.cfg
         with torch.cuda.device(points.device):
             xyz = points.float().contiguous()

@@ -123,12 +123,14 @@ class PointNet2(nn.Module):
         self._engine = None  # parameters may change: re-fold BN on the next eval forward
         return super().train(mode)
 
-    def forward(self, data_batch, fused=None):
+    def forward(self, data_batch, fused=None, host_out=None):
+        """``host_out`` (fused path only): dict of pinned host tensors that receive the predictions while the later
+        heads are still computing (engine.FusedPointNet2.forward)."""
         points = data_batch["scene_points"]
         if fused is None:
             fused = (not self.training) and (not torch.is_grad_enabled()) and points.is_cuda
         if fused:
-            return self.fused_engine().forward(points)
+            return self.fused_engine().forward(points, host_out=host_out)
         return self.forward_modules(points)
 
     def init_weights(self):

@@ -92,3 +92,17 @@ def test_fused_engine_batch_consistency(tiny_net, golden_tiny):
     one = eng.forward(pts[1:2].contiguous())
     for k in HEADS:
         assert torch.equal(both[k][1:2], one[k]), k
+
+
+def test_host_out_streams_identical_predictions():
+    """forward(..., host_out=pinned dict): the results copied to the host head by head equal the returned tensors"""
+    import bench
+    net = bench.seeded_model().cuda()
+    x = bench.synthetic_scenes(2, 1000)[:, :, :8192].contiguous().cuda()
+    with torch.no_grad():
+        ref = net({"scene_points": x})
+        host = {k: torch.empty(v.shape, dtype=v.dtype).pin_memory() for k, v in ref.items()}
+        got = net({"scene_points": x}, host_out=host)
+        torch.cuda.synchronize()
+    for k in ref:
+        assert torch.equal(got[k], ref[k]) and torch.equal(host[k], ref[k].cpu()), k
