@@ -326,10 +326,12 @@ class FusedPointNet2:
         n = sparse_xyz.shape[2]
         names = ("score", "frame_R", "frame_t", "movable_logits")
         with _sec(timer, "heads.mlp"):
-            outs = []
-            for name, ch in zip(names, self.head_chains):
+            outs = [None] * 4
+            # widest head first: with host_out the copy that cannot hide behind a later head is then the smallest
+            for k in sorted(range(4), key=lambda k: -self.head_chains[k].out_c):
+                name, ch = names[k], self.head_chains[k]
                 o = ch.run_rows(sparse, n_points=n)
-                outs.append(o)
+                outs[k] = o
                 if host_out is not None:
                     # stream this head's result to the caller's pinned host tensor while the next head computes
                     if self._copy_stream is None:
