@@ -6,9 +6,9 @@ translation de-duplication, importance sampling), host buffers in, selected gras
     python bench_large.py [--scenes 4096] [--chunk 64] [--gpus N]        (N > 1: launch under torchrun like bench.py)
 
 Every rank owns scenes/N scenes (contiguous chunks of `chunk`, no collective: SURVEY.md §8e).  Per chunk: pinned
-host -> device copy on a copy stream (double-buffered, overlapping the previous chunk's compute), forward, five
-post-processing launches without any host round trip, device -> pinned host copy of the selected poses / scores /
-counts on a third stream.  The timed region runs from before the first copy to after the last one (CUDA events on the
+host -> device copy on a copy stream (double-buffered, overlapping the previous chunk's compute), forward; then, on a
+third stream and under the NEXT chunk's forward, five post-processing launches without any host round trip and the
+device -> pinned host copy of the selected poses / scores / counts.  The timed region runs from before the first copy to after the last one (CUDA events on the
 compute stream bracketing everything through cross-stream waits, and wall clock), max over ranks.
 
 Scenes: `--pool` distinct synthetic tabletop clouds (tests/inputs.py) per rank; chunk c re-uses
@@ -133,19 +133,23 @@ def main():
             main_stream.wait_event(ready)
             x = torch.roll(x_buf[k], shifts=131 * c, dims=2) if c >= n_views else x_buf[k]
             pred = eng.forward(x)
-            r = post.detect_batch_device(x, pred, num_selected=m, score_threshold=thr, verticalness_threshold=vthr,
-                                         nms_min_dist=args.nms or None, sorted_uniform=u_buf[k])
-            done = torch.cuda.Event()
-            done.record(main_stream)
-            free_ev[k] = done
+            fwd_done = torch.cuda.Event()
+            fwd_done.record(main_stream)
+            # the post-processing tail (small, latency-bound kernels) runs on the result stream, under the NEXT chunk's
+            # forward, and is followed there by the device -> host copies of the selected grasps
             with torch.cuda.stream(s_d2h):
-                s_d2h.wait_event(done)
+                s_d2h.wait_event(fwd_done)
+                r = post.detect_batch_device(x, pred, num_selected=m, score_threshold=thr, verticalness_threshold=vthr,
+                                             nms_min_dist=args.nms or None, sorted_uniform=u_buf[k])
                 res_n[c].copy_(r["n"], non_blocking=True)
                 res_cand[c].copy_(r["n_candidates"], non_blocking=True)
                 res_poses[c].copy_(r["poses"], non_blocking=True)
                 res_scores[c].copy_(r["scores"], non_blocking=True)
-                for t in r.values():
+                done = torch.cuda.Event()
+                done.record(s_d2h)
+                for t in list(pred.values()) + [x]:
                     t.record_stream(s_d2h)
+            free_ev[k] = done
         last = torch.cuda.Event()
         last.record(s_d2h)
     main_stream.wait_event(last)
