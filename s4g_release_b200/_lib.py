@@ -54,6 +54,7 @@ _SIGNATURES = {
     "s4g_chain_create": ([_i, _ip, _ip, _ip, _i, _i, _i, _i, _i, _i], _vp),
     "s4g_chain_create_slots": ([_i, _ip, _ip, _ip, _i, _i, _i, _i, _i, _i, _i], _vp),
     "s4g_chain_create_tuned": ([_i, _ip, _ip, _ip, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i], _vp),
+    "s4g_chain_create_tuned_in": ([_i, _ip, _ip, _ip, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i], _vp),
     "s4g_chain_destroy": ([_vp], None),
     "s4g_chain_weight_bytes": ([_vp], ctypes.c_size_t),
     "s4g_chain_cout_pad": ([_vp, _i], _i),

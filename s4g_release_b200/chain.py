@@ -21,10 +21,11 @@ class MlpChain:
     layer 3 -> <= 128 channels, more layers behind it) as IN_XYZ_MLP: the kernel evaluates that first layer in fp32 on
     the CUDA cores while it stages the tile.  Off by default — measured on the first set-abstraction level
     (64 x 5120 x 64 rows, 3 -> 128 -> 128 -> 256): 5.57 ms against 4.27 ms with the K = 16 tensor-core layer; the two
-    loader warps cannot issue the 49 k FMAs of a tile as fast as the rest of the tile runs."""
+    loader warps cannot issue the 49 k FMAs of a tile as fast as the rest of the tile runs.
+    ``tma_in=1`` (row chains, cin[0] % 64 == 0): input blocks arrive by TMA tensor copies (s4g_chain_create_tuned_in)."""
 
     def __init__(self, layers, device, in_mode=IN_ROWS, feat_c=0, out_mode=OUT_ROWS, group=1, sigmoid=False,
-                 xyz_layer_on_cuda_cores=False, slots=0, pairs=-1, coop=-1, subs=1):
+                 xyz_layer_on_cuda_cores=False, slots=0, pairs=-1, coop=-1, subs=1, tma_in=0):
         self.device = torch.device(device)
         self.all_cin = [int(w.shape[1]) for w, _, _ in layers]
         self.all_cout = [int(w.shape[0]) for w, _, _ in layers]
@@ -43,9 +44,11 @@ class MlpChain:
         self.in_mode, self.out_mode, self.group = in_mode, out_mode, group
         self.out_c = self.cout[-1]
         relu = [1 if r else 0 for _, _, r in layers]
-        self._h = lib.s4g_chain_create_tuned(self.n_layers, _int_array(self.cin), _int_array(self.cout), _int_array(relu),
-                                             in_mode, feat_c, out_mode, self.out_c, group, 1 if sigmoid else 0, int(slots),
-                                             int(pairs), int(coop), int(subs))
+        self.tma_in = int(tma_in)
+        self._h = lib.s4g_chain_create_tuned_in(self.n_layers, _int_array(self.cin), _int_array(self.cout),
+                                                _int_array(relu), in_mode, feat_c, out_mode, self.out_c, group,
+                                                1 if sigmoid else 0, int(slots), int(pairs), int(coop), int(subs),
+                                                self.tma_in)
         if not self._h:
             raise RuntimeError("s4g_chain_create failed: " + lib.s4g_last_error().decode())
         nbytes = lib.s4g_chain_weight_bytes(self._h)

@@ -55,7 +55,7 @@ int coop_policy() {
 // R = row blocks (sub-tiles of 128 rows) per tile.  With R = 2 every layer is emitted for sub-tile 0, then for sub-tile
 // 1: the job streams of two 128-row tiles interleaved layer by layer, so that the MMAs of one run while the epilogue
 // of the other drains — for narrow chains, whose tile is otherwise a strict MMA -> epilogue -> MMA ping-pong.
-bool build_draft(const s4g_chain* ch, const int* relu, int feat_c, int S, bool pair_ok, int R, Draft& d) {
+bool build_draft(const s4g_chain* ch, const int* relu, int feat_c, int S, bool pair_ok, int R, bool tma_in, Draft& d) {
   const int L = ch->n_layers;
   std::vector<Block> in_desc;
   if (ch->in_mode == IN_ROWS) {
@@ -138,7 +138,8 @@ bool build_draft(const s4g_chain* ch, const int* relu, int feat_c, int S, bool p
         const Grp& g = grps[gi];
         const Block& b = d.blocks[kin[kb]];
         const int steps = b.c_count / 16;
-        const int per_job = g.cnt == 2 ? 4 : 8;  // <= 32 KB of weights per job
+        // <= 32 KB of weights per job; a job on a swizzled (TMA-loaded) input block stays inside one 64-channel half
+        const int per_job = (g.cnt == 2 || (tma_in && l == 0)) ? 4 : 8;
         for (int ks = 0; ks < steps; ks += per_job) {
           const int k16 = std::min(per_job, steps - ks);
           const bool tail = ks + per_job >= steps;
@@ -149,6 +150,7 @@ bool build_draft(const s4g_chain* ch, const int* relu, int feat_c, int S, bool p
           if (gi + 1 == grps.size() && tail) flags |= MF_RELEASE;
           if (transposed) flags |= MF_TRANSPOSED;
           if (g.cnt == 2) flags |= MF_PAIR;
+          if (tma_in && l == 0) flags |= MF_SWZ;
           const int n_rows = transposed ? 128 : (g.cnt == 2 ? 256 : nbs[g.nb].second);
           d.mma.push_back({kin[kb], acc0 + g.nb - nb0, k16, ks, n_rows, flags, l, nbs[g.nb].first, b.c_begin + ks * 16,
                            transposed ? 128 : n_rows});
@@ -412,7 +414,9 @@ void evaluate(Candidate& c) {
 }  // namespace
 
 int plan_chain(s4g_chain* ch, int n_layers, const int* cin, const int* cout, const int* relu, int in_mode, int feat_c,
-               int out_mode, int out_c, int group, int sigmoid, int force_slots, int force_pairs, int force_coop, int subs) {
+               int out_mode, int out_c, int group, int sigmoid, int force_slots, int force_pairs, int force_coop, int subs, int tma_in) {
+  S4G_CHECK_ARG(!tma_in || (in_mode == IN_ROWS && out_mode != OUT_MAXPOOL && cin[0] % 64 == 0),
+                "mlp_chain: TMA input needs row input, a multiple of 64 input channels and no transposed last layer");
   S4G_CHECK_ARG(subs == 1 || subs == 2, "mlp_chain: 1 or 2 row blocks per tile");
   struct CoopScope {  // force_coop: -1 = default policy, 0..2 = see coop_policy()
     explicit CoopScope(int v) { g_force_coop = v; }
@@ -468,7 +472,7 @@ int plan_chain(s4g_chain* ch, int n_layers, const int* cin, const int* cout, con
       if (force_pairs >= 0 && pair_ok != force_pairs) continue;  // -1 = both, 0 = N <= 128 only, 1 = N = 256 pairs
       for (int depth = 3; depth >= 1; --depth) {
         Candidate c;
-        if (!build_draft(ch, relu, feat_c, S, pair_ok != 0, subs, c.d)) continue;
+        if (!build_draft(ch, relu, feat_c, S, pair_ok != 0, subs, tma_in != 0, c.d)) continue;
         if (pair_ok && (c.d.n_acc & 1)) continue;  // pairs need tile-invariant accumulator parity
         c.d.stages = stages;
         c.d.depth = depth;
@@ -514,6 +518,7 @@ int plan_chain(s4g_chain* ch, int n_layers, const int* cin, const int* cout, con
   p.stages = d.stages;
   p.in_mode = in_mode;
   p.subs = subs;
+  p.tma_in = tma_in ? 1 : 0;
   p.feat_c = feat_c;
   p.out_c = out_c;
   p.group = group > 0 ? group : 1;

@@ -32,6 +32,7 @@
 // freedom depends only on the dependency graph, which the planner checks by simulating the streams
 // (a Kahn network: if one schedule completes, every schedule does).
 #pragma once
+#include <cuda.h>
 #include <stdint.h>
 
 namespace s4g {
@@ -64,7 +65,9 @@ enum InMode { IN_ROWS = 0, IN_GATHER = 1, IN_XYZ_MLP = 5 };
 enum OutMode { OUT_ROWS = 2, OUT_MAXPOOL = 3, OUT_LOGITS = 4 };
 
 // MF_PAIR: the job's MMAs are N = 256 wide and fill accumulators acc and acc + 1 (adjacent TMEM blocks)
-enum MmaFlags { MF_WAIT_ACT = 1, MF_FIRST_K = 2, MF_LAST_K = 4, MF_RELEASE = 8, MF_TRANSPOSED = 16, MF_PAIR = 32 };
+// MF_SWZ: the activation block read is a TMA-loaded INPUT block in the 128-byte-swizzled K-major layout (two 16 KB halves
+// of 64 channels, rows 128 B apart) instead of the interleaved layout the epilogue writes
+enum MmaFlags { MF_WAIT_ACT = 1, MF_FIRST_K = 2, MF_LAST_K = 4, MF_RELEASE = 8, MF_TRANSPOSED = 16, MF_PAIR = 32, MF_SWZ = 64 };
 
 struct MmaJob {      // one weight chunk x one activation K-block (part) -> one accumulator block (or pair)
   uint8_t blk_mod;   // activation block read: tile-relative production index i, as i % S ...
@@ -115,6 +118,8 @@ struct ChainParams {
   int slots, stages;
   int load_depth;            // cp.async input blocks a loader thread keeps in flight (1..3)
   int subs;                  // row blocks per tile (1 or 2): a tile is 128 * subs rows
+  int tma_in;                // IN_ROWS: input blocks arrive by TMA tensor copies (in_map) in the swizzled layout
+  alignas(64) CUtensorMap in_map;  // 2-D map of the input rows [P][in_stride] bf16, box 64 channels x 128 rows, 128 B swizzle
   const void* weights;       // packed chunk stream of one tile, in MMA-job order
   const float* bias[kMaxLayers];
   int P;                     // rows (positions)
@@ -161,5 +166,5 @@ namespace s4g {
 // Plans the chain: fills ch->prm job streams, ring sizes, chunk sources.  Returns S4G_OK or sets the error.
 int plan_chain(s4g_chain* ch, int n_layers, const int* cin, const int* cout, const int* relu, int in_mode, int feat_c,
                int out_mode, int out_c, int group, int sigmoid, int force_slots = 0, int force_pairs = -1,
-               int force_coop = -1, int subs = 1);
+               int force_coop = -1, int subs = 1, int tma_in = 0);
 }  // namespace s4g

@@ -80,6 +80,11 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned by
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
                    smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
+// one box of a 2-D tensor map (coordinates: c0 = innermost) into shared memory, completing `bar`'s transaction count
+__device__ __forceinline__ void tma_load_2d(void* dst, const void* map, int c0, int c1, uint64_t* bar) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+                   smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
+}
 __device__ __forceinline__ void cp_async16(void* dst, const void* src, bool valid) {
   const unsigned n = valid ? 16u : 0u;
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(dst)), "l"(src), "r"(n) : "memory");
@@ -213,7 +218,9 @@ __device__ __forceinline__ void ring_at(const Ring& base, const ChainParams& p, 
 // five roles, and every extra block of rarely-run code costs the other chains instruction-cache misses.
 // OUT (the chain's output mode) and GATHER (gathered vs row input) are compile-time for the same reason: a chain only
 // carries the loader and the final epilogue it uses.
-template <bool PROF, bool XYZ_MLP, int OUT, bool GATHER>
+// TMA_IN (row input only): the input blocks are fetched by one thread with 2-D tensor copies (64 channels x 128 rows
+// per box) into the 128-byte-swizzled K-major layout, instead of 64 threads x 16-byte cp.async into the interleaved one.
+template <bool PROF, bool XYZ_MLP, int OUT, bool GATHER, bool TMA_IN = false>
 __global__ void __launch_bounds__(kChainThreads, 1) mlp_chain_kernel(const __grid_constant__ ChainParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* slots = smem;
@@ -291,6 +298,8 @@ __global__ void __launch_bounds__(kChainThreads, 1) mlp_chain_kernel(const __gri
     // descriptor high word: SBO = 128 B, version 1;  low word: (addr >> 4) | (LBO >> 4) << 16
     const uint64_t desc_hi = (uint64_t)((128u >> 4) | (1u << 14)) << 32;
     const uint32_t a_lbo16 = (uint32_t)kTileRows;  // (128 rows * 16 B) >> 4
+    // swizzled input blocks: SBO = 1024 B (8 rows x 128 B), version 1, layout type 2 = SWIZZLE_128B; LBO unused
+    const uint64_t swz_hi = (uint64_t)((1024u >> 4) | (1u << 14) | (2u << 29)) << 32;
     long long c_act = 0, c_tm = 0, c_w = 0;
     const long long t_begin = tick<PROF>();
     struct Next {
@@ -347,11 +356,17 @@ __global__ void __launch_bounds__(kChainThreads, 1) mlp_chain_kernel(const __gri
         const uint32_t n = (uint32_t)job.n8 * 8u;
         const bool transposed = OUT == OUT_MAXPOOL && (job.flags & MF_TRANSPOSED) != 0;
         const uint32_t idesc = make_idesc(128, transposed ? kTileRows : (int)n);
-        const uint32_t a_lo = (slots16 + (uint32_t)slot * (kSlotBytes >> 4) + (uint32_t)job.koff * (2u * a_lbo16)) | (a_lbo16 << 16);
+        const bool swz = TMA_IN && (job.flags & MF_SWZ) != 0;
+        // swizzled block: halves of 64 channels 16 KB apart, 16 channels = 32 B inside a 128-byte row
+        const uint32_t a_lo = swz ? (slots16 + (uint32_t)slot * (kSlotBytes >> 4) + (uint32_t)(job.koff >> 2) * (16384u >> 4) +
+                                     (uint32_t)(job.koff & 3) * 2u) | (1u << 16)
+                                  : (slots16 + (uint32_t)slot * (kSlotBytes >> 4) + (uint32_t)job.koff * (2u * a_lbo16)) | (a_lbo16 << 16);
+        const uint64_t a_hi = swz ? swz_hi : desc_hi;
         const uint32_t w_lo = (ring16 + (uint32_t)cur.s * (kStageBytes >> 4)) | (n << 16);  // LBO = n rows * 16 B
         // operand order is swapped BEFORE the loop: a predicated-off tcgen05.mma still costs an issue slot
         const uint32_t x0 = transposed ? w_lo : a_lo, y0 = transposed ? a_lo : w_lo;
-        const uint32_t x_step = transposed ? 2u * n : 2u * a_lbo16;  // next 16 channels = 2 K pieces
+        const uint32_t x_step = transposed ? 2u * n : (swz ? 2u : 2u * a_lbo16);  // next 16 channels = 2 K pieces
+        const uint64_t x_hi = transposed ? desc_hi : a_hi;  // (a TMA_IN chain has no transposed layer)
         const uint32_t y_step = transposed ? 2u * a_lbo16 : 2u * n;
         const uint32_t d_addr = tmem_base + tb * 128u;
         const uint32_t acc0 = (job.flags & MF_FIRST_K) ? 0u : 1u;
@@ -360,7 +375,7 @@ __global__ void __launch_bounds__(kChainThreads, 1) mlp_chain_kernel(const __gri
           uint32_t x_lo = x0, y_lo = y0, acc = acc0;
 #pragma unroll 1
           for (int k = 0; k < k_last; ++k) {
-            umma_bf16(d_addr, desc_hi | x_lo, desc_hi | y_lo, idesc, acc);
+            umma_bf16(d_addr, x_hi | x_lo, desc_hi | y_lo, idesc, acc);
             acc = 1u;
             x_lo += x_step;
             y_lo += y_step;
@@ -379,7 +394,7 @@ __global__ void __launch_bounds__(kChainThreads, 1) mlp_chain_kernel(const __gri
         if (jn != 0 || it + 1 < n_my) cur = prepare(jn);
         if (PROF && p.prof && blockIdx.x == 0 && it == 2 && lane == 0) p.prof[148 * 16 + j * 4 + 2] = tick<PROF>();
         if (elect_one()) {
-          umma_bf16(d_addr, desc_hi | (x0 + x_step * (uint32_t)k_last), desc_hi | (y0 + y_step * (uint32_t)k_last), idesc,
+          umma_bf16(d_addr, x_hi | (x0 + x_step * (uint32_t)k_last), desc_hi | (y0 + y_step * (uint32_t)k_last), idesc,
                     k_last > 0 ? 1u : acc0);
           umma_commit(&w_empty[s_cur]);                              // stage reusable once these MMAs have read it
           if (job.flags & MF_LAST_K) {                               // accumulator(s) complete
@@ -397,6 +412,32 @@ __global__ void __launch_bounds__(kChainThreads, 1) mlp_chain_kernel(const __gri
       p.prof[blockIdx.x * 16 + 3] = c_act;
       p.prof[blockIdx.x * 16 + 4] = c_tm;
       p.prof[blockIdx.x * 16 + 5] = c_w;
+    }
+  } else if (TMA_IN && warp >= kLoadWarp0) {
+    // ===================== TMA input loader: one elected thread of loader warp 0 =====================
+    if (warp == kLoadWarp0) {
+      Ring base = {0, 0u};
+      for (int it = 0; it < n_my; ++it) {
+        const int row0 = ((int)blockIdx.x + it * (int)gridDim.x) * tile_rows;
+        for (int j = 0; j < p.n_ld; ++j) {
+          const WorkerJob job = p.ld[j];
+          int slot;
+          unsigned use;
+          ring_at(base, p, job.blk_mod, job.blk_div, slot, use);
+          if (job.same || it >= (int)job.min_it) mbar_wait(&blk_free[job.pred], (unsigned)(job.same ? it : it - 1) & 1u);
+          if (elect_one()) {
+            // rows past P are zero-filled by the copy engine and still count towards the transaction bytes
+            mbar_expect_tx(&act_ready[slot], (unsigned)job.c_count * (kTileRows * 2u));
+            uint8_t* dst = slots + (size_t)slot * kSlotBytes;
+            for (int c = 0; c < (int)job.c_count; c += 64)
+              tma_load_2d(dst + (size_t)(c >> 6) * 16384, &p.in_map, (int)job.c_begin + c, row0 + (int)job.sub * kTileRows,
+                          &act_ready[slot]);
+            mbar_arrive_n(&act_ready[slot], kEpiWarps - 1);
+          }
+          __syncwarp();
+        }
+        ring_advance(base, p);
+      }
     }
   } else if (warp >= kLoadWarp0) {
     // ===================== loader warps: thread r stages rows r and r + 64 of every layer-0 input block =====================
@@ -795,17 +836,25 @@ extern "C" s4g_chain* s4g_chain_create(int n_layers, const int* cin, const int* 
 // pairs = -1 planner's choice / 0 no N = 256 accumulator pairs / 1 pairs only, coop = -1 default policy / 0 none /
 // 1 every row epilogue shared by all 16 warps / 2 the unpaired ones, subs = row blocks (128 rows) per tile: 1, or 2 =
 // two tiles interleaved layer by layer.  NULL when no plan exists under the constraints.
-extern "C" s4g_chain* s4g_chain_create_tuned(int n_layers, const int* cin, const int* cout, const int* relu, int in_mode,
-                                             int feat_c, int out_mode, int out_c, int group, int sigmoid, int slots,
-                                             int pairs, int coop, int subs) {
+// tma_in = 1 (row input, cin[0] a multiple of 64, not OUT_MAXPOOL): the input blocks are fetched with TMA tensor copies.
+extern "C" s4g_chain* s4g_chain_create_tuned_in(int n_layers, const int* cin, const int* cout, const int* relu, int in_mode,
+                                                int feat_c, int out_mode, int out_c, int group, int sigmoid, int slots,
+                                                int pairs, int coop, int subs, int tma_in) {
   s4g_chain* ch = new (std::nothrow) s4g_chain;
   if (!ch) return nullptr;
   if (s4g::plan_chain(ch, n_layers, cin, cout, relu, in_mode, feat_c, out_mode, out_c, group, sigmoid, slots, pairs,
-                      coop, subs) != S4G_OK) {
+                      coop, subs, tma_in) != S4G_OK) {
     delete ch;
     return nullptr;
   }
   return ch;
+}
+
+extern "C" s4g_chain* s4g_chain_create_tuned(int n_layers, const int* cin, const int* cout, const int* relu, int in_mode,
+                                             int feat_c, int out_mode, int out_c, int group, int sigmoid, int slots,
+                                             int pairs, int coop, int subs) {
+  return s4g_chain_create_tuned_in(n_layers, cin, cout, relu, in_mode, feat_c, out_mode, out_c, group, sigmoid, slots,
+                                   pairs, coop, subs, 0);
 }
 
 extern "C" s4g_chain* s4g_chain_create_slots(int n_layers, const int* cin, const int* cout, const int* relu, int in_mode,
@@ -903,9 +952,9 @@ extern "C" int s4g_chain_set_profile(s4g_chain* ch, void* counters_dev) {
 }
 
 namespace s4g {
-template <bool PROF, bool XYZ_MLP, int OUT, bool GATHER>
+template <bool PROF, bool XYZ_MLP, int OUT, bool GATHER, bool TMA_IN = false>
 static int launch_chain(const ChainParams& p, int grid, size_t smem, cudaStream_t stream) {
-  auto kern = mlp_chain_kernel<PROF, XYZ_MLP, OUT, GATHER>;
+  auto kern = mlp_chain_kernel<PROF, XYZ_MLP, OUT, GATHER, TMA_IN>;
   static bool attr_set = false;
   if (!attr_set) {
     S4G_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
@@ -924,7 +973,12 @@ static int s4g_chain_launch(const s4g_chain* ch, s4g::ChainParams& p, cudaStream
   const int grid = tiles < s4g::num_sms() ? tiles : s4g::num_sms();
   const bool gather = p.in_mode != s4g::IN_ROWS, xyz = p.in_mode == s4g::IN_XYZ_MLP, prof = p.prof != nullptr;
   S4G_CHECK_ARG(!(xyz && prof), "mlp_chain: the cycle counters are not built for IN_XYZ_MLP chains");
+  S4G_CHECK_ARG(!(p.tma_in && prof), "mlp_chain: the cycle counters are not built for TMA-input chains");
   int rc = S4G_E_UNSUPPORTED;
+  if (p.tma_in) {
+    if (ch->out_mode == s4g::OUT_ROWS) rc = s4g::launch_chain<false, false, s4g::OUT_ROWS, false, true>(p, grid, ch->smem_bytes, stream);
+    if (ch->out_mode == s4g::OUT_LOGITS) rc = s4g::launch_chain<false, false, s4g::OUT_LOGITS, false, true>(p, grid, ch->smem_bytes, stream);
+  } else {
 #define S4G_CHAIN_CASE(PROF_, XYZ_, OUT_, GATHER_)                                                                     \
   if (prof == PROF_ && xyz == XYZ_ && ch->out_mode == s4g::OUT_ && gather == GATHER_)                                  \
     rc = s4g::launch_chain<PROF_, XYZ_, s4g::OUT_, GATHER_>(p, grid, ch->smem_bytes, stream);
@@ -944,6 +998,7 @@ static int s4g_chain_launch(const s4g_chain* ch, s4g::ChainParams& p, cudaStream
   S4G_CHAIN_CASE(false, true, OUT_LOGITS, true)
   S4G_CHAIN_CASE(false, true, OUT_MAXPOOL, true)
 #undef S4G_CHAIN_CASE
+  }
   if (rc != S4G_OK) return rc == S4G_E_UNSUPPORTED ? s4g::set_error(rc, "mlp_chain: no kernel for this chain type") : rc;
   S4G_LAUNCH_CHECK("mlp_chain");
   return S4G_OK;
@@ -966,6 +1021,28 @@ extern "C" int s4g_chain_run_rows(const s4g_chain* ch, const void* in_rows, int 
   p.in_stride = in_stride;
   p.out = out;
   p.n_points = n_points > 0 ? n_points : 1;
+  if (p.tma_in && P > 0) {
+    // 2-D map of the input rows: dim 0 = channels (in_stride wide), dim 1 = rows; box = 64 channels x 128 rows
+    typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                 const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                 CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    static EncodeFn encode = nullptr;
+    if (!encode) {
+      void* fn = nullptr;
+      cudaDriverEntryPointQueryResult qres;
+      S4G_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+      S4G_CHECK_ARG(fn != nullptr && qres == cudaDriverEntryPointSuccess, "mlp_chain: cuTensorMapEncodeTiled is not available");
+      encode = reinterpret_cast<EncodeFn>(fn);
+    }
+    const cuuint64_t dims[2] = {(cuuint64_t)in_stride, (cuuint64_t)P};
+    const cuuint64_t strides[1] = {(cuuint64_t)in_stride * 2u};
+    const cuuint32_t box[2] = {64u, (cuuint32_t)s4g::kTileRows};
+    const cuuint32_t estr[2] = {1u, 1u};
+    const CUresult r = encode(&p.in_map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(in_rows), dims, strides, box,
+                              estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                              CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    S4G_CHECK_ARG(r == CUDA_SUCCESS, "mlp_chain: cuTensorMapEncodeTiled failed");
+  }
   return s4g_chain_launch(ch, p, (cudaStream_t)stream);
 }
 

@@ -111,9 +111,9 @@ class FusedPointNet2:
         sig = _chain_signature(layers, in_mode, feat_c, out_mode, group)
         if self.autotune and sig not in _TUNED_SLOTS:
             _TUNED_SLOTS[sig] = self._tune_slots(layers, in_mode, feat_c, out_mode, group, sigmoid)
-        slots, pairs, coop, subs = _TUNED_SLOTS.get(sig, (0, -1, -1, 1))
+        slots, pairs, coop, subs, tma = _TUNED_SLOTS.get(sig, (0, -1, -1, 1, 0))
         return MlpChain(layers, self.device, in_mode, feat_c, out_mode, group=group, sigmoid=sigmoid, slots=slots,
-                        pairs=pairs, coop=coop, subs=subs)
+                        pairs=pairs, coop=coop, subs=subs, tma_in=tma)
 
     def _tune_slots(self, layers, in_mode, feat_c, out_mode, group, sigmoid):
         dev = self.device
@@ -135,19 +135,22 @@ class FusedPointNet2:
             x = torch.randn(rows, layers[0][0].shape[1], device=dev, generator=g).to(torch.bfloat16)
             n_points = rows if out_mode == OUT_LOGITS else 0
             run = lambda ch: ch.run_rows(x, n_points=n_points)
-        best, best_ms = (0, -1, -1, 1), None
+        best, best_ms = (0, -1, -1, 1, 0), None
         seen = set()
-        candidates = [(0, -1, -1, 1)] + [(sl, pr, co, 1) for sl in (3, 4, 5) for pr in (1, 0) for co in (-1, 0, 2)]
+        candidates = [(0, -1, -1, 1, 0)] + [(sl, pr, co, 1, 0) for sl in (3, 4, 5) for pr in (1, 0) for co in (-1, 0, 2)]
         # two row blocks per tile (two 128-row tiles interleaved layer by layer): only narrow chains have the shared
         # memory for it; the planner refuses the others
-        candidates += [(sl, -1, co, 2) for sl in (0, 3, 4, 5) for co in (-1, 0, 1)]
-        for slots, pairs, coop, subs in candidates:
+        candidates += [(sl, -1, co, 2, 0) for sl in (0, 3, 4, 5) for co in (-1, 0, 1)]
+        # row chains: the same plans with the input blocks fetched by TMA tensor copies (refused unless cin % 64 == 0)
+        if in_mode == IN_ROWS and out_mode != OUT_MAXPOOL:
+            candidates += [c[:4] + (1,) for c in candidates]
+        for slots, pairs, coop, subs, tma in candidates:
             try:
                 ch = MlpChain(layers, dev, in_mode, feat_c, out_mode, group=group, sigmoid=sigmoid, slots=slots,
-                              pairs=pairs, coop=coop, subs=subs)
+                              pairs=pairs, coop=coop, subs=subs, tma_in=tma)
             except RuntimeError:
                 continue  # no deadlock-free plan under these constraints
-            plan = ch.describe()
+            plan = (ch.describe(), tma)
             if plan in seen:  # different constraints, same job streams
                 continue
             seen.add(plan)
@@ -162,7 +165,7 @@ class FusedPointNet2:
                 ts.append(a.elapsed_time(b))
             ms = min(ts)
             if best_ms is None or ms < best_ms * 0.97:  # keep the planner's choice unless another is clearly faster
-                best, best_ms = (slots, pairs, coop, subs), ms
+                best, best_ms = (slots, pairs, coop, subs, tma), ms
             del ch
         return best
 

@@ -203,3 +203,47 @@ def test_two_row_blocks_logits_head():
     torch.cuda.synchronize()
     want = torch.sigmoid(_ref_chain(x, layers)).reshape(B, n_points, n_out).transpose(1, 2)
     _check(got, want)
+
+
+# ---- input blocks fetched by TMA tensor copies into the 128-byte-swizzled layout (s4g_chain_create_tuned_in) ----
+@pytest.mark.parametrize("dims,P,stride_pad,subs", [
+    ([64, 64], 128, 0, 1), ([64, 64, 64], 700, 0, 1), ([128, 256], 333, 0, 1), ([256, 512, 256, 256, 128], 2048, 0, 1),
+    ([192, 128, 64], 1000, 0, 1), ([384, 256, 256], 20000, 0, 1), ([512, 256, 256, 256], 1000, 64, 1),
+    ([1280, 512, 512], 513, 0, 1), ([64, 64, 64], 1300, 0, 2), ([128, 128, 128, 64], 77, 8, 2),
+])
+def test_tma_input_rows(dims, P, stride_pad, subs):
+    from s4g_release_b200.chain import MlpChain
+    layers = _layers(dims, seed=sum(dims) + 7)
+    x = _bf(torch.randn(P, dims[0], generator=torch.Generator().manual_seed(P)))
+    try:
+        ch = MlpChain(layers, "cuda", subs=subs, tma_in=1)
+    except RuntimeError:
+        assert subs == 2  # the planner may refuse two row blocks per tile; one block must always plan
+        pytest.skip("no two-row-block plan for this chain")
+    xd = torch.zeros(P, dims[0] + stride_pad, dtype=torch.bfloat16, device="cuda")
+    xd[:, :dims[0]] = x.cuda().to(torch.bfloat16)
+    xd[:, dims[0]:] = 7.0  # channels past cin belong to someone else: they must not leak in
+    got = ch.run_rows(xd)
+    torch.cuda.synchronize()
+    _check(got, _bf(_ref_chain(x, layers)))
+    same = MlpChain(layers, "cuda", subs=subs).run_rows(xd)  # same plan, cp.async input: bit-identical
+    assert torch.equal(got, same)
+
+
+def test_tma_input_logits_head():
+    from s4g_release_b200.chain import OUT_LOGITS, MlpChain
+    dims, n_out, B, n_points = [256, 512, 256, 256, 128], 3, 2, 1280
+    layers = _layers(dims + [n_out], seed=n_out, relu_last=False)
+    x = _bf(torch.randn(B * n_points, dims[0], generator=torch.Generator().manual_seed(3)))
+    got = MlpChain(layers, "cuda", out_mode=OUT_LOGITS, tma_in=1).run_rows(x.cuda().to(torch.bfloat16), n_points)
+    torch.cuda.synchronize()
+    want = _ref_chain(x, layers).reshape(B, n_points, n_out).transpose(1, 2)
+    _check(got, want)
+
+
+def test_tma_input_refused_where_it_cannot_apply():
+    from s4g_release_b200.chain import IN_GATHER, OUT_MAXPOOL, MlpChain
+    with pytest.raises(RuntimeError):
+        MlpChain(_layers([32, 64], seed=1), "cuda", tma_in=1)  # 32 input channels: not a whole 128-byte row
+    with pytest.raises(RuntimeError):
+        MlpChain(_layers([16, 64, 64], seed=1), "cuda", in_mode=IN_GATHER, feat_c=0, out_mode=OUT_MAXPOOL, group=16, tma_in=1)
