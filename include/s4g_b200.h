@@ -148,7 +148,9 @@ s4g_chain* s4g_chain_create_tuned(int n_layers, const int* cin, const int* cout,
                                   int subs);
 /* ... and with the input path chosen: tma_in = 1 (row input, cin[0] a multiple of 64, not the max-pool output mode) has
  * one thread fetch the input blocks with 2-D TMA tensor copies into a 128-byte-swizzled layout instead of 64 threads
- * issuing 16-byte cp.async; the tensor map is encoded per s4g_chain_run_rows call. */
+ * issuing 16-byte cp.async; the tensor map is encoded per s4g_chain_run_rows call.  Gathered max-pool chains (>= 2
+ * layers, feat_c a multiple of 64, group % 4 == 0) fetch the neighbours' feature rows with tile::gather4 copies, four
+ * rows per instruction (s4g_chain_run_gather then needs K % 4 == 0 and 16-byte aligned indices). */
 s4g_chain* s4g_chain_create_tuned_in(int n_layers, const int* cin, const int* cout, const int* relu, int in_mode,
                                      int feat_c, int out_mode, int out_c, int group, int sigmoid, int slots, int pairs,
                                      int coop, int subs, int tma_in);

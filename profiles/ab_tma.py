@@ -53,3 +53,39 @@ for name, dims, out_mode, rows in cases:
                 continue
             print("%-30s slots %d subs %d  cp.async %s ms   tma %s ms" %
                   (name, slots, subs, *["%.3f" % t if t else "  -  " for t in row]), flush=True)
+
+
+# gathered set-abstraction chains (levels 1 and 2 of PN2_CLS): cp.async gather vs tile::gather4
+from s4g_release_b200.chain import IN_GATHER, OUT_MAXPOOL  # noqa: E402
+for name, feat_c, dims, N, M, K in [("sa1 (259-256-256-512)", 256, [256, 256, 512], 5120, 1024, 64),
+                                    ("sa2 (515-512-512-1024)", 512, [512, 512, 1024], 1024, 256, 64)]:
+    B = 64
+    L = layers([feat_c + 3] + dims)
+    g = torch.Generator(device="cuda").manual_seed(0)
+    xyz = torch.rand(B, 3, N, device="cuda", generator=g)
+    ctr = xyz[:, :, :M].contiguous()
+    near = torch.randint(0, 256, (B, M, K), device="cuda", generator=g)
+    nbr = ((torch.arange(M, device="cuda").view(1, M, 1) * (N // M) + near) % N).to(torch.int32)
+    feat = torch.randn(B * N, feat_c, device="cuda", generator=g).to(torch.bfloat16)
+
+    class G:
+        def __init__(self, ch):
+            self.ch = ch
+
+        def run_rows(self, x, n_points=0):
+            return self.ch.run_gather(feat, xyz, ctr, nbr)
+
+    for slots in (0, 3, 4, 5):
+        for pairs in (-1, 0):
+            row = []
+            for tma in (0, 1):
+                try:
+                    ch = MlpChain(L, "cuda", IN_GATHER, feat_c, OUT_MAXPOOL, group=K, slots=slots, pairs=pairs, tma_in=tma)
+                except RuntimeError:
+                    row.append(None)
+                    continue
+                row.append(time_chain(G(ch), None, 0))
+            if row[0] is None and row[1] is None:
+                continue
+            print("%-30s slots %d pairs %2d  cp.async %s ms   gather4 %s ms" %
+                  (name, slots, pairs, *["%.3f" % t if t else "  -  " for t in row]), flush=True)

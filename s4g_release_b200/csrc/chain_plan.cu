@@ -139,7 +139,8 @@ bool build_draft(const s4g_chain* ch, const int* relu, int feat_c, int S, bool p
         const Block& b = d.blocks[kin[kb]];
         const int steps = b.c_count / 16;
         // <= 32 KB of weights per job; a job on a swizzled (TMA-loaded) input block stays inside one 64-channel half
-        const int per_job = (g.cnt == 2 || (tma_in && l == 0)) ? 4 : 8;
+        const bool swz = tma_in && l == 0 && b.kind != WK_LOAD_XYZ;  // (the xyz block is written by threads: interleaved)
+        const int per_job = (g.cnt == 2 || swz) ? 4 : 8;
         for (int ks = 0; ks < steps; ks += per_job) {
           const int k16 = std::min(per_job, steps - ks);
           const bool tail = ks + per_job >= steps;
@@ -150,7 +151,7 @@ bool build_draft(const s4g_chain* ch, const int* relu, int feat_c, int S, bool p
           if (gi + 1 == grps.size() && tail) flags |= MF_RELEASE;
           if (transposed) flags |= MF_TRANSPOSED;
           if (g.cnt == 2) flags |= MF_PAIR;
-          if (tma_in && l == 0) flags |= MF_SWZ;
+          if (swz) flags |= MF_SWZ;
           const int n_rows = transposed ? 128 : (g.cnt == 2 ? 256 : nbs[g.nb].second);
           d.mma.push_back({kin[kb], acc0 + g.nb - nb0, k16, ks, n_rows, flags, l, nbs[g.nb].first, b.c_begin + ks * 16,
                            transposed ? 128 : n_rows});
@@ -415,8 +416,11 @@ void evaluate(Candidate& c) {
 
 int plan_chain(s4g_chain* ch, int n_layers, const int* cin, const int* cout, const int* relu, int in_mode, int feat_c,
                int out_mode, int out_c, int group, int sigmoid, int force_slots, int force_pairs, int force_coop, int subs, int tma_in) {
-  S4G_CHECK_ARG(!tma_in || (in_mode == IN_ROWS && out_mode != OUT_MAXPOOL && cin[0] % 64 == 0),
-                "mlp_chain: TMA input needs row input, a multiple of 64 input channels and no transposed last layer");
+  S4G_CHECK_ARG(!tma_in || (in_mode == IN_ROWS && out_mode != OUT_MAXPOOL && cin[0] % 64 == 0) ||
+                    (in_mode == IN_GATHER && out_mode == OUT_MAXPOOL && n_layers > 1 && feat_c > 0 && feat_c % 64 == 0 &&
+                     group % 4 == 0),
+                "mlp_chain: TMA input needs row input with a multiple of 64 channels and no max-pool, or a gathered "
+                "max-pool chain of >= 2 layers over a feature table of a multiple of 64 channels, group % 4 == 0");
   S4G_CHECK_ARG(subs == 1 || subs == 2, "mlp_chain: 1 or 2 row blocks per tile");
   struct CoopScope {  // force_coop: -1 = default policy, 0..2 = see coop_policy()
     explicit CoopScope(int v) { g_force_coop = v; }

@@ -85,6 +85,12 @@ __device__ __forceinline__ void tma_load_2d(void* dst, const void* map, int c0, 
   asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
                    smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
 }
+// four rows (r0..r3, any order) of a 2-D tensor map with a {64, 1} box -> four consecutive 128-byte rows at dst
+__device__ __forceinline__ void tma_gather4(void* dst, const void* map, int c0, int r0, int r1, int r2, int r3, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cta.global.tile::gather4.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];" ::
+          "r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(r0), "r"(r1), "r"(r2), "r"(r3) : "memory");
+}
 __device__ __forceinline__ void cp_async16(void* dst, const void* src, bool valid) {
   const unsigned n = valid ? 16u : 0u;
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(dst)), "l"(src), "r"(n) : "memory");
@@ -413,7 +419,92 @@ __global__ void __launch_bounds__(kChainThreads, 1) mlp_chain_kernel(const __gri
       p.prof[blockIdx.x * 16 + 4] = c_tm;
       p.prof[blockIdx.x * 16 + 5] = c_w;
     }
-  } else if (TMA_IN && warp >= kLoadWarp0) {
+  } else if (TMA_IN && GATHER && warp >= kLoadWarp0) {
+    // ===================== gathered input by TMA: lane l of loader warp w fetches rows 4l..4l+3 of half w of a feature
+    // block with ONE tile::gather4 copy (4 table rows -> 4 consecutive rows of the swizzled layout); the relative-xyz
+    // block is computed by the 64 threads as in the cp.async path =====================
+    const int lw = warp - kLoadWarp0;
+    const int r = (int)threadIdx.x - kLoadWarp0 * 32;  // 0..63
+    const int per_b = p.M * p.K;
+    const int oob = (int)((long long)p.P / per_b) * p.N;  // first row past the feature table: zero-filled by the copy engine
+    Ring base = {0, 0u};
+    int jn[4] = {0, 0, 0, 0}, jn_next[4] = {0, 0, 0, 0};  // xyz block: rows r, r + 64 of each row block
+    int4 g4[2], g4_next[2];                              // feature blocks: rows 4 lane .. 4 lane + 3 of each row block
+    auto tile_base = [&](int jt) -> long long { return ((long long)blockIdx.x + (long long)jt * gridDim.x) * tile_rows; };
+    auto load_idx = [&](int jt) {
+#pragma unroll
+      for (int sub = 0; sub < 2; ++sub) {
+        const bool on = jt < n_my && sub < p.subs;
+        const long long row4 = tile_base(jt) + sub * kTileRows + 4 * lane;
+        g4_next[sub] = (on && row4 < p.P) ? __ldg(reinterpret_cast<const int4*>(p.nbr + row4)) : make_int4(-1, -1, -1, -1);
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const long long row = tile_base(jt) + sub * kTileRows + r + 64 * h;
+          jn_next[2 * sub + h] = (on && row < p.P) ? __ldg(p.nbr + row) : 0;
+        }
+      }
+    };
+    load_idx(0);
+    for (int it = 0; it < n_my; ++it) {
+#pragma unroll
+      for (int q = 0; q < 4; ++q) jn[q] = jn_next[q];
+      g4[0] = g4_next[0]; g4[1] = g4_next[1];
+      load_idx(it + 1);
+      for (int j = 0; j < p.n_ld; ++j) {
+        const WorkerJob job = p.ld[j];
+        int slot;
+        unsigned use;
+        ring_at(base, p, job.blk_mod, job.blk_div, slot, use);
+        if (job.same || it >= (int)job.min_it) mbar_wait(&blk_free[job.pred], (unsigned)(job.same ? it : it - 1) & 1u);
+        if (job.kind == WK_LOAD_XYZ) {
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            const long long row = tile_base(it) + job.sub * kTileRows + r + 64 * h;
+            float xa = 0.f, xb = 0.f, xc = 0.f;
+            if (row < p.P) {
+              const int b = (int)(row / per_b);
+              const int m = (int)((row - (long long)b * per_b) / p.K);
+              const float* X = p.xyz + (long long)b * 3 * p.N;
+              const float* C = p.ctr + (long long)b * 3 * p.M;
+              const int jq = job.sub ? jn[2 + h] : jn[h];
+              xa = __fsub_rn(__ldg(X + jq), __ldg(C + m));
+              xb = __fsub_rn(__ldg(X + p.N + jq), __ldg(C + p.M + m));
+              xc = __fsub_rn(__ldg(X + 2 * p.N + jq), __ldg(C + 2 * p.M + m));
+            }
+            uint8_t* sbase = slots + (size_t)slot * kSlotBytes + (size_t)(r + 64 * h) * 16;
+            __nv_bfloat162 h0 = __floats2bfloat162_rn(xa, xb), h1 = __floats2bfloat162_rn(xc, 0.f);
+            *reinterpret_cast<uint4*>(sbase) =
+                make_uint4(*reinterpret_cast<uint32_t*>(&h0), *reinterpret_cast<uint32_t*>(&h1), 0u, 0u);
+            *reinterpret_cast<uint4*>(sbase + kTileRows * 16) = make_uint4(0u, 0u, 0u, 0u);
+          }
+          fence_proxy_async();
+          __syncwarp();
+          if (lane == 0) mbar_arrive_n(&act_ready[slot], kEpiWarps / kLoadWarps);
+        } else {
+          const bool mine = lw < ((int)job.c_count >> 6);  // warp w takes the 64-channel half w
+          if (lane == 0) {
+            if (mine) {
+              mbar_expect_tx(&act_ready[slot], 64u * kTileRows * 2u);
+              mbar_arrive_n(&act_ready[slot], kEpiWarps / kLoadWarps - 1);
+            } else {
+              mbar_arrive_n(&act_ready[slot], kEpiWarps / kLoadWarps);
+            }
+          }
+          __syncwarp();
+          if (mine) {
+            const int4 q = job.sub ? g4[1] : g4[0];
+            const long long row4 = tile_base(it) + job.sub * kTileRows + 4 * lane;
+            const int t0 = (int)(row4 / per_b) * p.N;  // K % 4 == 0: the four rows belong to one cloud
+            const bool valid = q.x >= 0;
+            tma_gather4(slots + (size_t)slot * kSlotBytes + (size_t)lw * 16384 + (size_t)lane * 512, &p.in_map,
+                        (int)job.c_begin + 64 * lw, valid ? t0 + q.x : oob, valid ? t0 + q.y : oob, valid ? t0 + q.z : oob,
+                        valid ? t0 + q.w : oob, &act_ready[slot]);
+          }
+        }
+      }
+      ring_advance(base, p);
+    }
+  } else if (TMA_IN && !GATHER && warp >= kLoadWarp0) {
     // ===================== TMA input loader: one elected thread of loader warp 0 =====================
     if (warp == kLoadWarp0) {
       Ring base = {0, 0u};
@@ -976,8 +1067,9 @@ static int s4g_chain_launch(const s4g_chain* ch, s4g::ChainParams& p, cudaStream
   S4G_CHECK_ARG(!(p.tma_in && prof), "mlp_chain: the cycle counters are not built for TMA-input chains");
   int rc = S4G_E_UNSUPPORTED;
   if (p.tma_in) {
-    if (ch->out_mode == s4g::OUT_ROWS) rc = s4g::launch_chain<false, false, s4g::OUT_ROWS, false, true>(p, grid, ch->smem_bytes, stream);
+    if (ch->out_mode == s4g::OUT_ROWS && !gather) rc = s4g::launch_chain<false, false, s4g::OUT_ROWS, false, true>(p, grid, ch->smem_bytes, stream);
     if (ch->out_mode == s4g::OUT_LOGITS) rc = s4g::launch_chain<false, false, s4g::OUT_LOGITS, false, true>(p, grid, ch->smem_bytes, stream);
+    if (ch->out_mode == s4g::OUT_MAXPOOL && gather) rc = s4g::launch_chain<false, false, s4g::OUT_MAXPOOL, true, true>(p, grid, ch->smem_bytes, stream);
   } else {
 #define S4G_CHAIN_CASE(PROF_, XYZ_, OUT_, GATHER_)                                                                     \
   if (prof == PROF_ && xyz == XYZ_ && ch->out_mode == s4g::OUT_ && gather == GATHER_)                                  \
@@ -1004,6 +1096,30 @@ static int s4g_chain_launch(const s4g_chain* ch, s4g::ChainParams& p, cudaStream
   return S4G_OK;
 }
 
+// 2-D tensor map of a bf16 row table [rows][width] (dim 0 = channels), box = 64 channels x box_rows rows, 128-byte swizzle
+static int encode_rows_map(CUtensorMap* map, const void* base, long long width, long long rows, int box_rows) {
+  typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                               const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                               CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+  static EncodeFn encode = nullptr;
+  if (!encode) {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    S4G_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+    S4G_CHECK_ARG(fn != nullptr && qres == cudaDriverEntryPointSuccess, "mlp_chain: cuTensorMapEncodeTiled is not available");
+    encode = reinterpret_cast<EncodeFn>(fn);
+  }
+  const cuuint64_t dims[2] = {(cuuint64_t)width, (cuuint64_t)rows};
+  const cuuint64_t strides[1] = {(cuuint64_t)width * 2u};
+  const cuuint32_t box[2] = {64u, (cuuint32_t)box_rows};
+  const cuuint32_t estr[2] = {1u, 1u};
+  const CUresult r = encode(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  S4G_CHECK_ARG(r == CUDA_SUCCESS, "mlp_chain: cuTensorMapEncodeTiled failed");
+  return S4G_OK;
+}
+
 // rows in: in_rows [P][in_stride] bf16 channel-last.  out: ROWS -> bf16 [P][out_c];
 // LOGITS -> fp32 (P / n_points, out_c, n_points).
 extern "C" int s4g_chain_run_rows(const s4g_chain* ch, const void* in_rows, int in_stride, long long P, void* out,
@@ -1021,27 +1137,9 @@ extern "C" int s4g_chain_run_rows(const s4g_chain* ch, const void* in_rows, int 
   p.in_stride = in_stride;
   p.out = out;
   p.n_points = n_points > 0 ? n_points : 1;
-  if (p.tma_in && P > 0) {
-    // 2-D map of the input rows: dim 0 = channels (in_stride wide), dim 1 = rows; box = 64 channels x 128 rows
-    typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
-                                 const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                 CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-    static EncodeFn encode = nullptr;
-    if (!encode) {
-      void* fn = nullptr;
-      cudaDriverEntryPointQueryResult qres;
-      S4G_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
-      S4G_CHECK_ARG(fn != nullptr && qres == cudaDriverEntryPointSuccess, "mlp_chain: cuTensorMapEncodeTiled is not available");
-      encode = reinterpret_cast<EncodeFn>(fn);
-    }
-    const cuuint64_t dims[2] = {(cuuint64_t)in_stride, (cuuint64_t)P};
-    const cuuint64_t strides[1] = {(cuuint64_t)in_stride * 2u};
-    const cuuint32_t box[2] = {64u, (cuuint32_t)s4g::kTileRows};
-    const cuuint32_t estr[2] = {1u, 1u};
-    const CUresult r = encode(&p.in_map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(in_rows), dims, strides, box,
-                              estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
-                              CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    S4G_CHECK_ARG(r == CUDA_SUCCESS, "mlp_chain: cuTensorMapEncodeTiled failed");
+  if (p.tma_in && P > 0) {  // box = 64 channels x 128 rows
+    const int rc = encode_rows_map(&p.in_map, in_rows, in_stride, P, s4g::kTileRows);
+    if (rc != S4G_OK) return rc;
   }
   return s4g_chain_launch(ch, p, (cudaStream_t)stream);
 }
@@ -1064,5 +1162,10 @@ extern "C" int s4g_chain_run_gather(const s4g_chain* ch, const void* feat, const
   p.nbr = nbr;
   p.N = N; p.M = M; p.K = K;
   p.out = out;
+  if (p.tma_in && p.P > 0) {  // tile::gather4 copies: box = 64 channels x 1 row of the feature table
+    S4G_CHECK_ARG(K % 4 == 0 && ((uintptr_t)nbr & 15) == 0, "mlp_chain: TMA gather needs K % 4 == 0 and 16-byte aligned indices");
+    const int rc = encode_rows_map(&p.in_map, feat, ch->prm.feat_c, (long long)B * N, 1);
+    if (rc != S4G_OK) return rc;
+  }
   return s4g_chain_launch(ch, p, (cudaStream_t)stream);
 }

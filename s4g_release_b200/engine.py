@@ -141,8 +141,9 @@ class FusedPointNet2:
         # two row blocks per tile (two 128-row tiles interleaved layer by layer): only narrow chains have the shared
         # memory for it; the planner refuses the others
         candidates += [(sl, -1, co, 2, 0) for sl in (0, 3, 4, 5) for co in (-1, 0, 1)]
-        # row chains: the same plans with the input blocks fetched by TMA tensor copies (refused unless cin % 64 == 0)
-        if in_mode == IN_ROWS and out_mode != OUT_MAXPOOL:
+        # the same plans with the input blocks fetched by TMA: tensor copies for row chains (refused unless
+        # cin % 64 == 0), tile::gather4 copies of the neighbours' feature rows for gathered max-pool chains
+        if (in_mode == IN_ROWS and out_mode != OUT_MAXPOOL) or (in_mode == IN_GATHER and feat_c > 0):
             candidates += [c[:4] + (1,) for c in candidates]
         for slots, pairs, coop, subs, tma in candidates:
             try:

@@ -247,3 +247,30 @@ def test_tma_input_refused_where_it_cannot_apply():
         MlpChain(_layers([32, 64], seed=1), "cuda", tma_in=1)  # 32 input channels: not a whole 128-byte row
     with pytest.raises(RuntimeError):
         MlpChain(_layers([16, 64, 64], seed=1), "cuda", in_mode=IN_GATHER, feat_c=0, out_mode=OUT_MAXPOOL, group=16, tma_in=1)
+
+
+@pytest.mark.parametrize("subs", [1, 2])
+@pytest.mark.parametrize("feat_c,dims,B,N,M,K", [(64, [64, 64, 128], 2, 1024, 64, 16), (256, [256, 256, 512], 1, 2048, 128, 64),
+                                                  (512, [512, 512, 1024], 1, 512, 64, 64), (128, [128, 128], 3, 300, 50, 8),
+                                                  (192, [64, 64], 2, 500, 33, 8), (256, [256, 256, 512], 3, 4096, 1000, 32)])
+def test_tma_gather4_input_maxpool(feat_c, dims, B, N, M, K, subs):
+    """Neighbour feature rows fetched with tile::gather4 copies (tma_in=1): bit-identical to the cp.async path (which
+    test_set_abstraction_gather_maxpool checks against torch), including ragged last tiles."""
+    from s4g_release_b200.chain import IN_GATHER, OUT_MAXPOOL, MlpChain
+    g = torch.Generator().manual_seed(feat_c + M)
+    layers = _layers([feat_c + 3] + dims, seed=M, scale=2.0)
+    xyz = torch.rand(B, 3, N, generator=g).cuda()
+    ctr = xyz[:, :, :M].contiguous()
+    nbr = torch.randint(0, N, (B, M, K), generator=g, dtype=torch.int32).cuda()
+    feat = torch.randn(B * N, feat_c, generator=g).cuda().to(torch.bfloat16)
+    try:
+        ch = MlpChain(layers, "cuda", IN_GATHER, feat_c, OUT_MAXPOOL, group=K, subs=subs, tma_in=1)
+        ref = MlpChain(layers, "cuda", IN_GATHER, feat_c, OUT_MAXPOOL, group=K, subs=subs)
+    except RuntimeError:
+        assert subs == 2
+        pytest.skip("no two-row-block plan for this chain")
+    got = ch.run_gather(feat, xyz, ctr, nbr)
+    want = ref.run_gather(feat, xyz, ctr, nbr)
+    torch.cuda.synchronize()
+    assert torch.isfinite(got.float()).all() and got.float().abs().max() > 0
+    assert torch.equal(got, want)
