@@ -8,8 +8,10 @@ from ..models.pointnet2_utils import pn2_ext
 
 
 def gather_knn_forward(feature, index):
-    if index.dim() != 3 or feature.dim() != 3 or index.size(0) != feature.size(0) or index.size(1) != feature.size(2):
-        raise RuntimeError("gather_knn_forward: feature (B,C,N) and index (B,N,K) expected")
+    # (the reference leaves index.size(1) == N unchecked, gather_knn_kernel.cu:41, and EdgeFeatureInterpolator relies
+    # on it: the queries are the DENSE points, the gathered features the sparse ones)
+    if index.dim() != 3 or feature.dim() != 3 or index.size(0) != feature.size(0):
+        raise RuntimeError("gather_knn_forward: feature (B,C,N) and index (B,M,K) expected")
     return pn2_ext.group_points_forward(feature, index)
 
 
