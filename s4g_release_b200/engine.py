@@ -85,6 +85,8 @@ class FusedPointNet2:
         self.cfg = model.config
         self.autotune = bool(autotune)
         self._copy_stream = None
+        self._geom_stream = None
+        self.overlap_geometry = True  # 3-NN searches on a side stream beside the next level's sampling
         self.device = next(model.parameters()).device
         if self.device.type != "cuda":
             raise RuntimeError("FusedPointNet2 needs the model on a CUDA device (there is no CPU path)")
@@ -306,15 +308,39 @@ class FusedPointNet2:
         feat = None  # bf16 [B*N, C] channel-last
         lv_xyz, lv_feat = [xyz], [None]
         trace = {"fps": [], "ball": []}
+        # The 3-NN searches of the propagation levels only need coordinates.  Farthest point sampling of levels >= 1 is
+        # a latency chain on at most B x cluster SMs, so the search between levels i and i + 1 runs on a side stream
+        # beside the sampling of level i + 1 (submitted after it: the sampler's CTAs are placed first): 0.54 + 0.37 ms
+        # alone, 0.56 ms together at 64 scenes (profiles/r01/overlap_probe.txt).  A stage timer then sees only the
+        # main stream's wait in "fpK.three_nn".
+        n_sa = len(self.sa_chains)
+        overlap = self.overlap_geometry
+        main = torch.cuda.current_stream()
+        pending, early_nn = None, {}
         for i, chain in enumerate(self.sa_chains):
             with _sec(timer, "sa%d.fps" % i):
                 idx = self.fps(xyz, cfg["num_centroids"][i])
+            if pending is not None:
+                dense_p, sparse_p, ready, fp_level = pending
+                if self._geom_stream is None:
+                    self._geom_stream = torch.cuda.Stream(device=xyz.device)
+                self._geom_stream.wait_event(ready)
+                with torch.cuda.stream(self._geom_stream):
+                    found = self.three_nn_weights(dense_p, sparse_p)
+                    done = torch.cuda.Event()
+                    done.record()
+                early_nn[fp_level] = (found, done)
+                pending = None
             with _sec(timer, "sa%d.gather_xyz" % i):
                 new_xyz = self.gather_xyz(xyz, idx)
             with _sec(timer, "sa%d.ball_query" % i):
                 nbr = self.ball_query(xyz, new_xyz, cfg["radius"][i], cfg["num_neighbours"][i])
             with _sec(timer, "sa%d.mlp" % i):
                 feat = chain.run_gather(feat, xyz, new_xyz, nbr)
+            if overlap and i + 1 < n_sa and len(self.fp_chains) == n_sa:
+                ready = torch.cuda.Event()
+                ready.record()  # after this level's chain: the search starts together with the next level's sampling
+                pending = (xyz, new_xyz, ready, n_sa - 1 - i)
             xyz = new_xyz
             lv_xyz.append(xyz)
             lv_feat.append(feat)
@@ -325,7 +351,13 @@ class FusedPointNet2:
         for i, chains in enumerate(self.fp_chains):
             dense_xyz, dense = lv_xyz[-2 - i], lv_feat[-2 - i]
             with _sec(timer, "fp%d.three_nn" % i):
-                idx3, w = self.three_nn_weights(dense_xyz, sparse_xyz)
+                if i in early_nn:
+                    (idx3, w), done = early_nn.pop(i)
+                    main.wait_event(done)
+                    idx3.record_stream(main)
+                    w.record_stream(main)
+                else:
+                    idx3, w = self.three_nn_weights(dense_xyz, sparse_xyz)
             with _sec(timer, "fp%d.interp_concat" % i):
                 x = self.interp_concat(sparse, idx3, w, dense, B, sparse_xyz.shape[2], dense_xyz.shape[2])
             with _sec(timer, "fp%d.mlp" % i):
