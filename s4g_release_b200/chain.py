@@ -91,14 +91,17 @@ class MlpChain:
     def flops(self, rows):
         return 2.0 * rows * sum(ci * co for ci, co in zip(self.all_cin, self.all_cout))
 
-    def run_rows(self, x, n_points=0):
-        """x: bf16 [P, stride] channel-last (stride >= cin).  Returns bf16 [P, out_c] or fp32 (B, out_c, n_points)."""
+    def run_rows(self, x, n_points=0, out=None):
+        """x: bf16 [P, stride] channel-last (stride >= cin).  Returns bf16 [P, out_c] or fp32 (B, out_c, n_points);
+        ``out``: optional preallocated contiguous result tensor of that shape and dtype (e.g. a slice of a batch)."""
         assert x.is_cuda and x.dtype == torch.bfloat16 and x.dim() == 2 and x.stride(1) == 1
         P = x.shape[0]
-        if self.out_mode == OUT_LOGITS:
-            out = torch.empty((P // n_points, self.out_c, n_points), dtype=torch.float32, device=x.device)
+        shape, dtype = (((P // n_points, self.out_c, n_points), torch.float32) if self.out_mode == OUT_LOGITS
+                        else ((P, self.out_c), torch.bfloat16))
+        if out is None:
+            out = torch.empty(shape, dtype=dtype, device=x.device)
         else:
-            out = torch.empty((P, self.out_c), dtype=torch.bfloat16, device=x.device)
+            assert tuple(out.shape) == shape and out.dtype == dtype and out.is_contiguous() and out.device == x.device
         check(lib.s4g_chain_run_rows(self._h, ptr(x), x.stride(0), P, ptr(out), n_points, stream_ptr(x.device)),
               "chain_run_rows")
         return out

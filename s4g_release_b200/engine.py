@@ -369,20 +369,27 @@ class FusedPointNet2:
         with _sec(timer, "heads.mlp"):
             outs = [None] * 4
             # widest head first: with host_out the copy that cannot hide behind a later head is then the smallest
-            for k in sorted(range(4), key=lambda k: -self.head_chains[k].out_c):
+            order = sorted(range(4), key=lambda k: -self.head_chains[k].out_c)
+            for k in order:
                 name, ch = names[k], self.head_chains[k]
-                o = ch.run_rows(sparse, n_points=n)
-                outs[k] = o
-                if host_out is not None:
-                    # stream this head's result to the caller's pinned host tensor while the next head computes
-                    if self._copy_stream is None:
-                        self._copy_stream = torch.cuda.Stream(device=o.device)
+                if host_out is None:
+                    outs[k] = ch.run_rows(sparse, n_points=n)
+                    continue
+                # stream this head's result to the caller's pinned host tensor while the next head computes; the LAST
+                # head has nothing behind it, so it runs as two half-batches: only the second half's copy is exposed
+                if self._copy_stream is None:
+                    self._copy_stream = torch.cuda.Stream(device=sparse.device)
+                o = torch.empty((B, ch.out_c, n), dtype=torch.float32, device=sparse.device)
+                cuts = [0, B // 2, B] if (k == order[-1] and B >= 2) else [0, B]
+                for b0, b1 in zip(cuts[:-1], cuts[1:]):
+                    ch.run_rows(sparse[b0 * n:b1 * n], n_points=n, out=o[b0:b1])
                     ev = torch.cuda.Event()
                     ev.record()
                     self._copy_stream.wait_event(ev)
                     with torch.cuda.stream(self._copy_stream):
-                        host_out[name].copy_(o, non_blocking=True)
-                    o.record_stream(self._copy_stream)
+                        host_out[name][b0:b1].copy_(o[b0:b1], non_blocking=True)
+                o.record_stream(self._copy_stream)
+                outs[k] = o
         if host_out is not None:
             torch.cuda.current_stream().wait_stream(self._copy_stream)  # the caller's synchronize covers the copies
         preds = dict(zip(names, outs))
