@@ -106,3 +106,21 @@ def test_host_out_streams_identical_predictions():
         torch.cuda.synchronize()
     for k in ref:
         assert torch.equal(got[k], ref[k]) and torch.equal(host[k], ref[k].cpu()), k
+
+
+def test_side_stream_three_nn_is_bit_identical():
+    """the 3-NN searches that run on a side stream beside the next level's sampling (engine.overlap_geometry) produce
+    exactly the serial schedule's predictions, call after call"""
+    import bench
+    net = bench.seeded_model().cuda().eval()
+    x = bench.synthetic_scenes(3, 1000)[:, :, :8192].contiguous().cuda()
+    eng = net.fused_engine()
+    assert eng.overlap_geometry
+    with torch.no_grad():
+        a = eng.forward(x)
+        b = eng.forward(x)
+        eng.overlap_geometry = False
+        c = eng.forward(x)
+        torch.cuda.synchronize()
+    for k in a:
+        assert torch.equal(a[k], b[k]) and torch.equal(a[k], c[k]), k
