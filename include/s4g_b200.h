@@ -61,6 +61,16 @@ int s4g_ball_query_f32(const float* points, const float* centroids, int B, int N
                        int64_t* index, int64_t* count, void* stream);
 int s4g_ball_query_f32_i32(const float* points, const float* centroids, int B, int N, int M, float radius, int K,
                            int32_t* index, int32_t* count, void* stream);
+/* The same query in two calls (reference: ball_query_kernel.cu:20-97, one call there).  The spatial index only needs the
+ * cloud, so it can be built on another stream while the centroids are still being sampled.  s4g_ball_query_uses_grid
+ * tells whether the grid path serves this shape (else use the one-call form); the build returns NULL on failure;
+ * the query's stream must be ordered after the build; the free is stream-ordered after the queries on `stream`. */
+typedef struct s4g_ball_grid s4g_ball_grid;
+int s4g_ball_query_uses_grid(int N, int K, float radius);
+s4g_ball_grid* s4g_ball_grid_build_f32(const float* points, int B, int N, float radius, void* stream);
+int s4g_ball_query_with_grid_f32_i32(const s4g_ball_grid* grid, const float* points, const float* centroids, int M, int K,
+                                     int32_t* index, int32_t* count, void* stream);
+int s4g_ball_grid_free(s4g_ball_grid* grid, void* stream);
 
 /* group_points_forward / backward — csrc/grouping.h:7-14, grouping_kernel.cu:32-54,106-152.
  * fwd: input (B,C,N), index (B,M,K) -> out (B,C,M,K).   bwd: grad_out (B,C,M,K) -> grad_in (B,C,N). */

@@ -1,6 +1,7 @@
 // Grid build + grid-accelerated ball query and 3-NN (see grid.cuh for the exactness argument).
 
 #include "grid.cuh"
+#include <new>
 
 namespace s4g {
 
@@ -498,3 +499,52 @@ template int three_nn_grid<0>(const float*, const float*, int, int, int, void*, 
 template int three_nn_grid<1>(const float*, const float*, int, int, int, void*, float*, cudaStream_t);
 
 }  // namespace s4g
+
+// ------------------------------------------------------------------------------------------------
+// Ball query in two calls: the index over the points only needs the cloud, so a caller can build it on another stream
+// while the centroids are still being sampled (engine.py runs it beside the first level's farthest point sampling).
+// ------------------------------------------------------------------------------------------------
+struct s4g_ball_grid {
+  s4g::Grid grid;
+  float radius;
+};
+
+extern "C" int s4g_ball_query_uses_grid(int N, int K, float radius) {
+  return (N >= s4g::kGridBallMinPoints && K <= s4g::kGridBallMaxK && radius > 0.f) ? 1 : 0;
+}
+
+extern "C" s4g_ball_grid* s4g_ball_grid_build_f32(const float* points, int B, int N, float radius, void* stream) {
+  if (!points || B <= 0 || B > 65535 || !s4g_ball_query_uses_grid(N, 1, radius)) {
+    s4g::set_error(S4G_E_ARG, "ball_grid_build: needs a cloud the grid path serves (s4g_ball_query_uses_grid)");
+    return nullptr;
+  }
+  s4g_ball_grid* g = new (std::nothrow) s4g_ball_grid();
+  if (!g) return nullptr;
+  g->radius = radius;
+  if (s4g::grid_build(points, B, N, s4g::GRID_BALL, radius, &g->grid, (cudaStream_t)stream) != S4G_OK) {
+    delete g;
+    return nullptr;
+  }
+  return g;
+}
+
+// same result as s4g_ball_query_f32_i32 on the cloud the grid was built from; `stream` must be ordered after the build
+extern "C" int s4g_ball_query_with_grid_f32_i32(const s4g_ball_grid* g, const float* points, const float* centroids, int M,
+                                                int K, int32_t* index, int32_t* count, void* stream) {
+  S4G_CHECK_ARG(g && points && centroids && index, "ball_query_with_grid: null pointer");
+  S4G_CHECK_ARG(M > 0 && K > 0 && K <= s4g::kGridBallMaxK, "ball_query_with_grid: bad shape");
+  const float r2 = g->radius * g->radius;
+  dim3 grid((M + s4g::kBqgWarps - 1) / s4g::kBqgWarps, g->grid.B);
+  s4g::ball_query_grid_kernel<int32_t><<<grid, s4g::kBqgWarps * 32, 0, (cudaStream_t)stream>>>(
+      points, centroids, g->grid.N, M, r2, K, g->grid.desc, g->grid.start, g->grid.sorted, index, count);
+  S4G_LAUNCH_CHECK("ball_query_grid");
+  return S4G_OK;
+}
+
+// releases the index (stream-ordered: after the queries issued on `stream`)
+extern "C" int s4g_ball_grid_free(s4g_ball_grid* g, void* stream) {
+  if (!g) return S4G_OK;
+  const int rc = s4g::grid_free(&g->grid, (cudaStream_t)stream);
+  delete g;
+  return rc;
+}

@@ -318,8 +318,26 @@ class FusedPointNet2:
         main = torch.cuda.current_stream()
         pending, early_nn = None, {}
         for i, chain in enumerate(self.sa_chains):
+            ball_grid = None
+            if overlap and lib.s4g_ball_query_uses_grid(xyz.shape[2], cfg["num_neighbours"][i], float(cfg["radius"][i])):
+                cloud_ready = torch.cuda.Event()
+                cloud_ready.record()
+            else:
+                cloud_ready = None
             with _sec(timer, "sa%d.fps" % i):
                 idx = self.fps(xyz, cfg["num_centroids"][i])
+            if cloud_ready is not None:
+                # the ball query's spatial index only needs the cloud: built beside the sampler (submitted after it)
+                if self._geom_stream is None:
+                    self._geom_stream = torch.cuda.Stream(device=xyz.device)
+                self._geom_stream.wait_event(cloud_ready)
+                with torch.cuda.stream(self._geom_stream):
+                    ball_grid = lib.s4g_ball_grid_build_f32(ptr(xyz), B, xyz.shape[2], float(cfg["radius"][i]),
+                                                            stream_ptr(xyz.device))
+                    if not ball_grid:
+                        raise RuntimeError("s4g_ball_grid_build_f32 failed: " + lib.s4g_last_error().decode())
+                    grid_done = torch.cuda.Event()
+                    grid_done.record()
             if pending is not None:
                 dense_p, sparse_p, ready, fp_level = pending
                 if self._geom_stream is None:
@@ -334,7 +352,16 @@ class FusedPointNet2:
             with _sec(timer, "sa%d.gather_xyz" % i):
                 new_xyz = self.gather_xyz(xyz, idx)
             with _sec(timer, "sa%d.ball_query" % i):
-                nbr = self.ball_query(xyz, new_xyz, cfg["radius"][i], cfg["num_neighbours"][i])
+                if ball_grid:
+                    main.wait_event(grid_done)
+                    k = cfg["num_neighbours"][i]
+                    nbr = torch.empty((B, new_xyz.shape[2], k), dtype=torch.int32, device=xyz.device)
+                    rc = lib.s4g_ball_query_with_grid_f32_i32(ball_grid, ptr(xyz), ptr(new_xyz), new_xyz.shape[2], k,
+                                                              ptr(nbr), None, stream_ptr(xyz.device))
+                    lib.s4g_ball_grid_free(ball_grid, stream_ptr(xyz.device))
+                    check(rc, "ball_query_with_grid")
+                else:
+                    nbr = self.ball_query(xyz, new_xyz, cfg["radius"][i], cfg["num_neighbours"][i])
             with _sec(timer, "sa%d.mlp" % i):
                 feat = chain.run_gather(feat, xyz, new_xyz, nbr)
             if overlap and i + 1 < n_sa and len(self.fp_chains) == n_sa:
