@@ -514,8 +514,8 @@ extern "C" int s4g_ball_query_uses_grid(int N, int K, float radius) {
 }
 
 extern "C" s4g_ball_grid* s4g_ball_grid_build_f32(const float* points, int B, int N, float radius, void* stream) {
-  if (!points || B <= 0 || B > 65535 || !s4g_ball_query_uses_grid(N, 1, radius)) {
-    s4g::set_error(S4G_E_ARG, "ball_grid_build: needs a cloud the grid path serves (s4g_ball_query_uses_grid)");
+  if (!points || B <= 0 || B > 65535 || N < 1 || !(radius > 0.f)) {
+    s4g::set_error(S4G_E_ARG, "ball_grid_build: bad cloud or radius");
     return nullptr;
   }
   s4g_ball_grid* g = new (std::nothrow) s4g_ball_grid();

@@ -319,6 +319,8 @@ class FusedPointNet2:
         pending, early_nn = None, {}
         for i, chain in enumerate(self.sa_chains):
             ball_grid = None
+            # (levels below the one-call form's grid threshold stay on the linear scan: with the build hidden the grid
+            # query of the second level, 5 120 points, still measured 0.30 ms against 0.26 ms)
             if overlap and lib.s4g_ball_query_uses_grid(xyz.shape[2], cfg["num_neighbours"][i], float(cfg["radius"][i])):
                 cloud_ready = torch.cuda.Event()
                 cloud_ready.record()

@@ -266,3 +266,31 @@ def test_gather_knn_like_the_reference_test(B, C, N, K, dtype):
     want.backward(torch.ones_like(want))
     got.backward(torch.ones_like(got))
     assert f_ref.grad.allclose(f_ours.grad)
+
+
+@pytest.mark.parametrize("B,N,M,radius,K", [(2, 25600, 5120, 0.02, 64), (3, 5120, 1024, 0.08, 64), (2, 2048, 300, 0.1, 16),
+                                             (1, 700, 64, 0.3, 8)])
+def test_ball_query_in_two_calls_matches_the_one_call_form(B, N, M, radius, K):
+    """index build (s4g_ball_grid_build_f32, here on a second stream) + query = s4g_ball_query_f32_i32, bit for bit"""
+    import ctypes
+    from s4g_release_b200._lib import check, lib, ptr
+    g = torch.Generator().manual_seed(N + M)
+    xyz = (torch.rand(B, 3, N, generator=g) * torch.tensor([1.0, 0.8, 0.3]).view(1, 3, 1)).cuda()
+    ctr = xyz[:, :, torch.randperm(N, generator=g)[:M]].contiguous()
+    want = torch.empty((B, M, K), dtype=torch.int32, device="cuda")
+    want_n = torch.empty((B, M), dtype=torch.int32, device="cuda")
+    main = torch.cuda.current_stream()
+    check(lib.s4g_ball_query_f32_i32(ptr(xyz), ptr(ctr), B, N, M, radius, K, ptr(want), ptr(want_n),
+                                     ctypes.c_void_p(main.cuda_stream)), "ball_query")
+    side = torch.cuda.Stream()
+    side.wait_stream(main)
+    grid = lib.s4g_ball_grid_build_f32(ptr(xyz), B, N, radius, ctypes.c_void_p(side.cuda_stream))
+    assert grid
+    main.wait_stream(side)
+    got = torch.empty_like(want)
+    got_n = torch.empty_like(want_n)
+    check(lib.s4g_ball_query_with_grid_f32_i32(grid, ptr(xyz), ptr(ctr), M, K, ptr(got), ptr(got_n),
+                                               ctypes.c_void_p(main.cuda_stream)), "ball_query_with_grid")
+    check(lib.s4g_ball_grid_free(grid, ctypes.c_void_p(main.cuda_stream)), "ball_grid_free")
+    torch.cuda.synchronize()
+    assert torch.equal(got, want) and torch.equal(got_n, want_n)
