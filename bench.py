@@ -204,7 +204,7 @@ def run_reference(args, rank, world):
     print(json.dumps(line), flush=True)
 
 
-TRAFFIC_FILE = "profiles/r01/ncu_launches_v18.json"
+TRAFFIC_FILE = "profiles/r01/ncu_launches_v21.json"
 
 
 def stage_traffic():
