@@ -264,7 +264,7 @@ def main():
     B = args.batch
     net = seeded_model().to(dev)
     eng = FusedPointNet2(net, mlp_backend=args.mlp_backend)
-    net._engine = eng
+    net.attach_engine(eng)
     host_scenes = synthetic_scenes(B, 1000 + rank * B).pin_memory()
     scenes = host_scenes.to(dev)
     flush = torch.empty(L2_FLUSH_BYTES, dtype=torch.uint8, device=dev)

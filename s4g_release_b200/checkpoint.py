@@ -1,75 +1,110 @@
-"""CheckPointer — on-disk compatibility with the reference's checkpoints (utils/checkpoint.py:9-91).
+"""Checkpoint files in the reference's on-disk format (the format is the contract; reference utils/checkpoint.py:26-63).
 
-File format (``torch.save`` of a dict): ``"model"`` = the model's state_dict (keys of the reference's module tree,
-which this package mirrors 1:1; a ``"module."`` prefix left by nn.DataParallel is stripped on load, :80-90),
-optional ``"optimizer"`` / ``"scheduler"`` state_dicts, plus any extra keys the caller passed to ``save``; a text file
-``last_checkpoint`` in the save directory holds the path of the newest ``<name>.pth`` and takes precedence on
-``load(resume=True)``.  Loading into a model invalidates its fused inference engine (the folded BatchNorm weights are
-rebuilt on the next eval forward).
+A checkpoint is ``torch.save`` of one dict: ``"model"`` -> state_dict under the reference's module-tree keys (this
+package mirrors that tree 1:1), optionally ``"optimizer"`` / ``"scheduler"`` state_dicts, and whatever extra entries
+the caller adds (epoch, best metric ...).  Beside the ``<name>.pth`` files a one-line text file ``last_checkpoint``
+names the newest one.  State dicts written through ``nn.DataParallel`` carry a ``module.`` prefix on every key; it is
+removed when reading (reference :81-89).
+
+Implementation notes (ours): files are written to a temporary name and renamed, so an interrupted save never leaves a
+truncated ``.pth`` behind the pointer; module functions do the work, ``CheckPointer`` is the reference-shaped handle
+(``save`` / ``load`` / ``has_checkpoint`` / ``get_check_point_path``) that scripts written for the reference call.
 """
-import collections
 import logging
 import os
+import tempfile
+from pathlib import Path
 
 import torch
 
+POINTER_NAME = "last_checkpoint"
+_DP_PREFIX = "module."
 
-class CheckPointer(object):
+
+def strip_data_parallel_prefix(state):
+    """Keys as an unwrapped model expects them (order preserved)."""
+    return {(k[len(_DP_PREFIX):] if k.startswith(_DP_PREFIX) else k): v for k, v in state.items()}
+
+
+def _atomic_write(path, writer):
+    path = Path(path)
+    fd, tmp = tempfile.mkstemp(dir=str(path.parent), prefix=path.name + ".", suffix=".tmp")
+    os.close(fd)
+    try:
+        writer(tmp)
+        os.replace(tmp, path)
+    finally:
+        if os.path.exists(tmp):
+            os.unlink(tmp)
+
+
+def write_checkpoint(directory, name, model, optimizer=None, scheduler=None, **extra):
+    """Writes ``<directory>/<name>.pth`` and points ``last_checkpoint`` at it; returns the file path."""
+    payload = dict(extra)
+    payload["model"] = model.state_dict()
+    for key, part in (("optimizer", optimizer), ("scheduler", scheduler)):
+        if part is not None:
+            payload[key] = part.state_dict()
+    target = Path(directory) / (str(name) + ".pth")
+    _atomic_write(target, lambda tmp: torch.save(payload, tmp))
+    _atomic_write(Path(directory) / POINTER_NAME, lambda tmp: Path(tmp).write_text(str(target)))
+    return str(target)
+
+
+def latest_checkpoint(directory):
+    """Path stored in ``<directory>/last_checkpoint`` or None."""
+    pointer = Path(directory) / POINTER_NAME if directory else None
+    if pointer is None or not pointer.is_file():
+        return None
+    return pointer.read_text().strip() or None
+
+
+def read_checkpoint(path, model, optimizer=None, scheduler=None):
+    """Loads ``path`` into ``model`` (strict) and, when present on both sides, optimizer / scheduler; returns the
+    remaining entries of the file.  The model's cached fused inference engine is dropped: it holds BN-folded copies
+    of the old weights."""
+    blob = torch.load(path, map_location="cpu")
+    model.load_state_dict(strip_data_parallel_prefix(blob.pop("model")), strict=True)
+    if hasattr(model, "invalidate_engine"):
+        model.invalidate_engine()
+    for key, part in (("optimizer", optimizer), ("scheduler", scheduler)):
+        if part is not None and key in blob:
+            part.load_state_dict(blob.pop(key))
+    return blob
+
+
+class CheckPointer:
+    """Reference-shaped handle: ``CheckPointer(model, optimizer, scheduler, save_dir, logger)``."""
+
     def __init__(self, model, optimizer=None, scheduler=None, save_dir="", logger=None):
-        self.model = model
-        self.optimizer = optimizer
-        self.scheduler = scheduler
+        self.model, self.optimizer, self.scheduler = model, optimizer, scheduler
         self.save_dir = save_dir
-        self.logger = logger if logger is not None else logging.getLogger(__name__)
+        self.logger = logger or logging.getLogger(__name__)
 
     def save(self, name, **kwargs):
         if not self.save_dir:
-            self.logger.warning("No save directory specified. Can not save check point")
-            return
-        data = {"model": self.model.state_dict()}
-        if self.optimizer is not None:
-            data["optimizer"] = self.optimizer.state_dict()
-        if self.scheduler is not None:
-            data["scheduler"] = self.scheduler.state_dict()
-        data.update(kwargs)
-        save_file = os.path.join(self.save_dir, "{}.pth".format(name))
-        self.logger.info("Saving checkpoint to {}".format(save_file))
-        torch.save(data, save_file)
-        with open(os.path.join(self.save_dir, "last_checkpoint"), "w") as f:
-            f.write(save_file)
-
-    def load(self, filename=None, resume=True):
-        if resume and self.has_checkpoint():
-            filename = self.get_check_point_path()  # an existing checkpoint overrides the argument
-        if not filename:
-            self.logger.info("No checkpoint found. Initializing model from scratch")
-            return {}
-        self.logger.info("Loading checkpoint from {}".format(filename))
-        checkpoint = torch.load(filename, map_location=torch.device("cpu"))
-        self.model.load_state_dict(self._compatible_from_old_version(checkpoint.pop("model")), True)
-        if hasattr(self.model, "_engine"):
-            self.model._engine = None  # the fused path re-folds BN from the new parameters
-        if "optimizer" in checkpoint and self.optimizer:
-            self.optimizer.load_state_dict(checkpoint.pop("optimizer"))
-        if "scheduler" in checkpoint and self.scheduler:
-            self.scheduler.load_state_dict(checkpoint.pop("scheduler"))
-        return checkpoint
+            self.logger.warning("checkpoint %r not written: this CheckPointer has no save_dir", name)
+            return None
+        path = write_checkpoint(self.save_dir, name, self.model, self.optimizer, self.scheduler, **kwargs)
+        self.logger.info("checkpoint written: %s", path)
+        return path
 
     def has_checkpoint(self):
-        return os.path.exists(os.path.join(self.save_dir, "last_checkpoint"))
+        return bool(self.save_dir) and (Path(self.save_dir) / POINTER_NAME).exists()
 
     def get_check_point_path(self):
-        save_file = os.path.join(self.save_dir, "last_checkpoint")
-        try:
-            with open(save_file, "r") as f:
-                return f.read().strip()
-        except IOError:
-            self.logger.warning("Last check point indicator file not exist, please check {}".format(save_file))
+        found = latest_checkpoint(self.save_dir)
+        if found is None:
+            self.logger.warning("no readable %s under %r", POINTER_NAME, self.save_dir)
             return ""
+        return found
 
-    @staticmethod
-    def _compatible_from_old_version(old_model):
-        new_model = collections.OrderedDict()
-        for key, value in old_model.items():
-            new_model[key[7:] if key.startswith("module.") else key] = value
-        return new_model
+    def load(self, filename=None, resume=True):
+        """``resume`` and a ``last_checkpoint`` pointer in save_dir -> that file wins over ``filename``; nothing to
+        load -> ``{}`` and the model keeps its initialisation."""
+        source = (latest_checkpoint(self.save_dir) if resume else None) or filename
+        if not source:
+            self.logger.info("nothing to load (no pointer file, no filename): model left as initialised")
+            return {}
+        self.logger.info("reading checkpoint %s", source)
+        return read_checkpoint(source, self.model, self.optimizer, self.scheduler)

@@ -11,6 +11,7 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from ..functions.functions import toRotMatrix
+from ..nn_utils.functional import smooth_cross_entropy
 from . import PointNet2_tcls as _tcls
 
 
@@ -25,14 +26,10 @@ class PointNet2(_tcls.PointNet2):
         nn.init.zeros_(self.t_logit.weight)
         nn.init.zeros_(self.t_logit.bias)
 
-    def _fusable(self):
-        c = self.config
-        return all(n > 0 for n in c["num_centroids"]) and all(k == 3 for k in c["num_fp_neighbours"])
-
     def forward(self, data_batch, fused=None):
         points = data_batch["scene_points"]
         if fused is None:
-            fused = (not self.training) and (not torch.is_grad_enabled()) and points.is_cuda and self._fusable()
+            fused = (not self.training) and (not torch.is_grad_enabled()) and points.is_cuda and self.fusable()
         raw = self.fused_engine().forward(points) if fused else self.forward_modules(points)
         return {"scene_score_logits": raw["score"], "frame_R": toRotMatrix(raw["frame_R"]),
                 "frame_t": points + raw["frame_t"], "movable_logits": raw["movable_logits"]}
@@ -44,8 +41,6 @@ class PointNet2Loss(nn.Module):
 
     def __init__(self, label_smoothing=0, neg_weight=0.1):
         super().__init__()
-        if label_smoothing > 0:
-            raise NotImplementedError("smooth_cross_entropy (nn_utils/functional.py) is outside the hot path")
         self.label_smoothing, self.neg_weight = label_smoothing, neg_weight
 
     def forward(self, preds, labels):
@@ -59,7 +54,13 @@ class PointNet2Loss(nn.Module):
         R_err = torch.minimum(((pred_R - gt_R) ** 2).mean(1), ((pred_R - gt_R * flip) ** 2).mean(1))
         gt_score = labels["scene_score"][:, :n]
         t_err = ((preds["frame_t"][:, :, :n] - labels["best_frame_t"]) ** 2).sum(1)
-        return {"cls_loss": F.cross_entropy(logits, labels["scene_score_labels"], weight),
+        if self.label_smoothing > 0:  # reference PointNet2.py:174-178
+            cls_loss = smooth_cross_entropy(logits.transpose(1, 2).reshape(-1, logits.shape[1]),
+                                            labels["scene_score_labels"].reshape(-1), float(self.label_smoothing),
+                                            weight=weight)
+        else:
+            cls_loss = F.cross_entropy(logits, labels["scene_score_labels"], weight)
+        return {"cls_loss": cls_loss,
                 "R_loss": (R_err * gt_score).mean() * 5.0,
                 "t_loss": (t_err * gt_score).mean() * 20.0,
                 "mov_loss": F.l1_loss(preds["movable_logits"], labels["scene_movable_labels"])}

@@ -12,6 +12,7 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
+from ..nn_utils.functional import smooth_cross_entropy
 from ..nn_utils.mlp import SharedMLP
 from .pointnet2_utils.modules import PointNetSAModule, PointnetFPModule
 
@@ -100,8 +101,6 @@ class PointNet2Loss(nn.Module):
 
     def __init__(self, label_smoothing=0, neg_weight=0.1):
         super().__init__()
-        if label_smoothing > 0:
-            raise NotImplementedError("smooth_cross_entropy (nn_utils/functional.py) is outside the hot path")
         self.label_smoothing, self.neg_weight = label_smoothing, neg_weight
 
     def forward(self, preds, labels):
@@ -115,10 +114,19 @@ class PointNet2Loss(nn.Module):
         pred_R = preds["frame_R"][:, :, :n]
         flip = gt_R.new_tensor([1, -1, -1, 1, -1, -1, 1, -1, -1]).view(1, 9, 1)
         R_err = torch.minimum(((pred_R - gt_R) ** 2).mean(1), ((pred_R - gt_R * flip) ** 2).mean(1))
-        return {"cls_loss": F.cross_entropy(logits, labels["scored_grasp_labels"], weight),
+        if self.label_smoothing > 0:  # reference :186-195
+            eps = float(self.label_smoothing)
+            cls_loss = smooth_cross_entropy(logits.permute(0, 2, 3, 1).reshape(-1, logits.shape[1]),
+                                            labels["scored_grasp_labels"].reshape(-1), eps, weight=weight)
+            mov_loss = smooth_cross_entropy(preds["movable_logits"].transpose(1, 2).reshape(-1, 2),
+                                            labels["scene_movable_labels"].reshape(-1), eps, weight=mov_weight)
+        else:
+            cls_loss = F.cross_entropy(logits, labels["scored_grasp_labels"], weight)
+            mov_loss = F.cross_entropy(preds["movable_logits"], labels["scene_movable_labels"], mov_weight)
+        return {"cls_loss": cls_loss,
                 "R_loss": R_err.mean() * 4.0,
                 "t_loss": torch.mean((preds["frame_t"][:, :, :n] - labels["best_frame_t"]) ** 2) * 20.0,
-                "mov_loss": F.cross_entropy(preds["movable_logits"], labels["scene_movable_labels"], mov_weight)}
+                "mov_loss": mov_loss}
 
 
 class PointNet2Metric(nn.Module):
