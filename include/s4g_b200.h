@@ -115,6 +115,17 @@ int s4g_interpolate_forward_f64(const double* input, const int64_t* index, const
 int s4g_interpolate_backward_f64(const double* grad_out, const int64_t* index, const double* weight, int B, int C,
                                  int Nk, int Nq, double* grad_in, void* stream);
 
+/* ---- tight-parity layer (TF32 tensor cores) ------------------------------------------------ */
+
+/* One shared-MLP block — Conv{1,2}d 1x1 (bias-free) + BatchNorm (eval, folded by the caller) + ReLU, reference
+ * nn_utils/conv.py:30-36,70-76 — as Y[P][N] = act(X[P][K] W[N][K]^T + shift[N]) on tcgen05 kind::tf32 with fp32
+ * accumulation: the arithmetic cuDNN's TF32 default gives the unmodified reference on this GPU.  X, W, Y fp32 row-major
+ * (channel-last rows), ldx / ldw multiples of 4 floats and 16-byte aligned bases; relu: apply max(.,0); round_out: round
+ * the result to the nearest TF32 value (for the next layer's operand).  Layer by layer, nothing fused: the tight-parity
+ * mode of the fused path (its throughput path is the bf16 chain below). */
+int s4g_linear_tf32(const float* x, long long ldx, const float* w, long long ldw, const float* shift, float* y,
+                    long long ldy, long long P, int N, int K, int relu, int round_out, void* stream);
+
 /* ---- fused inference path (channel-last bf16 features, int32 indices) ---------------------- */
 
 /* PointSearch (interpolate_kernel.cu:33-81) fused with the inverse-squared-distance weights of
@@ -127,6 +138,12 @@ int s4g_three_nn_weights_f32_i32(const float* query, const float* key, int B, in
  * sparse [B*Nk][C2] bf16, dense [B*Nq][C1] bf16 (NULL when C1 == 0) -> out [B*Nq][C2+C1] bf16. */
 int s4g_interp_concat_bf16(const void* sparse, const int* index, const float* weight, const void* dense, int B, int Nk,
                            int Nq, int C2, int C1, void* out, void* stream);
+/* The same with ReLU on the interpolated channels (relu != 0).  Interpolation is linear, so the first layer of a
+ * feature-propagation MLP can run on the SPARSE points first — W (sum_k w_k f_k) = sum_k w_k (W f_k), 5x fewer rows at
+ * the finest level — and this kernel then interpolates the pre-activations (shift already added: the weights sum to
+ * one) and applies the ReLU: PointnetFPModule.forward (modules.py:498-507) with conv and interpolation commuted. */
+int s4g_interp_concat_act_bf16(const void* sparse, const int* index, const float* weight, const void* dense, int B, int Nk,
+                               int Nq, int C2, int C1, int relu, void* out, void* stream);
 
 /* gather_points for xyz with int32 indices (functions.py:10-25): (B,3,N),(B,M) -> (B,3,M). */
 int s4g_gather_xyz_f32_i32(const float* xyz, const int* index, int B, int N, int M, float* out, void* stream);

@@ -1,9 +1,9 @@
-"""ncu launch-list CSV -> JSON summary (the profiles/r01/ncu_launches_*.json files).
+"""ncu launch-list CSV -> JSON summary (the profiles/rNN/ncu_launches*.json files).
 
     ncu --profile-from-start off --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum,\
-sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active,launch__registers_per_thread,launch__grid_size,\
-launch__block_size --clock-control none --csv --log-file gpurun_out/launches.csv python profiles/one_forward.py
-    python profiles/ncu_to_json.py gpurun_out/launches.csv profiles/r01/ncu_launches_vN.json [launches per forward = 46]
+sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active,smsp__issue_active.avg.pct_of_peak_sustained_active,\
+lts__t_sector_hit_rate.pct,launch__registers_per_thread,launch__grid_size,launch__block_size --clock-control none --csv --log-file gpurun_out/launches.csv python profiles/one_forward.py
+    python profiles/ncu_to_json.py gpurun_out/launches.csv profiles/r01/ncu_launches_vN.json [launches per forward = 47]
 
 Keeps the launches of the LAST forward (the first one pays lazy module loading)."""
 import csv
@@ -27,6 +27,10 @@ for r in rows[1:]:
             val * {"byte": 1e-6, "Kbyte": 1e-3, "Mbyte": 1.0, "Gbyte": 1e3}.get(unit, 1e-6), 2)
     elif name.startswith("sm__pipe_tensor"):
         e["tensor_active_pct"] = round(val, 2)
+    elif name.startswith("smsp__issue_active"):
+        e["issue_active_pct"] = round(val, 2)
+    elif name.startswith("lts__t_sector_hit_rate"):
+        e["l2_hit_pct"] = round(val, 2)
     elif name == "launch__registers_per_thread":
         e["regs"] = int(val)
     elif name == "launch__grid_size":
@@ -35,7 +39,7 @@ for r in rows[1:]:
         e["block"] = int(val)
 ids = sorted(launches)
 names = [launches[i]["kernel"] for i in ids]
-per = int(sys.argv[3]) if len(sys.argv) > 3 else 46  # launches of one forward (s4g_launch_count() per step)
+per = int(sys.argv[3]) if len(sys.argv) > 3 else 47  # launches of one forward (s4g_launch_count() per step)
 last = [launches[i] for i in ids[-per:]]
 total = sum(e["ms"] for e in last)
 for e in last:

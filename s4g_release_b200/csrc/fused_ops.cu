@@ -67,7 +67,7 @@ three_nn_weights_kernel(const float* __restrict__ query, const float* __restrict
 __global__ void __launch_bounds__(256)
 interp_concat_kernel(const __nv_bfloat16* __restrict__ sparse, const int* __restrict__ index,
                      const float* __restrict__ weight, const __nv_bfloat16* __restrict__ dense, int Nk, int Nq,
-                     int C2, int C1, long long rows, __nv_bfloat16* __restrict__ out) {
+                     int C2, int C1, long long rows, __nv_bfloat16* __restrict__ out, int relu) {
   const int lane = threadIdx.x & 31;
   const long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
   if (row >= rows) return;
@@ -93,7 +93,7 @@ interp_concat_kernel(const __nv_bfloat16* __restrict__ sparse, const int* __rest
       // fma(in2,w2, fma(in1,w1, in0*w0)) as interpolate_kernel.cu:167-174
       const float x = __fmaf_rn(fc.x, w2, __fmaf_rn(fb.x, w1, __fmul_rn(fa.x, w0)));
       const float y = __fmaf_rn(fc.y, w2, __fmaf_rn(fb.y, w1, __fmul_rn(fa.y, w0)));
-      pr[e] = __floats2bfloat162_rn(x, y);
+      pr[e] = __floats2bfloat162_rn(relu ? fmaxf(x, 0.f) : x, relu ? fmaxf(y, 0.f) : y);
     }
     o[c] = r;
   }
@@ -134,8 +134,8 @@ extern "C" int s4g_three_nn_weights_f32_i32(const float* query, const float* key
   return S4G_OK;
 }
 
-extern "C" int s4g_interp_concat_bf16(const void* sparse, const int* index, const float* weight, const void* dense,
-                                      int B, int Nk, int Nq, int C2, int C1, void* out, void* stream) {
+extern "C" int s4g_interp_concat_act_bf16(const void* sparse, const int* index, const float* weight, const void* dense,
+                                          int B, int Nk, int Nq, int C2, int C1, int relu, void* out, void* stream) {
   S4G_CHECK_ARG(sparse && index && weight && out, "interp_concat: null pointer");
   S4G_CHECK_ARG(C2 > 0 && C2 % 8 == 0 && C1 >= 0 && C1 % 8 == 0, "interp_concat: channel counts must be multiples of 8");
   S4G_CHECK_ARG(C1 == 0 || dense != nullptr, "interp_concat: dense feature missing");
@@ -144,9 +144,14 @@ extern "C" int s4g_interp_concat_bf16(const void* sparse, const int* index, cons
   const unsigned grid = (unsigned)((rows + 7) / 8);
   s4g::interp_concat_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(
       reinterpret_cast<const __nv_bfloat16*>(sparse), index, weight, reinterpret_cast<const __nv_bfloat16*>(dense), Nk,
-      Nq, C2, C1, rows, reinterpret_cast<__nv_bfloat16*>(out));
+      Nq, C2, C1, rows, reinterpret_cast<__nv_bfloat16*>(out), relu);
   S4G_LAUNCH_CHECK("interp_concat");
   return S4G_OK;
+}
+
+extern "C" int s4g_interp_concat_bf16(const void* sparse, const int* index, const float* weight, const void* dense,
+                                      int B, int Nk, int Nq, int C2, int C1, void* out, void* stream) {
+  return s4g_interp_concat_act_bf16(sparse, index, weight, dense, B, Nk, Nq, C2, C1, 0, out, stream);
 }
 
 extern "C" int s4g_gather_xyz_f32_i32(const float* xyz, const int* index, int B, int N, int M, float* out,

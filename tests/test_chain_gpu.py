@@ -274,3 +274,74 @@ def test_tma_gather4_input_maxpool(feat_c, dims, B, N, M, K, subs):
     torch.cuda.synchronize()
     assert torch.isfinite(got.float()).all() and got.float().abs().max() > 0
     assert torch.equal(got, want)
+
+
+@pytest.mark.parametrize("kind", ["rows", "logits", "gather", "gather_feat", "rows_linear"])
+def test_every_tunable_plan_is_bit_identical(kind):
+    """Every plan constraint set the engine's tuner may pin (engine.candidate_plans: ring sizes, accumulator pairing,
+    cooperative epilogues, one / two row blocks per tile, cp.async / TMA input) yields the SAME bits: each accumulator
+    sums its K-blocks in the same order in all of them, so the tuned choice can never change a result."""
+    from s4g_release_b200.chain import IN_GATHER, IN_ROWS, OUT_LOGITS, OUT_MAXPOOL, OUT_ROWS, MlpChain
+    from s4g_release_b200.engine import candidate_plans
+    g = torch.Generator().manual_seed(5)
+    if kind in ("rows", "logits", "rows_linear"):
+        dims = {"rows": [512, 256, 256, 256], "logits": [256, 512, 256, 256, 128, 9], "rows_linear": [512, 256]}[kind]
+        in_mode, feat_c, group = IN_ROWS, 0, 1
+        out_mode = OUT_LOGITS if kind == "logits" else OUT_ROWS
+        layers = _layers(dims, seed=3, relu_last=(kind == "rows"))
+        P = 128 * 37 + 61
+        x = torch.randn(P, dims[0], generator=g).cuda().to(torch.bfloat16)
+        run = lambda ch: ch.run_rows(x, n_points=P if kind == "logits" else 0)
+    else:
+        feat_c = 256 if kind == "gather_feat" else 0
+        dims = [256, 256, 512] if feat_c else [128, 128, 256]
+        in_mode, out_mode, group = IN_GATHER, OUT_MAXPOOL, 64
+        layers = _layers([feat_c + 3] + dims, seed=4, scale=2.0)
+        B, N, M = 2, 4096, 300
+        xyz = torch.rand(B, 3, N, generator=g).cuda()
+        ctr = xyz[:, :, :M].contiguous()
+        nbr = torch.randint(0, N, (B, M, group), generator=g, dtype=torch.int32).cuda()
+        feat = torch.randn(B * N, feat_c, generator=g).cuda().to(torch.bfloat16) if feat_c else None
+        run = lambda ch: ch.run_gather(feat, xyz, ctr, nbr)
+    want, seen = None, set()
+    for slots, pairs, coop, subs, tma in candidate_plans(in_mode, feat_c, out_mode):
+        try:
+            ch = MlpChain(layers, "cuda", in_mode, feat_c, out_mode, group=group, slots=slots, pairs=pairs, coop=coop,
+                          subs=subs, tma_in=tma)
+        except RuntimeError:
+            continue  # the planner has no deadlock-free plan under these constraints
+        key = (ch.describe(), tma)
+        if key in seen:
+            continue
+        seen.add(key)
+        got = run(ch)
+        torch.cuda.synchronize()
+        if want is None:
+            want = got
+        assert torch.equal(got, want), "plan %r differs from the planner's default" % ((slots, pairs, coop, subs, tma),)
+    assert len(seen) >= 4, "only %d distinct plans were exercised" % len(seen)
+
+
+@pytest.mark.parametrize("P,N,K,relu", [(128, 128, 32, True), (300, 70, 45, True), (1000, 260, 515, False),
+                                        (4096, 512, 256, True), (77, 9, 128, False), (129, 1024, 1536, True)])
+def test_linear_tf32_layer(P, N, K, relu):
+    """csrc/linear_tf32.cu (tcgen05 kind::tf32) against fp64 on the SAME TF32-rounded operands: what is left is fp32
+    accumulation order, |err| <= 2e-5 * sum|x||w| scale (stated as 1e-4 * max|ref|)."""
+    from s4g_release_b200.engine import FusedPointNet2 as E
+    g = torch.Generator().manual_seed(P + N + K)
+    x = E._round_tf32(torch.randn(P, K, generator=g))
+    w = E._round_tf32(torch.randn(N, K, generator=g) / np.sqrt(K))
+    b = torch.randn(N, generator=g) * 0.1
+    K4 = (K + 3) // 4 * 4
+    wp = torch.zeros(N, K4)
+    wp[:, :K] = w
+    got = E.linear_tf32(x.cuda(), wp.cuda(), b.cuda(), relu=relu, round_out=False)
+    torch.cuda.synchronize()
+    want = x.double() @ w.double().t() + b.double()
+    if relu:
+        want = torch.relu(want)
+    err = (got.double().cpu() - want).abs().max().item()
+    assert tuple(got.shape) == (P, N) and err <= 1e-4 * max(1.0, want.abs().max().item()), err
+    # round_out: the stored value is the nearest TF32 of the same result
+    got_r = E.linear_tf32(x.cuda(), wp.cuda(), b.cuda(), relu=relu, round_out=True)
+    assert torch.equal(got_r.cpu(), E._round_tf32(got.cpu()))

@@ -124,3 +124,42 @@ def test_side_stream_three_nn_is_bit_identical():
         torch.cuda.synchronize()
     for k in a:
         assert torch.equal(a[k], b[k]) and torch.equal(a[k], c[k]), k
+
+
+def test_tf32_tight_parity_backend(cloud_2638, golden_full):
+    """mlp_backend="tf32" (csrc/linear_tf32.cu, one tcgen05 kind::tf32 launch per layer): the tight-parity mode of
+    SURVEY.md §7 on BASELINE config 1.  Stated tolerance: head outputs within 4e-3 * max(1, max|ref|) of the fp32
+    oracle golden (10-bit mantissa operands, 17 layers deep); geometry bit-exact."""
+    from s4g_release_b200.engine import FusedPointNet2
+    from s4g_release_b200.network_models.models.PointNet2_tcls import PN2_CLS_CONFIG, PointNet2
+    from tests.golden.make_golden import seed_reference_weights
+    torch.manual_seed(0)
+    net = seed_reference_weights(PointNet2(**PN2_CLS_CONFIG)).cuda().eval()
+    eng = FusedPointNet2(net, mlp_backend="tf32")
+    out, trace = eng.forward(torch.from_numpy(cloud_2638)[None].cuda(), return_trace=True)
+    torch.cuda.synchronize()
+    for i in range(3):
+        assert np.array_equal(trace["fps"][i].cpu().numpy(), golden_full[f"sa{i}/fps_index"])
+    stride = int(golden_full["stride"])
+    worst = max(_rel_err(out[k][:, :, ::stride], golden_full["out/" + k]) for k in HEADS)
+    print("tf32 backend: worst head error %.3e" % worst)
+    assert worst <= eng.tolerance() == 4e-3
+
+
+def test_fp_linear_split_matches_the_concat_order(cloud_2638):
+    """The finest propagation level runs its first conv on the sparse points and interpolates the pre-activations
+    (engine.fp_linear_split; conv and interpolation commute).  Against the interpolate-then-conv order of the reference
+    the difference is only where the bf16 rounding happens: <= 2e-2 * max|ref| on every head (measured ~3e-3)."""
+    from s4g_release_b200.engine import FusedPointNet2
+    from s4g_release_b200.network_models.models.PointNet2_tcls import PN2_CLS_CONFIG, PointNet2
+    from tests.golden.make_golden import seed_reference_weights
+    torch.manual_seed(0)
+    net = seed_reference_weights(PointNet2(**PN2_CLS_CONFIG)).cuda().eval()
+    x = torch.from_numpy(cloud_2638)[None].cuda()
+    a = FusedPointNet2(net, fp_linear_split=True)
+    b = FusedPointNet2(net, fp_linear_split=False)
+    assert a.fp_pre[2] is not None and a.fp_pre[0] is None and all(p is None for p in b.fp_pre)
+    oa, ob = a.forward(x), b.forward(x)
+    torch.cuda.synchronize()
+    for k in HEADS:
+        assert _rel_err(oa[k], ob[k].float().cpu()) <= 2e-2, k
