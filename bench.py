@@ -326,8 +326,18 @@ def bind_to_gpu_numa_node(gpu_index):
     try:
         import pynvml
         pynvml.nvmlInit()
-        pynvml.nvmlDeviceSetCpuAffinity(pynvml.nvmlDeviceGetHandleByIndex(gpu_index))
-        return sorted(os.sched_getaffinity(0))
+        try:  # CUDA_VISIBLE_DEVICES may renumber the devices: resolve the NVML handle through the UUID
+            uuid = "GPU-" + str(torch.cuda.get_device_properties(gpu_index).uuid)
+            handle = pynvml.nvmlDeviceGetHandleByUUID(uuid.encode())
+        except Exception:
+            handle = pynvml.nvmlDeviceGetHandleByIndex(gpu_index)
+        before = os.sched_getaffinity(0)
+        pynvml.nvmlDeviceSetCpuAffinity(handle)
+        after = os.sched_getaffinity(0)
+        if len(after) < 4:  # a container cpuset that barely intersects the node: keep what we had
+            os.sched_setaffinity(0, before)
+            return None
+        return sorted(after)
     except Exception:
         return None
 

@@ -6,7 +6,7 @@ Sources: inference/grasp_proposal/network_models/models/pointnet2_utils/csrc/
          {sampling,ball_query,grouping,interpolate}_kernel.cu + main.cpp
 Flags mirror the reference's setup.py (nvcc -O2, default -fmad=true) plus the arch.
 
-The module only RUNS on a GPU (tests/test_ref_cuda_parity.py, tests/golden/make_ref_cuda_golden.py).
+The module only RUNS on a GPU (tests/test_ref_cuda_parity.py, tests/test_reference_dropin_gpu.py, bench.py reference_cuda).
 """
 import os
 import subprocess

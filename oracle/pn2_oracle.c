@@ -9,8 +9,8 @@
  * Parity pinning: the reference ships no golden vectors for these ops
  * (SURVEY.md §8c).  This file is pinned against the reference's own CUDA
  * kernels compiled unmodified for sm_100a (oracle/_ref, see build_ref.py) by
- * tests/test_ref_cuda_parity.py on the GPU box, and against fixtures captured
- * from such a run (tests/golden/ref_cuda_*.npz).
+ * tests/test_ref_cuda_parity.py on the GPU box (reference CUDA vs this file vs the
+ * sm_100a kernels, three ways, on the same seeded inputs).
  *
  * Every distance follows the arithmetic nvcc emits for the reference
  * expression (x2-x1)*(x2-x1)+(y2-y1)*(y2-y1)+(z2-z1)*(z2-z1) under the default

@@ -203,7 +203,12 @@ bool build_draft(const s4g_chain* ch, const int* relu, int feat_c, int S, bool p
   // The one-bit barrier phase makes "wait for the release of block pred in the previous tile" ambiguous when
   // that block of the CURRENT tile can already be dead, i.e. when pred < b for an epilogue-produced block,
   // which needs more slots than blocks per tile.  Chains with hidden layers therefore keep S <= blocks per tile.
-  if (!d.epi.empty() && d.epi[0].kind == WK_EPI_HIDDEN && S > nB) return false;
+  // The same holds for loader-produced blocks: with S > nB a block inherits its slot from a tile SEVERAL iterations
+  // back, its first wait (at iteration min_it) is then up to min_it completions away from the barrier, and a parity
+  // wait that far behind passes on the wrong phase — the loader overwrote a block the MMA warp had not read yet and
+  // published its slot twice (tiles of a single 64-channel block, e.g. a 64 -> 32 layer, from the 4th tile of a CTA on:
+  // mbarrier dead-lock -> trap; found by the tuner on the tiny test model, round 2).  So: S <= blocks per tile, always.
+  if (S > nB) return false;
   for (HLoad& l : d.loads) pred_of(l.blk, l.pred, l.same, l.min_it);
   for (HEpi& e : d.epi)
     if (e.kind == WK_EPI_HIDDEN) pred_of(e.blk, e.pred, e.same, e.min_it);
@@ -467,7 +472,7 @@ int plan_chain(s4g_chain* ch, int n_layers, const int* cin, const int* cout, con
   // force_slots > 0 restricts the search to that many activation slots (the rest of shared memory goes to weight
   // stages): the simulation ranks slot counts imperfectly — the set-abstraction level 2 chain runs 23 % faster with 5
   // slots than with the 3 it prefers — so the host can time the alternatives and pin the best (engine.py autotune)
-  for (int S = kMaxSlots; S >= 2; --S) {
+  for (int S = kMaxSlots; S >= 1; --S) {
     if (force_slots > 0 && S != force_slots) continue;
     int stages = (kSmemBudget - S * kSlotBytes) / kStageBytes;
     if (stages < 2) continue;

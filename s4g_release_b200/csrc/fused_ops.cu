@@ -63,44 +63,79 @@ three_nn_weights_kernel(const float* __restrict__ query, const float* __restrict
   }
 }
 
-// one warp per query row; each lane moves 16-byte pieces (8 bf16 channels)
+// One warp per kInterpRows consecutive query rows of one cloud (blockIdx.y = cloud: no 64-bit divisions); the 3 x 4
+// neighbour indices / weights of the rows are one coalesced load by 12 lanes and travel by shuffle; per 16-byte piece
+// (8 bf16 channels) the 3 x 4 gathered loads of all rows are issued before any arithmetic, so 12 requests per lane are
+// in flight.  (r1 kernel: one row per warp, index arithmetic in 64 bit per lane — 24.7 % of the HBM peak with 61 % of the
+// issue slots busy at the finest level, profiles/r02/ncu_geometry.txt.)
+constexpr int kInterpRows = 4;
+
+__device__ __forceinline__ uint32_t interp_pair(uint32_t a, uint32_t b, uint32_t c, float w0, float w1, float w2, bool relu) {
+  // bf16 -> fp32 is a 16-bit shift; fma(in2,w2, fma(in1,w1, in0*w0)) as interpolate_kernel.cu:167-174
+  const float x = __fmaf_rn(__uint_as_float(c << 16), w2, __fmaf_rn(__uint_as_float(b << 16), w1, __fmul_rn(__uint_as_float(a << 16), w0)));
+  const float y = __fmaf_rn(__uint_as_float(c & 0xffff0000u), w2,
+                            __fmaf_rn(__uint_as_float(b & 0xffff0000u), w1, __fmul_rn(__uint_as_float(a & 0xffff0000u), w0)));
+  __nv_bfloat162 h = __floats2bfloat162_rn(x, y);
+  uint32_t r = *reinterpret_cast<uint32_t*>(&h);
+  if (relu) asm("max.bf16x2 %0, %1, %2;" : "=r"(r) : "r"(r), "r"(0u));
+  return r;
+}
+
 __global__ void __launch_bounds__(256)
 interp_concat_kernel(const __nv_bfloat16* __restrict__ sparse, const int* __restrict__ index,
                      const float* __restrict__ weight, const __nv_bfloat16* __restrict__ dense, int Nk, int Nq,
-                     int C2, int C1, long long rows, __nv_bfloat16* __restrict__ out, int relu) {
+                     int C2, int C1, __nv_bfloat16* __restrict__ out, int relu) {
   const int lane = threadIdx.x & 31;
-  const long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
-  if (row >= rows) return;
-  const long long b = row / Nq;
-  const int* idx = index + row * 3;
-  const float* w = weight + row * 3;
-  const int j0 = idx[0], j1 = idx[1], j2 = idx[2];
-  const float w0 = w[0], w1 = w[1], w2 = w[2];
-  const uint4* s0 = reinterpret_cast<const uint4*>(sparse + (b * Nk + j0) * C2);
-  const uint4* s1 = reinterpret_cast<const uint4*>(sparse + (b * Nk + j1) * C2);
-  const uint4* s2 = reinterpret_cast<const uint4*>(sparse + (b * Nk + j2) * C2);
-  uint4* o = reinterpret_cast<uint4*>(out + row * (long long)(C2 + C1));
-  for (int c = lane; c < C2 / 8; c += 32) {
-    const uint4 a = __ldg(s0 + c), bq = __ldg(s1 + c), cq = __ldg(s2 + c);
-    const __nv_bfloat162* pa = reinterpret_cast<const __nv_bfloat162*>(&a);
-    const __nv_bfloat162* pb = reinterpret_cast<const __nv_bfloat162*>(&bq);
-    const __nv_bfloat162* pc = reinterpret_cast<const __nv_bfloat162*>(&cq);
-    uint4 r;
-    __nv_bfloat162* pr = reinterpret_cast<__nv_bfloat162*>(&r);
+  const int b = blockIdx.y;
+  const int row0 = (blockIdx.x * 8 + (threadIdx.x >> 5)) * kInterpRows;
+  if (row0 >= Nq) return;
+  const int n_rows = min(kInterpRows, Nq - row0);
+  const size_t q0 = (size_t)b * Nq + row0;  // first (batch-global) query row of this warp
+  int my_i = 0;
+  float my_w = 0.f;
+  if (lane < 3 * n_rows) {
+    my_i = __ldg(index + q0 * 3 + lane);
+    my_w = __ldg(weight + q0 * 3 + lane);
+  }
+  const uint4* src[kInterpRows][3];
+  float w[kInterpRows][3];
 #pragma unroll
-    for (int e = 0; e < 4; ++e) {
-      const float2 fa = __bfloat1622float2(pa[e]), fb = __bfloat1622float2(pb[e]), fc = __bfloat1622float2(pc[e]);
-      // fma(in2,w2, fma(in1,w1, in0*w0)) as interpolate_kernel.cu:167-174
-      const float x = __fmaf_rn(fc.x, w2, __fmaf_rn(fb.x, w1, __fmul_rn(fa.x, w0)));
-      const float y = __fmaf_rn(fc.y, w2, __fmaf_rn(fb.y, w1, __fmul_rn(fa.y, w0)));
-      pr[e] = __floats2bfloat162_rn(relu ? fmaxf(x, 0.f) : x, relu ? fmaxf(y, 0.f) : y);
+  for (int r = 0; r < kInterpRows; ++r)
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      const int j = __shfl_sync(0xffffffffu, my_i, 3 * r + k);  // rows past n_rows read index 0 (valid) and are not stored
+      w[r][k] = __shfl_sync(0xffffffffu, my_w, 3 * r + k);
+      src[r][k] = reinterpret_cast<const uint4*>(sparse + ((size_t)b * Nk + j) * C2);
     }
-    o[c] = r;
+  const int width = C2 + C1;
+  for (int c = lane; c < C2 / 8; c += 32) {
+    uint4 v[kInterpRows][3];
+#pragma unroll
+    for (int r = 0; r < kInterpRows; ++r)
+#pragma unroll
+      for (int k = 0; k < 3; ++k) v[r][k] = __ldg(src[r][k] + c);
+#pragma unroll
+    for (int r = 0; r < kInterpRows; ++r) {
+      if (r < n_rows) {
+        uint4 o;
+        o.x = interp_pair(v[r][0].x, v[r][1].x, v[r][2].x, w[r][0], w[r][1], w[r][2], relu);
+        o.y = interp_pair(v[r][0].y, v[r][1].y, v[r][2].y, w[r][0], w[r][1], w[r][2], relu);
+        o.z = interp_pair(v[r][0].z, v[r][1].z, v[r][2].z, w[r][0], w[r][1], w[r][2], relu);
+        o.w = interp_pair(v[r][0].w, v[r][1].w, v[r][2].w, w[r][0], w[r][1], w[r][2], relu);
+        reinterpret_cast<uint4*>(out + (q0 + r) * width)[c] = o;
+      }
+    }
   }
   if (C1 > 0) {
-    const uint4* d = reinterpret_cast<const uint4*>(dense + row * (long long)C1);
-    uint4* od = o + C2 / 8;
-    for (int c = lane; c < C1 / 8; c += 32) od[c] = __ldg(d + c);
+    for (int c = lane; c < C1 / 8; c += 32) {
+      uint4 d[kInterpRows];
+#pragma unroll
+      for (int r = 0; r < kInterpRows; ++r)
+        if (r < n_rows) d[r] = __ldg(reinterpret_cast<const uint4*>(dense + (q0 + r) * C1) + c);
+#pragma unroll
+      for (int r = 0; r < kInterpRows; ++r)
+        if (r < n_rows) reinterpret_cast<uint4*>(out + (q0 + r) * width + C2)[c] = d[r];
+    }
   }
 }
 
@@ -139,12 +174,14 @@ extern "C" int s4g_interp_concat_act_bf16(const void* sparse, const int* index, 
   S4G_CHECK_ARG(sparse && index && weight && out, "interp_concat: null pointer");
   S4G_CHECK_ARG(C2 > 0 && C2 % 8 == 0 && C1 >= 0 && C1 % 8 == 0, "interp_concat: channel counts must be multiples of 8");
   S4G_CHECK_ARG(C1 == 0 || dense != nullptr, "interp_concat: dense feature missing");
-  const long long rows = (long long)B * Nq;
-  if (rows == 0) return S4G_OK;
-  const unsigned grid = (unsigned)((rows + 7) / 8);
+  S4G_CHECK_ARG(B >= 0 && B <= 65535 && Nq > 0 && Nk > 0, "interp_concat: bad shape");
+  S4G_CHECK_ARG(((uintptr_t)sparse & 15) == 0 && ((uintptr_t)out & 15) == 0 && ((uintptr_t)dense & 15) == 0,
+                "interp_concat: feature rows must be 16-byte aligned");
+  if (B == 0) return S4G_OK;
+  const dim3 grid((unsigned)((Nq + 8 * s4g::kInterpRows - 1) / (8 * s4g::kInterpRows)), (unsigned)B);
   s4g::interp_concat_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(
       reinterpret_cast<const __nv_bfloat16*>(sparse), index, weight, reinterpret_cast<const __nv_bfloat16*>(dense), Nk,
-      Nq, C2, C1, rows, reinterpret_cast<__nv_bfloat16*>(out), relu);
+      Nq, C2, C1, reinterpret_cast<__nv_bfloat16*>(out), relu);
   S4G_LAUNCH_CHECK("interp_concat");
   return S4G_OK;
 }

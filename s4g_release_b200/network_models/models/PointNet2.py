@@ -64,3 +64,32 @@ class PointNet2Loss(nn.Module):
                 "R_loss": (R_err * gt_score).mean() * 5.0,
                 "t_loss": (t_err * gt_score).mean() * 20.0,
                 "mov_loss": F.l1_loss(preds["movable_logits"], labels["scene_movable_labels"])}
+
+
+class PointNet2Metric(nn.Module):
+    """PointNet2.py:216-255: per-point score-class and movable accuracies (unreduced 0/1 tensors), score-weighted geodesic
+    angle to the closer of the ground-truth frame and its flip about x, mean translation error."""
+
+    def forward(self, preds, labels):
+        cls_acc = (preds["scene_score_logits"].argmax(1).reshape(-1) == labels["scene_score_labels"].reshape(-1)).float()
+        mov_acc = ((preds["movable_logits"] > 0.5).reshape(-1).int() ==
+                   labels["scene_movable_labels"].reshape(-1).int()).float()
+        gt = labels["best_frame_R"]
+        b, _, n = gt.shape
+        gt = gt.transpose(1, 2).reshape(b * n, 3, 3)
+        pred = preds["frame_R"][:, :, :n].transpose(1, 2).reshape(b * n, 3, 3)
+        angle = torch.minimum(_tcls._rotation_angle(gt, pred),
+                              _tcls._rotation_angle(gt * gt.new_tensor([1.0, -1.0, -1.0]), pred))
+        R_err = (labels["scene_score"][:, :n].reshape(-1) * angle).mean()
+        t_err = torch.sqrt(((labels["best_frame_t"] - preds["frame_t"][:, :, :n]) ** 2).sum(1)).mean()
+        return {"cls_acc": cls_acc, "mov_acc": mov_acc, "R_err": R_err, "t_err": t_err}
+
+
+def build_pointnet2(cfg):
+    """PointNet2.py:258-280 (``MODEL.PN2`` node)."""
+    node = cfg.MODEL.PN2
+    net = PointNet2(score_classes=cfg.DATA.SCORE_CLASSES, num_centroids=node.NUM_CENTROIDS, radius=node.RADIUS,
+                    num_neighbours=node.NUM_NEIGHBOURS, sa_channels=node.SA_CHANNELS, fp_channels=node.FP_CHANNELS,
+                    num_fp_neighbours=node.NUM_FP_NEIGHBOURS, seg_channels=node.SEG_CHANNELS,
+                    dropout_prob=node.DROPOUT_PROB)
+    return net, PointNet2Loss(label_smoothing=node.LABEL_SMOOTHING, neg_weight=node.NEG_WEIGHT), PointNet2Metric()

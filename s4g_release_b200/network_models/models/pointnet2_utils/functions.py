@@ -71,7 +71,12 @@ class _FeatureInterpolate(torch.autograd.Function):
 
 
 def gather_points(points, index):
-    """points (B,C,N), index (B,M) -> (B,C,M); differentiable through torch.gather like the reference."""
+    """points (B,C,N), index (B,M) -> (B,C,M) — reference functions.py:10-25.  Without autograd on fp32 CUDA tensors
+    this is one launch of the library's gather kernel (s4g_gather_points_f32: the index row is read once for all C
+    channels); whenever a gradient may be needed it is torch.gather, differentiable like the reference's."""
+    if (points.is_cuda and points.dtype == torch.float32 and index.dtype == torch.int64 and
+            not (torch.is_grad_enabled() and points.requires_grad)):
+        return pn2_ext.gather_points(points, index)
     return points.gather(2, index.unsqueeze(1).expand(points.size(0), points.size(1), index.size(1)))
 
 

@@ -104,6 +104,23 @@ def group_points_forward(input, index):
     return out
 
 
+def gather_points(points, index):
+    """(B,C,N) fp32, (B,M) int64 -> (B,C,M): out[b,c,m] = points[b,c,index[b,m]].  Not one of the reference's seven
+    extension functions — its ``functions.gather_points`` (functions.py:10-25) is a torch.gather; this is the same
+    result from the library's kernel for the no-autograd path."""
+    points = _cuda_f32(points, "points")
+    index = _cuda_i64(index, "index")
+    _require(points.dtype == torch.float32, "gather_points: float32 only")
+    _require(points.dim() == 3 and index.dim() == 2 and index.size(0) == points.size(0), "gather_points: bad shapes")
+    B, C, N = points.shape
+    M = index.size(1)
+    with torch.cuda.device(points.device):
+        out = torch.empty((B, C, M), dtype=points.dtype, device=points.device)
+        check(lib.s4g_gather_points_f32(ptr(points), ptr(index), B, C, N, M, ptr(out), stream_ptr(points.device)),
+              "gather_points")
+    return out
+
+
 def group_points_backward(grad_output, index, num_points):
     """(B,C,M,K),(B,M,K), N -> (B,C,N).  grouping.h:11-14 / grouping_kernel.cu:106-152."""
     grad_output = _cuda_f32(grad_output, "grad_output")

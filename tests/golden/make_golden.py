@@ -19,7 +19,7 @@ What it does
 
 The ops inside are the C restatement, so these fixtures pin the *python layer* of the oracle
 (modules / model / post-process maths).  The ops themselves are pinned against the reference's CUDA
-kernels by tests/golden/make_ref_cuda_golden.py (run on the GPU box).
+kernels by tests/test_ref_cuda_parity.py (three-way, on the GPU box).
 """
 import hashlib
 import os

@@ -345,3 +345,32 @@ def test_linear_tf32_layer(P, N, K, relu):
     # round_out: the stored value is the nearest TF32 of the same result
     got_r = E.linear_tf32(x.cuda(), wp.cuda(), b.cuda(), relu=relu, round_out=True)
     assert torch.equal(got_r.cpu(), E._round_tf32(got.cpu()))
+
+
+@pytest.mark.parametrize("dims", [[64, 32], [16, 32], [64, 64], [32, 32, 32]])
+def test_many_tiles_of_a_one_block_chain(dims):
+    """Regression (round 2): chains whose tile is a single activation block ran into a slot-phase ambiguity from the 4th
+    tile of a CTA on (mbarrier dead-lock -> trap) under plans with more slots than blocks.  40 tiles per CTA, every plan
+    the tuner may try, result checked against torch."""
+    from s4g_release_b200.chain import IN_ROWS, OUT_ROWS, MlpChain
+    from s4g_release_b200.engine import candidate_plans
+    layers = _layers(dims, seed=11)
+    P = 148 * 40 * 128 + 77
+    x = _bf(torch.randn(P, dims[0], generator=torch.Generator().manual_seed(3)))
+    want = _bf(_ref_chain(x[:4096], layers))
+    xd = x.cuda().to(torch.bfloat16)
+    seen = set()
+    for slots, pairs, coop, subs, tma in candidate_plans(IN_ROWS, 0, OUT_ROWS):
+        try:
+            ch = MlpChain(layers, "cuda", IN_ROWS, 0, OUT_ROWS, slots=slots, pairs=pairs, coop=coop, subs=subs, tma_in=tma)
+        except RuntimeError:
+            continue
+        key = (ch.describe(), tma)
+        if key in seen:
+            continue
+        seen.add(key)
+        for _ in range(3):
+            got = ch.run_rows(xd)
+        torch.cuda.synchronize()
+        _check(got[:4096], want)
+    assert seen

@@ -84,3 +84,28 @@ def test_rejects_unsupported_shapes():
     assert _plan([67, 64], IN_GATHER, 60, OUT_MAXPOOL, 64)[0] is None  # feat_c not a multiple of 16
     assert _plan([64, 64], IN_ROWS, 0, OUT_MAXPOOL, 128)[0] is None    # group 128 unsupported
     assert _plan([64, 64, 40], IN_ROWS, 0, OUT_LOGITS)[0] is None      # > 16 logits
+
+
+@pytest.mark.parametrize("dims", [[64, 32], [16, 32], [64, 64], [128, 96], [512, 256], [32, 32, 32], [1536, 1024]])
+def test_never_more_slots_than_blocks_per_tile(dims):
+    """Round-2 planner fix: a block must inherit its slot from the SAME or the PREVIOUS tile — with more slots than
+    activation blocks per tile the loader's first slot wait is several barrier completions behind and passes on the
+    wrong one-bit phase (a 64 -> 32 chain dead-locked from the 4th tile of a CTA on).  Every constraint set the tuner
+    may pin must respect slots <= blocks per tile."""
+    n = len(dims) - 1
+    arr = lambda v: (ctypes.c_int * n)(*v)
+    checked = 0
+    for slots in (0, 1, 2, 3, 4, 5, 6):
+        for subs in (1, 2):
+            for tma in (0, 1):
+                h = lib.s4g_chain_create_tuned_in(n, arr(dims[:-1]), arr(dims[1:]), arr([1] * n), IN_ROWS, 0, OUT_ROWS, dims[-1],
+                                                  1, 0, slots, -1, -1, subs, tma)
+                if not h:
+                    continue
+                buf = ctypes.create_string_buffer(1 << 16)
+                lib.s4g_chain_describe(h, buf, len(buf))
+                lib.s4g_chain_destroy(h)
+                head = dict(kv.split("=") for kv in buf.value.decode().splitlines()[0].split() if "=" in kv)
+                assert int(head["slots"]) <= int(head["n_act"]), (slots, subs, tma, head)
+                checked += 1
+    assert checked >= 2

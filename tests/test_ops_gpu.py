@@ -294,3 +294,21 @@ def test_ball_query_in_two_calls_matches_the_one_call_form(B, N, M, radius, K):
     check(lib.s4g_ball_grid_free(grid, ctypes.c_void_p(main.cuda_stream)), "ball_grid_free")
     torch.cuda.synchronize()
     assert torch.equal(got, want) and torch.equal(got_n, want_n)
+
+
+@pytest.mark.parametrize("B,C,N,M", [(2, 3, 5120, 1024), (3, 64, 777, 300), (1, 1, 10, 10), (2, 259, 1024, 7)])
+def test_gather_points_kernel_equals_torch_gather(ext, B, C, N, M):
+    """functions.gather_points: the no-autograd path is one s4g_gather_points_f32 launch, bit-identical to the
+    torch.gather the reference uses (functions.py:10-25); with autograd it stays torch.gather."""
+    from s4g_release_b200.network_models.models.pointnet2_utils import functions as F_
+    g = torch.Generator().manual_seed(B * C + M)
+    pts = torch.randn(B, C, N, generator=g).cuda()
+    idx = torch.randint(0, N, (B, M), generator=g).cuda()
+    want = pts.gather(2, idx.unsqueeze(1).expand(B, C, M))
+    with torch.no_grad():
+        assert torch.equal(F_.gather_points(pts, idx), want)
+    assert torch.equal(ext.gather_points(pts.transpose(1, 2).contiguous().transpose(1, 2), idx), want)  # non-contiguous in
+    p2 = pts.clone().requires_grad_(True)
+    out = F_.gather_points(p2, idx)
+    out.sum().backward()
+    assert torch.equal(out, want) and p2.grad is not None
