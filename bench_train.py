@@ -4,10 +4,12 @@ process per GPU, ONE flat NCCL all-reduce of the 6.63 M fp32 gradients per step 
 
     python bench_train.py [--gpus N] [--steps K] [--warmup W] [--batch 32]      (N > 1: under torchrun like bench.py)
 
-The training step runs the MODULE path: the reference-shaped nn.Module stack on this repo's seven sm_100a operators
-(FPS, ball query, group_points fwd/bwd, 3-NN, interpolate fwd/bwd) with torch autograd; the shared MLPs are torch
-convolutions (fp32 storage; TF32 math by default, like the unmodified reference on this GPU) — the fused tcgen05 chains
-are inference-only.  `value` = scenes/s with inputs and
+`--path fused` (default): s4g_release_b200/train_engine.py — forward, loss and the hand-written backward on the
+B200-native training kernels: tcgen05 GEMMs over channel-last bf16 rows (csrc/gemm_bf16.cu), fused BatchNorm-statistics /
+normalise / ReLU / dropout / max-pool passes and their backward (csrc/train_ops.cu), the sm_100a geometry operators.
+`--path module`: the reference-shaped nn.Module stack on the seven sm_100a operators under torch autograd; the shared
+MLPs are then torch convolutions (fp32 storage; TF32 math by default, like the unmodified reference on this GPU) — the
+round-1 path, kept as the comparison.  `value` = scenes/s with inputs and
 labels resident; `e2e` adds the pinned-host -> device copy of the clouds and labels and the device -> host read of
 the loss every step.  Dropout enabled (timing run), per-replica BatchNorm statistics, weak scaling.
 """
@@ -34,6 +36,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--batch", type=int, default=32, help="scenes per GPU per step")
     ap.add_argument("--num-frame", type=int, default=4000)
+    ap.add_argument("--path", default="fused", choices=["fused", "module"])
     ap.add_argument("--precision", default="tf32", choices=["tf32", "fp32"],
                     help="tf32 = torch's default for cuDNN convolutions, i.e. what the unmodified reference runs on this "
                          "GPU (SURVEY.md §8a6); fp32 = IEEE")
@@ -61,7 +64,7 @@ def main():
     B = args.batch
     torch.manual_seed(0)
     model = PointNet2(**PN2_CLS_CONFIG).to(dev)
-    trainer = Trainer(model, PointNet2Loss())
+    trainer = Trainer(model, PointNet2Loss(), fused=(args.path == "fused"))
     host_x = synthetic_scenes(B, 1000 + rank * B).pin_memory()
     host_y = {k: v.pin_memory() for k, v in synthetic_labels(B, NUM_POINTS, args.num_frame, 2000 + rank * B).items()}
     x = host_x.to(dev)
@@ -116,14 +119,16 @@ def main():
         line = {
             "metric": METRIC, "value": world * B / (ms * 1e-3), "unit": "scenes/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": args.precision, "data": "synthetic",
+            "dtype": "bf16" if args.path == "fused" else args.precision, "data": "synthetic",
             "config": {"workload": "PN2_CLS training step (BASELINE config[3]): forward + PointNet2Loss + backward + Adam, "
                                    "synthetic tabletop clouds, %d points/scene, %d labelled frames" % (NUM_POINTS, args.num_frame),
                        "scenes_per_gpu_per_step": B,
                        "parallelism": "dp%d, one flat all-reduce of 6.63 M fp32 gradients per step" % world,
-                       "path": "module path: sm_100a pn2_ext operators + torch convolutions (%s), torch autograd" %
-                               ("TF32 tensor cores, fp32 storage: torch's default, as the reference would run"
-                                if args.precision == "tf32" else "IEEE fp32"),
+                       "path": ("fused training kernels: tcgen05 bf16 GEMMs + fused BN / ReLU / dropout / max-pool passes, "
+                                "hand-written backward (train_engine.py)") if args.path == "fused" else
+                               ("module path: sm_100a pn2_ext operators + torch convolutions (%s), torch autograd" %
+                                ("TF32 tensor cores, fp32 storage: torch's default, as the reference would run"
+                                 if args.precision == "tf32" else "IEEE fp32")),
                        "l2": "activations (tens of GB per step) exceed L2; no explicit flush"},
             "clocks": clocks.summary(),
             "e2e": {"value": world * B / (e2e_ms * 1e-3), "unit": "scenes/s", "ms_per_step": e2e_ms,

@@ -126,6 +126,52 @@ int s4g_interpolate_backward_f64(const double* grad_out, const int64_t* index, c
 int s4g_linear_tf32(const float* x, long long ldx, const float* w, long long ldw, const float* shift, float* y,
                     long long ldy, long long P, int N, int K, int relu, int round_out, void* stream);
 
+/* ---- training path (channel-last bf16 rows, fp32 accumulation) ------------------------------- */
+/* A shared-MLP block of the reference in TRAINING mode — Conv{1,2}d 1x1 (bias-free) -> BatchNorm with batch statistics ->
+ * ReLU (-> dropout), nn_utils/conv.py:30-36,70-76, nn_utils/mlp.py:99-101 — and its backward, decomposed into one
+ * tcgen05 GEMM over channel-last bf16 rows and fused element-wise kernels.  All row matrices are [P][C] bf16 with
+ * C % 8 == 0 and 16-byte aligned rows.  (Host side: s4g_release_b200/train_engine.py.) */
+
+/* C[P][N] = A[P][K] · B[N][K]^T, bf16 in / bf16 out, fp32 accumulation in TMEM (persistent tcgen05 kernel).
+ * Forward: A = layer input, B = conv weight [cout][cin].  Input gradient: A = dY, B = weight^T [cin][cout]. */
+int s4g_gemm_bf16(const void* a, long long lda, const void* b, long long ldb, void* c, long long ldc, long long P, int N,
+                  int K, void* stream);
+/* sums2c[0..C) = sum_r y[r][c], sums2c[C..2C) = sum_r y[r][c]^2 (fp64; zeroed here) -> the batch mean / variance of
+ * BatchNorm's training mode (torch.nn.BatchNorm{1,2}d over the (B, M, K) positions of a channel). */
+int s4g_train_colstats_bf16(const void* y, long long ld, long long P, int C, double* sums2c, void* stream);
+/* z = dropout(relu(y * scale + shift)): BatchNorm's normalise + affine folded into (scale, shift) by the caller, ReLU
+ * when relu != 0, dropout with probability drop_p from a counter-based hash of (seed, row, channel) (0 = off). */
+int s4g_train_bn_act_bf16(const void* y, const float* scale, const float* shift, void* z, long long P, int C, int relu,
+                          unsigned seed, float drop_p, void* stream);
+/* the same followed by torch.max over each group of K consecutive rows (pointnet2_utils/modules.py:243):
+ * out [G][C] bf16, arg [G][C] uint8 = the row of the (first) maximum inside its group, kept for the backward. */
+int s4g_train_bn_act_maxpool_bf16(const void* y, const float* scale, const float* shift, void* out, uint8_t* arg,
+                                  long long G, int K, int C, int relu, void* stream);
+/* BatchNorm backward, pass 1: sums2c[0..C) = sum_r g, sums2c[C..2C) = sum_r g * xhat, with g = dz * relu'(.) * dropout
+ * mask and xhat = (y - mean) * rstd.  Upstream gradient: dz [P][C] (K = 0), or the pooled gradient [P/K][C] routed to
+ * the arg-max row of each group (K > 0, arg from s4g_train_bn_act_maxpool_bf16). */
+int s4g_train_bn_bwd_reduce_bf16(const void* dz, const uint8_t* arg, int K, const void* y, const float* scale,
+                                 const float* shift, const float* mean, const float* rstd, long long P, int C, int relu,
+                                 unsigned seed, float drop_p, double* sums2c, void* stream);
+/* pass 2: dy = coef * (g - m1 - xhat * m2) with coef = gamma * rstd, m1 = mean(g), m2 = mean(g * xhat), handed in folded
+ * per channel as dy = ka * g + kb * y + kc  (ka = coef, kb = -coef * rstd * m2, kc = coef * (rstd * m2 * mean - m1)). */
+int s4g_train_bn_bwd_apply_bf16(const void* dz, const uint8_t* arg, int K, const void* y, const float* scale,
+                                const float* shift, const float* ka, const float* kb, const float* kc, long long P, int C,
+                                int relu, unsigned seed, float drop_p, void* dy, void* stream);
+/* QueryGrouper.forward (pointnet2_utils/modules.py:37-54) in the row layout: out row (b, m, k) =
+ * [feat[b*N + nbr[b][m][k]][0..Cf) | xyz[b][:, nbr] - ctr[b][:, m] | 0 x 5]  (width Cf + 8; the weight columns are
+ * re-ordered to match by the caller).  feat may be NULL when Cf == 0. */
+int s4g_train_group_rows_bf16(const void* feat, const float* xyz, const float* ctr, const int* nbr, int B, int N, int M, int K,
+                              int Cf, void* out, void* stream);
+/* GroupPointsBackward (grouping_kernel.cu:57-96) in the row layout: dfeat[b*N + nbr][c] += dx[(b,m,k)][c], c < Cf; fp32
+ * vector atomics; dfeat is NOT zeroed here (it may already hold the skip connection's gradient). */
+int s4g_train_group_rows_bwd(const void* dx, long long ld, const int* nbr, int B, int N, int M, int K, int Cf, float* dfeat,
+                             void* stream);
+/* InterpolateBackward (interpolate_kernel.cu:243-286) in the row layout: dsparse[b*Nk + idx_k][c] += w_k * dx[(b,q)][c]. */
+int s4g_train_interp_rows_bwd(const void* dx, long long ld, const int* index, const float* weight, int B, int Nk, int Nq,
+                              int C2, float* dsparse, void* stream);
+int s4g_train_f32_to_bf16(const float* x, void* y, long long n, void* stream);
+
 /* ---- fused inference path (channel-last bf16 features, int32 indices) ---------------------- */
 
 /* PointSearch (interpolate_kernel.cu:33-81) fused with the inverse-squared-distance weights of

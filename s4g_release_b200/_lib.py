@@ -24,6 +24,7 @@ _i = ctypes.c_int
 _f = ctypes.c_float
 _d = ctypes.c_double
 _ip = ctypes.POINTER(ctypes.c_int)
+_ll = ctypes.c_longlong
 
 _SIGNATURES = {
     "s4g_version": ([], _i),
@@ -58,6 +59,16 @@ _SIGNATURES = {
     "s4g_gather_xyz_f32_i32": ([_vp, _vp, _i, _i, _i, _vp, _vp], _i),
     "s4g_linear_tf32": ([_vp, ctypes.c_longlong, _vp, ctypes.c_longlong, _vp, _vp, ctypes.c_longlong, ctypes.c_longlong,
                          _i, _i, _i, _i, _vp], _i),
+    "s4g_gemm_bf16": ([_vp, _ll, _vp, _ll, _vp, _ll, _ll, _i, _i, _vp], _i),
+    "s4g_train_colstats_bf16": ([_vp, _ll, _ll, _i, _vp, _vp], _i),
+    "s4g_train_bn_act_bf16": ([_vp, _vp, _vp, _vp, _ll, _i, _i, ctypes.c_uint, _f, _vp], _i),
+    "s4g_train_bn_act_maxpool_bf16": ([_vp, _vp, _vp, _vp, _vp, _ll, _i, _i, _i, _vp], _i),
+    "s4g_train_bn_bwd_reduce_bf16": ([_vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _ll, _i, _i, ctypes.c_uint, _f, _vp, _vp], _i),
+    "s4g_train_bn_bwd_apply_bf16": ([_vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _ll, _i, _i, ctypes.c_uint, _f, _vp, _vp], _i),
+    "s4g_train_group_rows_bf16": ([_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp], _i),
+    "s4g_train_group_rows_bwd": ([_vp, _ll, _vp, _i, _i, _i, _i, _i, _vp, _vp], _i),
+    "s4g_train_interp_rows_bwd": ([_vp, _ll, _vp, _vp, _i, _i, _i, _i, _vp, _vp], _i),
+    "s4g_train_f32_to_bf16": ([_vp, _vp, _ll, _vp], _i),
     "s4g_chain_create": ([_i, _ip, _ip, _ip, _i, _i, _i, _i, _i, _i], _vp),
     "s4g_chain_create_slots": ([_i, _ip, _ip, _ip, _i, _i, _i, _i, _i, _i, _i], _vp),
     "s4g_chain_create_tuned": ([_i, _ip, _ip, _ip, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i], _vp),

@@ -1,0 +1,256 @@
+// Persistent tcgen05 GEMM for the TRAINING path:   C[P][N] (bf16) = A[P][K] (bf16) · B[N][K]^T (bf16),  fp32 accumulation.
+//
+// The training step cannot use the fused inference chains (csrc/mlp_chain.cu): train-mode BatchNorm needs the statistics
+// of a layer's whole output before the next layer can start, and the backward pass needs every layer's input and
+// pre-activation again.  So a shared-MLP layer (reference nn_utils/conv.py:30-36,70-76 in training mode) is, on this
+// path, one GEMM over channel-last bf16 rows followed by small fused element-wise kernels (csrc/train_ops.cu); this
+// kernel is that GEMM — forward (Y = X W^T) and input gradient (dX = dY W, with W^T handed in as B).
+//
+//   * one persistent CTA per SM walks 128 x 128 output tiles, n-tile fastest (the CTAs that run side by side share the
+//     A rows through L2);
+//   * warp 0: TMA producer — per K-slab of 64 bf16 (= one 128-byte swizzle row) one A box and one B box {64, 128} into a
+//     5-stage ring; rows / channels out of range are zero-filled by the copy engine, so P, N, K need no padding;
+//   * warp 1: tcgen05.mma kind::f16 (M = 128, N = 128, K = 16), 4 per slab, into one of TWO TMEM accumulators;
+//     tcgen05.commit frees the stage / publishes the accumulator;
+//   * warps 2-5: epilogue — drain the other accumulator (tcgen05.ld, bf16 pack, 64 contiguous bytes per thread and
+//     chunk) while the tensor pipe fills the next one.
+#include <cuda.h>
+#include <cuda_bf16.h>
+
+#include "common.cuh"
+
+namespace s4g {
+namespace gemm {
+
+constexpr int kThreads = 192;
+constexpr int kStages = 5;
+constexpr int kTile = 128;
+constexpr int kSlab = 64;                          // K elements per stage: 64 bf16 = 128 B
+constexpr int kOperandBytes = kTile * kSlab * 2;   // 16 KB
+constexpr int kStageBytes = 2 * kOperandBytes;
+constexpr int kSmemBytes = kStages * kStageBytes + 1024;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity) {
+  unsigned ok = 0, spins = 0;
+  while (!ok) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    if (!ok && ++spins > (1u << 26)) __trap();  // a protocol bug traps instead of hanging the GPU
+  }
+}
+__device__ __forceinline__ void tma_load_2d(void* dst, const void* map, int c0, int c1, uint64_t* bar) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+                   smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc),
+      "r"(acc) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
+  uint32_t* r = reinterpret_cast<uint32_t*>(v);
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
+__device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
+  __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+
+__global__ void __launch_bounds__(kThreads, 1)
+gemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                 __nv_bfloat16* __restrict__ c, long long ldc, int P, int N, int K) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t full[kStages], empty[kStages], acc_full[2], acc_empty[2];
+  __shared__ uint32_t tmem_slot;
+  uint8_t* ring = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);  // swizzle atoms are 1024-byte aligned
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int tiles_n = (N + kTile - 1) / kTile;
+  const int n_tiles = ((P + kTile - 1) / kTile) * tiles_n;
+  const int n_slabs = (K + kSlab - 1) / kSlab;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kStages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(&acc_full[a], 1); mbar_init(&acc_empty[a], 4); }  // 4 epilogue warps
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "r"(256u)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem = tmem_slot;
+
+  if (warp == 0) {
+    if (elect_one()) {
+      unsigned g = 0;  // running slab index over all of this CTA's tiles
+      for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+        const int row0 = (t / tiles_n) * kTile, col0 = (t % tiles_n) * kTile;
+        for (int k = 0; k < n_slabs; ++k, ++g) {
+          const unsigned s = g % kStages, use = g / kStages;
+          if (use > 0) mbar_wait(&empty[s], (use - 1) & 1u);
+          mbar_expect_tx(&full[s], kStageBytes);  // zero-filled out-of-range elements count as transferred bytes
+          tma_load_2d(ring + (size_t)s * kStageBytes, &map_a, k * kSlab, row0, &full[s]);
+          tma_load_2d(ring + (size_t)s * kStageBytes + kOperandBytes, &map_b, k * kSlab, col0, &full[s]);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // instruction descriptor, kind::f16: D = f32 (bit 4), A = B = bf16 (1 at bits 7, 10), both K-major, N at 17, M at 24
+    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(kTile >> 3) << 17) | ((uint32_t)(kTile >> 4) << 24);
+    // shared-memory descriptor of a 128-byte-swizzled K-major tile: SBO = 1024 B (8 rows), version 1, layout 2; LBO unused
+    const uint64_t desc_hi = (uint64_t)((1024u >> 4) | (1u << 14) | (2u << 29)) << 32;
+    unsigned g = 0, i = 0;
+    for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++i) {
+      const unsigned a = i & 1u, ause = i >> 1;
+      if (ause > 0) mbar_wait(&acc_empty[a], (ause - 1) & 1u);  // the epilogue has drained this accumulator's previous tile
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const uint32_t d_addr = tmem + a * (uint32_t)kTile;
+      for (int k = 0; k < n_slabs; ++k, ++g) {
+        const unsigned s = g % kStages;
+        mbar_wait(&full[s], (g / kStages) & 1u);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        if (elect_one()) {
+          const uint32_t a16 = smem_u32(ring + (size_t)s * kStageBytes) >> 4;
+          const uint32_t b16 = a16 + (kOperandBytes >> 4);
+#pragma unroll
+          for (int j = 0; j < kSlab / 16; ++j)  // K = 16 per MMA = 32 B inside the 128-byte row: +2 in 16-byte units
+            umma_bf16(d_addr, desc_hi | (uint64_t)((a16 + 2u * j) | (1u << 16)), desc_hi | (uint64_t)((b16 + 2u * j) | (1u << 16)),
+                      idesc, (k > 0 || j > 0) ? 1u : 0u);
+          umma_commit(&empty[s]);
+          if (k == n_slabs - 1) umma_commit(&acc_full[a]);
+        }
+        __syncwarp();
+      }
+    }
+  } else {
+    const int qd = warp & 3;  // the TMEM lane quadrant a warp may read is fixed by warp id % 4
+    unsigned i = 0;
+    for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++i) {
+      const unsigned a = i & 1u;
+      const int row0 = (t / tiles_n) * kTile, col0 = (t % tiles_n) * kTile;
+      const long long row = (long long)row0 + qd * 32 + lane;
+      mbar_wait(&acc_full[a], (i >> 1) & 1u);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      __nv_bfloat16* out = c + row * ldc + col0;
+      const uint32_t t_addr = tmem + ((uint32_t)(qd * 32) << 16) + a * (uint32_t)kTile;
+#pragma unroll 1
+      for (int cc = 0; cc < kTile; cc += 32) {
+        float v[32];
+        tmem_ld32(t_addr + (uint32_t)cc, v);
+        if (row < P) {
+          if (col0 + cc + 32 <= N) {  // whole chunk in range: four 16-byte stores = 64 contiguous bytes
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+              *reinterpret_cast<uint4*>(out + cc + 8 * q) =
+                  make_uint4(pack_bf16(v[8 * q], v[8 * q + 1]), pack_bf16(v[8 * q + 2], v[8 * q + 3]),
+                             pack_bf16(v[8 * q + 4], v[8 * q + 5]), pack_bf16(v[8 * q + 6], v[8 * q + 7]));
+          } else {
+#pragma unroll
+            for (int e = 0; e < 32; ++e)
+              if (col0 + cc + e < N) out[cc + e] = __float2bfloat16(v[e]);
+          }
+        }
+      }
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&acc_empty[a]);
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(256u) : "memory");
+}
+
+static int encode_bf16_map(CUtensorMap* map, const void* base, long long width, long long ld, long long rows) {
+  typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                               const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                               CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+  static EncodeFn encode = nullptr;
+  if (!encode) {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    S4G_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+    S4G_CHECK_ARG(fn != nullptr && qres == cudaDriverEntryPointSuccess, "gemm_bf16: cuTensorMapEncodeTiled is not available");
+    encode = reinterpret_cast<EncodeFn>(fn);
+  }
+  const cuuint64_t dims[2] = {(cuuint64_t)width, (cuuint64_t)rows};
+  const cuuint64_t strides[1] = {(cuuint64_t)ld * 2u};
+  const cuuint32_t box[2] = {(cuuint32_t)kSlab, (cuuint32_t)kTile};
+  const cuuint32_t estr[2] = {1u, 1u};
+  const CUresult r = encode(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  S4G_CHECK_ARG(r == CUDA_SUCCESS, "gemm_bf16: cuTensorMapEncodeTiled failed (%d)", (int)r);
+  return S4G_OK;
+}
+
+}  // namespace gemm
+}  // namespace s4g
+
+extern "C" int s4g_gemm_bf16(const void* a, long long lda, const void* b, long long ldb, void* c, long long ldc, long long P,
+                             int N, int K, void* stream) {
+  using namespace s4g::gemm;
+  S4G_CHECK_ARG(a && b && c, "gemm_bf16: null pointer");
+  S4G_CHECK_ARG(P >= 0 && P < (1ll << 31) - kTile && N > 0 && K > 0, "gemm_bf16: bad shape");
+  S4G_CHECK_ARG(lda >= K && ldb >= K && ldc >= N, "gemm_bf16: leading dimension smaller than the row");
+  S4G_CHECK_ARG(lda % 8 == 0 && ldb % 8 == 0 && ldc % 8 == 0 && ((uintptr_t)a & 15) == 0 && ((uintptr_t)b & 15) == 0 &&
+                    ((uintptr_t)c & 15) == 0,
+                "gemm_bf16: rows must be 16-byte aligned (leading dimensions multiples of 8 bf16)");
+  if (P == 0) return S4G_OK;
+  CUtensorMap ma, mb;
+  int rc = encode_bf16_map(&ma, a, K, lda, P);
+  if (rc != S4G_OK) return rc;
+  rc = encode_bf16_map(&mb, b, K, ldb, N);
+  if (rc != S4G_OK) return rc;
+  static bool attr_set = false;
+  if (!attr_set) {
+    S4G_CUDA(cudaFuncSetAttribute(gemm_bf16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+    attr_set = true;
+  }
+  const long long tiles = ((P + kTile - 1) / kTile) * ((N + kTile - 1) / kTile);
+  const int grid = (int)(tiles < s4g::num_sms() ? tiles : s4g::num_sms());
+  gemm_bf16_kernel<<<grid, kThreads, kSmemBytes, (cudaStream_t)stream>>>(ma, mb, reinterpret_cast<__nv_bfloat16*>(c), ldc,
+                                                                         (int)P, N, K);
+  S4G_LAUNCH_CHECK("gemm_bf16");
+  return S4G_OK;
+}

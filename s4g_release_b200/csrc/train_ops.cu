@@ -1,0 +1,491 @@
+// Element-wise / reduction kernels of the TRAINING path (channel-last bf16 rows [P][C], C % 8 == 0), around the tcgen05
+// GEMM of csrc/gemm_bf16.cu.  Together they are one shared-MLP block of the reference in training mode
+// (nn_utils/conv.py:30-36,70-76: 1x1 conv -> BatchNorm with batch statistics -> ReLU, nn_utils/mlp.py:99-101 dropout) and
+// its backward, plus the set-abstraction max-pool (pointnet2_utils/modules.py:243), the grouping gather / scatter
+// (grouping_kernel.cu:32-54,57-96) and the interpolation scatter (interpolate_kernel.cu:243-286) in the same layout:
+//
+//   colstats            sum_r y, sum_r y^2 per channel (fp64 accumulation across blocks)        -> batch mean / variance
+//   bn_act              z = drop(relu(y * scale + shift))                                       -> next layer's input
+//   bn_act_maxpool      the same followed by the max over each group of K consecutive rows, arg-max kept (uint8)
+//   bn_bwd_reduce       sum_r g, sum_r g * xhat with g = dz * relu' * drop   (dz dense, or routed through the arg-max)
+//   bn_bwd_apply        dy = gamma * rstd * (g - mean(g) - xhat * mean(g * xhat))               -> bf16
+//   group_rows          X0[(b,m,k)] = [feat[b, nbr] | xyz[b, nbr] - ctr[b, m] | 0]              (gather, forward)
+//   group_rows_bwd      dfeat[b, nbr] += dX0[(b,m,k)]                                           (fp32 vector atomics)
+//   interp_rows_bwd     dsparse[b, idx_k] += w_k * dx[(b,q)]                                    (fp32 vector atomics)
+//
+// Every thread owns one 16-byte piece (8 channels) of a row, so all global accesses are 16-byte vectors and adjacent
+// threads touch adjacent pieces.  Dropout is a counter-based hash of (seed, row, channel): the backward recomputes the
+// mask instead of storing it.
+#include <cuda_bf16.h>
+
+#include "common.cuh"
+
+namespace s4g {
+namespace trn {
+
+struct F8 { float v[8]; };
+
+__device__ __forceinline__ F8 unpack8(const uint4 q) {
+  F8 r;
+  const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    r.v[2 * i] = __uint_as_float(w[i] << 16);
+    r.v[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
+  }
+  return r;
+}
+__device__ __forceinline__ uint4 pack8(const F8& f) {
+  uint32_t w[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    __nv_bfloat162 h = __floats2bfloat162_rn(f.v[2 * i], f.v[2 * i + 1]);
+    w[i] = *reinterpret_cast<uint32_t*>(&h);
+  }
+  return make_uint4(w[0], w[1], w[2], w[3]);
+}
+__device__ __forceinline__ F8 load_f8(const float* p) {
+  const float4 a = __ldg(reinterpret_cast<const float4*>(p)), b = __ldg(reinterpret_cast<const float4*>(p) + 1);
+  return F8{{a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w}};
+}
+// keep-mask bit of element (row, channel): a 32-bit mix of the linear index and the seed (murmur3 finaliser)
+__device__ __forceinline__ bool keep_elem(unsigned seed, long long row, int ch, int C, unsigned thresh) {
+  unsigned long long idx = (unsigned long long)row * (unsigned)C + (unsigned)ch;
+  unsigned h = (unsigned)idx ^ (unsigned)(idx >> 32) * 0x9E3779B9u ^ seed;
+  h ^= h >> 16; h *= 0x85EBCA6Bu; h ^= h >> 13; h *= 0xC2B2AE35u; h ^= h >> 16;
+  return h >= thresh;  // P(keep) = 1 - thresh / 2^32
+}
+
+// ---------------------------------------------------------------------------------------------- colstats
+constexpr int kStatThreads = 256;
+constexpr int kStatRows = 512;  // rows per block
+
+__global__ void __launch_bounds__(kStatThreads)
+colstats_kernel(const __nv_bfloat16* __restrict__ y, long long ld, long long P, int C, double* __restrict__ out) {
+  extern __shared__ float s_part[];  // [row lanes][C][2]
+  const int pieces = C >> 3;
+  const int lanes = kStatThreads / pieces;  // row lanes per block (pieces <= 256)
+  const int piece = threadIdx.x % pieces, rl = threadIdx.x / pieces;
+  const long long r0 = (long long)blockIdx.x * kStatRows;
+  const long long r1 = min(P, r0 + kStatRows);
+  F8 s{}, q{};
+  if (rl < lanes) {
+    for (long long r = r0 + rl; r < r1; r += lanes) {
+      const F8 v = unpack8(__ldg(reinterpret_cast<const uint4*>(y + r * ld) + piece));
+#pragma unroll
+      for (int e = 0; e < 8; ++e) { s.v[e] += v.v[e]; q.v[e] = fmaf(v.v[e], v.v[e], q.v[e]); }
+    }
+    float* dst = s_part + ((size_t)rl * pieces + piece) * 16;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) { dst[e] = s.v[e]; dst[8 + e] = q.v[e]; }
+  }
+  __syncthreads();
+  // thread t < 2 * C: column t of the [lanes][pieces * 16] table
+  for (int t = threadIdx.x; t < pieces * 16; t += kStatThreads) {
+    double acc = 0.0;
+    for (int l = 0; l < lanes; ++l) acc += (double)s_part[(size_t)l * pieces * 16 + t];
+    const int pc = t >> 4, e = t & 15;
+    atomicAdd(out + (e < 8 ? 0 : C) + pc * 8 + (e & 7), acc);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------- bn_act (+ maxpool)
+// thread = (16-byte piece, row lane): the per-channel parameters are loaded once and reused for every row of the block's
+// chunk; four rows are in flight per thread
+constexpr int kEltRows = 256;  // rows per block of the element-wise kernels
+
+__global__ void __launch_bounds__(256)
+bn_act_kernel(const __nv_bfloat16* __restrict__ y, const float* __restrict__ scale, const float* __restrict__ shift,
+              __nv_bfloat16* __restrict__ z, long long P, int C, int relu, unsigned seed, unsigned thresh, float keep_scale) {
+  const int pieces = C >> 3;
+  const int lanes = 256 / pieces;
+  const int piece = threadIdx.x % pieces, rl = threadIdx.x / pieces;
+  if (rl >= lanes) return;
+  const long long r1 = min(P, ((long long)blockIdx.x + 1) * kEltRows);
+  const F8 a = load_f8(scale + piece * 8), b = load_f8(shift + piece * 8);
+  for (long long r = (long long)blockIdx.x * kEltRows + rl; r < r1; r += 4LL * lanes) {
+    uint4 raw[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const long long rr = r + (long long)u * lanes;
+      if (rr < r1) raw[u] = __ldg(reinterpret_cast<const uint4*>(y + rr * C) + piece);
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const long long rr = r + (long long)u * lanes;
+      if (rr >= r1) break;
+      const F8 v = unpack8(raw[u]);
+      F8 o;
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        float t = fmaf(v.v[e], a.v[e], b.v[e]);
+        if (relu) t = fmaxf(t, 0.f);
+        if (thresh) t = keep_elem(seed, rr, piece * 8 + e, C, thresh) ? t * keep_scale : 0.f;
+        o.v[e] = t;
+      }
+      reinterpret_cast<uint4*>(z + rr * C)[piece] = pack8(o);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256)
+bn_act_maxpool_kernel(const __nv_bfloat16* __restrict__ y, const float* __restrict__ scale, const float* __restrict__ shift,
+                      __nv_bfloat16* __restrict__ out, uint8_t* __restrict__ arg, long long G, int K, int C, int relu) {
+  const int pieces = C >> 3;
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= G * pieces) return;
+  const long long g = i / pieces;
+  const int piece = (int)(i - g * pieces);
+  const F8 a = load_f8(scale + piece * 8), b = load_f8(shift + piece * 8);
+  F8 best;
+  int bi[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) { best.v[e] = -3.4e38f; bi[e] = 0; }
+  const uint4* src = reinterpret_cast<const uint4*>(y + g * K * C) + piece;
+  for (int k = 0; k < K; ++k) {
+    const F8 v = unpack8(__ldg(src + (size_t)k * pieces));
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      float t = fmaf(v.v[e], a.v[e], b.v[e]);
+      if (relu) t = fmaxf(t, 0.f);
+      if (t > best.v[e]) { best.v[e] = t; bi[e] = k; }  // first maximum wins, like torch.max
+    }
+  }
+  reinterpret_cast<uint4*>(out + g * C)[piece] = pack8(best);
+  uint2 packed;
+  packed.x = (unsigned)bi[0] | ((unsigned)bi[1] << 8) | ((unsigned)bi[2] << 16) | ((unsigned)bi[3] << 24);
+  packed.y = (unsigned)bi[4] | ((unsigned)bi[5] << 8) | ((unsigned)bi[6] << 16) | ((unsigned)bi[7] << 24);
+  reinterpret_cast<uint2*>(arg + g * C)[piece] = packed;
+}
+
+// ---------------------------------------------------------------------------------------------- BN backward
+// g of one piece: dense upstream gradient, or the pooled gradient routed to the arg-max row (K > 0)
+struct Upstream {
+  const __nv_bfloat16* dz;   // dense: [P][C];   pooled: [G][C]
+  const uint8_t* arg;        // pooled only: [G][C]
+  int K;                     // 0 = dense
+};
+struct UpRaw { uint4 d; uint2 a; int k; };
+// load now (raw, 16 B + 8 B), route later: keeps the loads of several rows in flight without holding converted values
+__device__ __forceinline__ UpRaw upstream_load(const Upstream& u, long long row, int piece, int C) {
+  UpRaw r;
+  if (u.K == 0) {
+    r.d = __ldg(reinterpret_cast<const uint4*>(u.dz + row * C) + piece);
+    r.a = make_uint2(0u, 0u);
+    r.k = -1;
+  } else {
+    const long long g = row / u.K;
+    r.k = (int)(row - g * u.K);
+    r.d = __ldg(reinterpret_cast<const uint4*>(u.dz + g * C) + piece);
+    r.a = __ldg(reinterpret_cast<const uint2*>(u.arg + g * C) + piece);
+  }
+  return r;
+}
+__device__ __forceinline__ F8 upstream_route(const UpRaw& r) {
+  F8 d = unpack8(r.d);
+  if (r.k >= 0) {
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const unsigned idx = ((e < 4 ? r.a.x : r.a.y) >> (8 * (e & 3))) & 0xffu;
+      if ((int)idx != r.k) d.v[e] = 0.f;
+    }
+  }
+  return d;
+}
+
+__global__ void __launch_bounds__(kStatThreads, 2)
+bn_bwd_reduce_kernel(Upstream up, const __nv_bfloat16* __restrict__ y, const float* __restrict__ scale,
+                     const float* __restrict__ shift, const float* __restrict__ mean, const float* __restrict__ rstd,
+                     long long P, int C, int relu, unsigned seed, unsigned thresh, float keep_scale, double* __restrict__ out) {
+  extern __shared__ float s_part[];
+  const int pieces = C >> 3;
+  const int lanes = kStatThreads / pieces;
+  const int piece = threadIdx.x % pieces, rl = threadIdx.x / pieces;
+  const long long r0 = (long long)blockIdx.x * kStatRows;
+  const long long r1 = min(P, r0 + kStatRows);
+  F8 s{}, q{};
+  if (rl < lanes) {
+    const F8 a = load_f8(scale + piece * 8), b = load_f8(shift + piece * 8), mu = load_f8(mean + piece * 8),
+             rs = load_f8(rstd + piece * 8);
+    for (long long r = r0 + rl; r < r1; r += 4LL * lanes) {
+      uint4 raw[4];
+      UpRaw ur[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const long long rr = r + (long long)u * lanes;
+        if (rr < r1) {
+          raw[u] = __ldg(reinterpret_cast<const uint4*>(y + rr * C) + piece);
+          ur[u] = upstream_load(up, rr, piece, C);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const long long rr = r + (long long)u * lanes;
+        if (rr >= r1) break;
+        const F8 v = unpack8(raw[u]);
+        const F8 d = upstream_route(ur[u]);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          float g = d.v[e];
+          if (relu && !(fmaf(v.v[e], a.v[e], b.v[e]) > 0.f)) g = 0.f;
+          if (thresh) g = keep_elem(seed, rr, piece * 8 + e, C, thresh) ? g * keep_scale : 0.f;
+          s.v[e] += g;
+          q.v[e] = fmaf(g, (v.v[e] - mu.v[e]) * rs.v[e], q.v[e]);
+        }
+      }
+    }
+    float* dst = s_part + ((size_t)rl * pieces + piece) * 16;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) { dst[e] = s.v[e]; dst[8 + e] = q.v[e]; }
+  }
+  __syncthreads();
+  for (int t = threadIdx.x; t < pieces * 16; t += kStatThreads) {
+    double acc = 0.0;
+    for (int l = 0; l < lanes; ++l) acc += (double)s_part[(size_t)l * pieces * 16 + t];
+    const int pc = t >> 4, e = t & 15;
+    atomicAdd(out + (e < 8 ? 0 : C) + pc * 8 + (e & 7), acc);
+  }
+}
+
+// dy = coef * (g - m1 - xhat * m2) = ka * g + kb * y + kc per channel, with ka = coef, kb = -coef * rstd * m2,
+// kc = coef * (rstd * m2 * mean - m1) folded by the host wrapper (coef = gamma * rstd, m1 = mean(g), m2 = mean(g * xhat))
+__global__ void __launch_bounds__(256, 2)
+bn_bwd_apply_kernel(Upstream up, const __nv_bfloat16* __restrict__ y, const float* __restrict__ scale,
+                    const float* __restrict__ shift, const float* __restrict__ ka, const float* __restrict__ kb,
+                    const float* __restrict__ kc, long long P, int C, int relu, unsigned seed, unsigned thresh,
+                    float keep_scale, __nv_bfloat16* __restrict__ dy) {
+  const int pieces = C >> 3;
+  const int lanes = 256 / pieces;
+  const int piece = threadIdx.x % pieces, rl = threadIdx.x / pieces;
+  if (rl >= lanes) return;
+  const long long r1 = min(P, ((long long)blockIdx.x + 1) * kEltRows);
+  const F8 a = load_f8(scale + piece * 8), b = load_f8(shift + piece * 8), A = load_f8(ka + piece * 8),
+           Bc = load_f8(kb + piece * 8), Cc = load_f8(kc + piece * 8);
+  for (long long r = (long long)blockIdx.x * kEltRows + rl; r < r1; r += 4LL * lanes) {
+    uint4 raw[4];
+    UpRaw ur[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const long long rr = r + (long long)u * lanes;
+      if (rr < r1) {
+        raw[u] = __ldg(reinterpret_cast<const uint4*>(y + rr * C) + piece);
+        ur[u] = upstream_load(up, rr, piece, C);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const long long rr = r + (long long)u * lanes;
+      if (rr >= r1) break;
+      const F8 v = unpack8(raw[u]);
+      const F8 d = upstream_route(ur[u]);
+      F8 o;
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        float g = d.v[e];
+        if (relu && !(fmaf(v.v[e], a.v[e], b.v[e]) > 0.f)) g = 0.f;
+        if (thresh) g = keep_elem(seed, rr, piece * 8 + e, C, thresh) ? g * keep_scale : 0.f;
+        o.v[e] = fmaf(A.v[e], g, fmaf(Bc.v[e], v.v[e], Cc.v[e]));
+      }
+      reinterpret_cast<uint4*>(dy + rr * C)[piece] = pack8(o);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------- grouping rows
+// X0 row (b, m, k) = [feat[b*N + j][0..Cf) | dx dy dz 0 0 0 0 0],  j = nbr[b][m][k];  width = Cf + 8
+__global__ void __launch_bounds__(256)
+group_rows_kernel(const __nv_bfloat16* __restrict__ feat, const float* __restrict__ xyz, const float* __restrict__ ctr,
+                  const int* __restrict__ nbr, int N, int M, int K, int Cf, long long rows, __nv_bfloat16* __restrict__ out) {
+  const int pieces = (Cf >> 3) + 1;
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= rows * pieces) return;
+  const long long row = i / pieces;
+  const int piece = (int)(i - row * pieces);
+  const long long per_b = (long long)M * K;
+  const int b = (int)(row / per_b);
+  const int m = (int)((row - (long long)b * per_b) / K);
+  const int j = __ldg(nbr + row);
+  uint4 v;
+  if (piece < (Cf >> 3)) {
+    v = __ldg(reinterpret_cast<const uint4*>(feat + ((long long)b * N + j) * Cf) + piece);
+  } else {
+    const float* X = xyz + (long long)b * 3 * N;
+    const float* Cn = ctr + (long long)b * 3 * M;
+    F8 r{};
+    r.v[0] = __fsub_rn(__ldg(X + j), __ldg(Cn + m));
+    r.v[1] = __fsub_rn(__ldg(X + N + j), __ldg(Cn + M + m));
+    r.v[2] = __fsub_rn(__ldg(X + 2 * N + j), __ldg(Cn + 2 * M + m));
+    v = pack8(r);
+  }
+  reinterpret_cast<uint4*>(out + row * (long long)(Cf + 8))[piece] = v;
+}
+
+__device__ __forceinline__ void atomic_add_f8(float* dst, const F8& v) {
+  atomicAdd(reinterpret_cast<float4*>(dst), make_float4(v.v[0], v.v[1], v.v[2], v.v[3]));
+  atomicAdd(reinterpret_cast<float4*>(dst) + 1, make_float4(v.v[4], v.v[5], v.v[6], v.v[7]));
+}
+
+// dfeat[b*N + nbr[row]][c] += dx[row][c]   for c < Cf;  dx rows are ld wide
+__global__ void __launch_bounds__(256)
+group_rows_bwd_kernel(const __nv_bfloat16* __restrict__ dx, long long ld, const int* __restrict__ nbr, int N, long long per_b,
+                      int Cf, long long rows, float* __restrict__ dfeat) {
+  const int pieces = Cf >> 3;
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= rows * pieces) return;
+  const long long row = i / pieces;
+  const int piece = (int)(i - row * pieces);
+  const int b = (int)(row / per_b);
+  const int j = __ldg(nbr + row);
+  const F8 v = unpack8(__ldg(reinterpret_cast<const uint4*>(dx + row * ld) + piece));
+  atomic_add_f8(dfeat + ((long long)b * N + j) * Cf + piece * 8, v);
+}
+
+// dsparse[b*Nk + idx[row][k]][c] += w[row][k] * dx[row][c]   for c < C2
+__global__ void __launch_bounds__(256)
+interp_rows_bwd_kernel(const __nv_bfloat16* __restrict__ dx, long long ld, const int* __restrict__ index,
+                       const float* __restrict__ weight, int Nk, int Nq, int C2, long long rows, float* __restrict__ dsparse) {
+  const int pieces = C2 >> 3;
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= rows * pieces) return;
+  const long long row = i / pieces;
+  const int piece = (int)(i - row * pieces);
+  const long long b = row / Nq;
+  const F8 v = unpack8(__ldg(reinterpret_cast<const uint4*>(dx + row * ld) + piece));
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    const int j = __ldg(index + row * 3 + k);
+    const float w = __ldg(weight + row * 3 + k);
+    F8 t;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) t.v[e] = v.v[e] * w;
+    atomic_add_f8(dsparse + (b * Nk + j) * C2 + piece * 8, t);
+  }
+}
+
+// fp32 [rows][C] -> bf16 (gradient buffers accumulated with atomics -> the next kernel's bf16 operand)
+__global__ void __launch_bounds__(256)
+f32_to_bf16_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ y, long long n8) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n8) return;
+  reinterpret_cast<uint4*>(y)[i] = pack8(load_f8(x + i * 8));
+}
+
+static unsigned grid_for(long long work, int threads) { return (unsigned)((work + threads - 1) / threads); }
+
+}  // namespace trn
+}  // namespace s4g
+
+using namespace s4g::trn;
+typedef __nv_bfloat16 bf16;
+
+#define TRN_CHECK_C(C) S4G_CHECK_ARG((C) > 0 && (C) % 8 == 0 && (C) <= 2048, "train_ops: channels must be a multiple of 8, <= 2048")
+
+extern "C" int s4g_train_colstats_bf16(const void* y, long long ld, long long P, int C, double* sums2c, void* stream) {
+  S4G_CHECK_ARG(y && sums2c && P > 0 && ld >= C && ld % 8 == 0, "train_colstats: bad arguments");
+  TRN_CHECK_C(C);
+  cudaStream_t s = (cudaStream_t)stream;
+  S4G_CUDA(cudaMemsetAsync(sums2c, 0, sizeof(double) * 2 * C, s));
+  const int pieces = C >> 3, lanes = kStatThreads / pieces;
+  S4G_CHECK_ARG(lanes >= 1, "train_colstats: too many channels");
+  const size_t smem = (size_t)lanes * pieces * 16 * sizeof(float);
+  colstats_kernel<<<grid_for(P, kStatRows), kStatThreads, smem, s>>>(reinterpret_cast<const bf16*>(y), ld, P, C, sums2c);
+  S4G_LAUNCH_CHECK("train_colstats");
+  return S4G_OK;
+}
+
+extern "C" int s4g_train_bn_act_bf16(const void* y, const float* scale, const float* shift, void* z, long long P, int C,
+                                     int relu, unsigned seed, float drop_p, void* stream) {
+  S4G_CHECK_ARG(y && scale && shift && z && P > 0 && drop_p >= 0.f && drop_p < 1.f, "train_bn_act: bad arguments");
+  TRN_CHECK_C(C);
+  const unsigned thresh = drop_p > 0.f ? (unsigned)((double)drop_p * 4294967296.0) : 0u;
+  bn_act_kernel<<<grid_for(P, kEltRows), 256, 0, (cudaStream_t)stream>>>(
+      reinterpret_cast<const bf16*>(y), scale, shift, reinterpret_cast<bf16*>(z), P, C, relu, seed, thresh, 1.f / (1.f - drop_p));
+  S4G_LAUNCH_CHECK("train_bn_act");
+  return S4G_OK;
+}
+
+extern "C" int s4g_train_bn_act_maxpool_bf16(const void* y, const float* scale, const float* shift, void* out, uint8_t* arg,
+                                             long long G, int K, int C, int relu, void* stream) {
+  S4G_CHECK_ARG(y && scale && shift && out && arg && G > 0 && K > 0 && K <= 255, "train_bn_act_maxpool: bad arguments");
+  TRN_CHECK_C(C);
+  bn_act_maxpool_kernel<<<grid_for(G * (C >> 3), 256), 256, 0, (cudaStream_t)stream>>>(
+      reinterpret_cast<const bf16*>(y), scale, shift, reinterpret_cast<bf16*>(out), arg, G, K, C, relu);
+  S4G_LAUNCH_CHECK("train_bn_act_maxpool");
+  return S4G_OK;
+}
+
+// upstream gradient: dz [P][C] when K == 0; pooled dz [P/K][C] + arg-max [P/K][C] when K > 0
+extern "C" int s4g_train_bn_bwd_reduce_bf16(const void* dz, const uint8_t* arg, int K, const void* y, const float* scale,
+                                            const float* shift, const float* mean, const float* rstd, long long P, int C,
+                                            int relu, unsigned seed, float drop_p, double* sums2c, void* stream) {
+  S4G_CHECK_ARG(dz && y && scale && shift && mean && rstd && sums2c && P > 0 && (K == 0 || (arg && P % K == 0)),
+                "train_bn_bwd_reduce: bad arguments");
+  TRN_CHECK_C(C);
+  cudaStream_t s = (cudaStream_t)stream;
+  S4G_CUDA(cudaMemsetAsync(sums2c, 0, sizeof(double) * 2 * C, s));
+  const int pieces = C >> 3, lanes = kStatThreads / pieces;
+  S4G_CHECK_ARG(lanes >= 1, "train_bn_bwd_reduce: too many channels");
+  const unsigned thresh = drop_p > 0.f ? (unsigned)((double)drop_p * 4294967296.0) : 0u;
+  const Upstream up{reinterpret_cast<const bf16*>(dz), arg, K};
+  bn_bwd_reduce_kernel<<<grid_for(P, kStatRows), kStatThreads, (size_t)lanes * pieces * 16 * sizeof(float), s>>>(
+      up, reinterpret_cast<const bf16*>(y), scale, shift, mean, rstd, P, C, relu, seed, thresh, 1.f / (1.f - drop_p), sums2c);
+  S4G_LAUNCH_CHECK("train_bn_bwd_reduce");
+  return S4G_OK;
+}
+
+extern "C" int s4g_train_bn_bwd_apply_bf16(const void* dz, const uint8_t* arg, int K, const void* y, const float* scale,
+                                           const float* shift, const float* ka, const float* kb, const float* kc,
+                                           long long P, int C, int relu, unsigned seed, float drop_p, void* dy, void* stream) {
+  S4G_CHECK_ARG(dz && y && scale && shift && ka && kb && kc && dy && P > 0 && (K == 0 || (arg && P % K == 0)),
+                "train_bn_bwd_apply: bad arguments");
+  TRN_CHECK_C(C);
+  const unsigned thresh = drop_p > 0.f ? (unsigned)((double)drop_p * 4294967296.0) : 0u;
+  const Upstream up{reinterpret_cast<const bf16*>(dz), arg, K};
+  bn_bwd_apply_kernel<<<grid_for(P, kEltRows), 256, 0, (cudaStream_t)stream>>>(
+      up, reinterpret_cast<const bf16*>(y), scale, shift, ka, kb, kc, P, C, relu, seed, thresh, 1.f / (1.f - drop_p),
+      reinterpret_cast<bf16*>(dy));
+  S4G_LAUNCH_CHECK("train_bn_bwd_apply");
+  return S4G_OK;
+}
+
+extern "C" int s4g_train_group_rows_bf16(const void* feat, const float* xyz, const float* ctr, const int* nbr, int B, int N,
+                                         int M, int K, int Cf, void* out, void* stream) {
+  S4G_CHECK_ARG(xyz && ctr && nbr && out && B > 0 && N > 0 && M > 0 && K > 0 && Cf >= 0 && Cf % 8 == 0 && (Cf == 0 || feat),
+                "train_group_rows: bad arguments");
+  const long long rows = (long long)B * M * K;
+  group_rows_kernel<<<grid_for(rows * ((Cf >> 3) + 1), 256), 256, 0, (cudaStream_t)stream>>>(
+      reinterpret_cast<const bf16*>(feat), xyz, ctr, nbr, N, M, K, Cf, rows, reinterpret_cast<bf16*>(out));
+  S4G_LAUNCH_CHECK("train_group_rows");
+  return S4G_OK;
+}
+
+// dfeat (fp32 [B*N][Cf]) must be zeroed (or hold the gradient to add to) by the caller
+extern "C" int s4g_train_group_rows_bwd(const void* dx, long long ld, const int* nbr, int B, int N, int M, int K, int Cf,
+                                        float* dfeat, void* stream) {
+  S4G_CHECK_ARG(dx && nbr && dfeat && B > 0 && N > 0 && M > 0 && K > 0 && Cf > 0 && Cf % 8 == 0 && ld >= Cf && ld % 8 == 0,
+                "train_group_rows_bwd: bad arguments");
+  const long long rows = (long long)B * M * K;
+  group_rows_bwd_kernel<<<grid_for(rows * (Cf >> 3), 256), 256, 0, (cudaStream_t)stream>>>(
+      reinterpret_cast<const bf16*>(dx), ld, nbr, N, (long long)M * K, Cf, rows, dfeat);
+  S4G_LAUNCH_CHECK("train_group_rows_bwd");
+  return S4G_OK;
+}
+
+extern "C" int s4g_train_interp_rows_bwd(const void* dx, long long ld, const int* index, const float* weight, int B, int Nk,
+                                         int Nq, int C2, float* dsparse, void* stream) {
+  S4G_CHECK_ARG(dx && index && weight && dsparse && B > 0 && Nk > 0 && Nq > 0 && C2 > 0 && C2 % 8 == 0 && ld >= C2 && ld % 8 == 0,
+                "train_interp_rows_bwd: bad arguments");
+  const long long rows = (long long)B * Nq;
+  interp_rows_bwd_kernel<<<grid_for(rows * (C2 >> 3), 256), 256, 0, (cudaStream_t)stream>>>(
+      reinterpret_cast<const bf16*>(dx), ld, index, weight, Nk, Nq, C2, rows, dsparse);
+  S4G_LAUNCH_CHECK("train_interp_rows_bwd");
+  return S4G_OK;
+}
+
+extern "C" int s4g_train_f32_to_bf16(const float* x, void* y, long long n, void* stream) {
+  S4G_CHECK_ARG(x && y && n >= 0 && n % 8 == 0, "train_f32_to_bf16: element count must be a multiple of 8");
+  if (n == 0) return S4G_OK;
+  f32_to_bf16_kernel<<<grid_for(n / 8, 256), 256, 0, (cudaStream_t)stream>>>(x, reinterpret_cast<bf16*>(y), n / 8);
+  S4G_LAUNCH_CHECK("train_f32_to_bf16");
+  return S4G_OK;
+}

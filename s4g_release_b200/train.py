@@ -66,8 +66,14 @@ def synthetic_labels(batch, num_points, num_frame=4000, first_seed=2000, device=
 
 class Trainer:
     def __init__(self, model, loss_fn, lr=1e-3, betas=(0.9, 0.999), weight_decay=0.0, step_size=20, gamma=0.5,
-                 group=None):
+                 group=None, fused=False):
+        """``fused``: forward + loss + backward on the B200-native training kernels (train_engine.TrainEngine: tcgen05
+        GEMMs over bf16 rows, fused BatchNorm / ReLU / max-pool passes) instead of the module path under torch autograd."""
         self.model, self.loss_fn, self.group = model, loss_fn, group
+        self.engine = None
+        if fused:
+            from .train_engine import TrainEngine
+            self.engine = TrainEngine(model, loss_fn)
         broadcast_parameters(model, 0, group)
         self.bucket = GradBucket(model.parameters())
         self.optimizer = torch.optim.Adam(self.bucket.params, lr=lr, betas=betas, weight_decay=weight_decay)
@@ -77,10 +83,13 @@ class Trainer:
         """One optimisation step on this rank's shard; returns the loss dict (detached)."""
         self.model.train()
         self.bucket.zero()
-        preds = self.model(data_batch)
-        losses = self.loss_fn(preds, labels)
-        total = sum(losses.values())
-        total.backward()
+        if self.engine is not None:
+            losses = self.engine.step_loss(data_batch, labels)
+        else:
+            preds = self.model(data_batch)
+            losses = self.loss_fn(preds, labels)
+            total = sum(losses.values())
+            total.backward()
         self.bucket.all_reduce_mean(self.group)
         self.optimizer.step()
         return {k: v.detach() for k, v in losses.items()}

@@ -1,0 +1,297 @@
+"""Fused TRAINING step of PN2_CLS on the B200-native kernels (BASELINE config 4).
+
+The module path (pointnet2_utils.modules + torch autograd) materialises every grouped tensor in fp32 channel-first
+layout and runs conv / BatchNorm / ReLU / max as separate library kernels: 339 ms and 115 GB for 32 scenes (round 1).
+This engine runs the SAME computation — reference PointNet2.forward in training mode (models/PointNet2_tcls.py:99-148),
+PointNet2Loss (:162-219) and the backward of all of it — on channel-last bf16 rows:
+
+  geometry        the sm_100a operators of the inference engine (FPS, ball query, 3-NN + weights), exact fp32, no grad
+                  (reference functions.py:46-47,76-77,131-132 return None for them too);
+  grouping        s4g_train_group_rows_bf16: one gathered row [features | relative xyz] per (centroid, neighbour);
+  shared MLP      per block ONE tcgen05 GEMM (csrc/gemm_bf16.cu, fp32 accumulation) + batch statistics (fp64 sums)
+                  + one fused normalise / ReLU / dropout pass — for the last block of a set-abstraction level fused with
+                  the max over the K neighbours (arg-max kept as uint8);
+  heads           the four 4-block MLPs as above; the final biased 1x1 convs (128 -> 3 / 9 / 4 / 5, + sigmoid) and the
+                  loss are tiny and stay in torch: autograd hands back d(loss)/d(head features);
+  backward        written out by hand — BatchNorm backward in two fused passes (reduce, apply) that also undo ReLU /
+                  dropout / max-pool routing on the fly, dX = dY · W on the tcgen05 GEMM, dW = dY^T · X as a plain
+                  library GEMM (torch.mm, bf16 operands, fp32 result: the one cuBLAS call per block), scatter-adds of the
+                  grouping and interpolation gradients with fp32 vector atomics.
+
+Parameters stay the fp32 master copies of the nn.Module (state_dict / checkpoints unchanged); gradients are written to
+``param.grad`` in fp32; BatchNorm running statistics are updated like torch does (momentum, unbiased variance).
+Activations are bf16, so this is the numerical regime of bf16 autocast training, not of the fp32 module path: the test
+(tests/test_train_engine_gpu.py) states the tolerance.  There is no CPU path.
+"""
+import torch
+import torch.nn.functional as F
+
+from ._lib import check, lib, ptr, stream_ptr
+from .engine import FusedPointNet2
+
+BF16 = torch.bfloat16
+
+
+# ------------------------------------------------------------------------------------------------ kernel wrappers
+def gemm(a, b):
+    """a [P, K] bf16 (row stride % 8 == 0), b [N, K] bf16 -> [P, N] bf16 (N padded to 8 internally when needed)."""
+    assert a.dtype == BF16 and b.dtype == BF16 and a.stride(1) == 1 and b.stride(1) == 1 and a.shape[1] == b.shape[1]
+    P, K = a.shape
+    N = b.shape[0]
+    ldc = (N + 7) // 8 * 8
+    c = torch.empty((P, ldc), dtype=BF16, device=a.device)
+    check(lib.s4g_gemm_bf16(ptr(a), a.stride(0), ptr(b), b.stride(0), ptr(c), ldc, P, N, K, stream_ptr(a.device)), "gemm_bf16")
+    return c if ldc == N else c[:, :N]
+
+
+def colstats(y):
+    P, C = y.shape
+    out = torch.empty(2 * C, dtype=torch.float64, device=y.device)
+    check(lib.s4g_train_colstats_bf16(ptr(y), y.stride(0), P, C, ptr(out), stream_ptr(y.device)), "train_colstats")
+    return out[:C], out[C:]
+
+
+class Block:
+    """One conv (bias-free 1x1) + BatchNorm + ReLU block of a SharedMLP in training mode, on rows.
+    ``in_perm``: for the first block of a set-abstraction level, the number of gathered feature channels Cf — the input
+    rows are [features(Cf) | xyz(3) | 0 x 5] while the reference's weight columns are [xyz(3) | features(Cf)]."""
+
+    def __init__(self, module, grouped_cf=None, drop_p=0.0):
+        self.conv, self.bn = module.conv, module.bn
+        self.cf = grouped_cf
+        self.drop_p = float(drop_p)
+        self.cout = self.conv.weight.shape[0]
+        self.cin = self.conv.weight.shape[1]
+        self.saved = None
+
+    def _weight_rows(self):
+        w = self.conv.weight.detach().reshape(self.cout, self.cin)
+        if self.cf is None:
+            kp = (self.cin + 7) // 8 * 8
+            if kp == self.cin:
+                return w.to(BF16)
+            wb = torch.zeros((self.cout, kp), dtype=BF16, device=w.device)
+            wb[:, :self.cin] = w
+            return wb
+        wb = torch.zeros((self.cout, self.cf + 8), dtype=BF16, device=w.device)
+        wb[:, :self.cf] = w[:, 3:]
+        wb[:, self.cf:self.cf + 3] = w[:, :3]
+        return wb
+
+    def forward(self, x, pool_k=0, seed=0):
+        """x [P, Kp] bf16 -> z [P, cout] bf16, or (pooled [P / pool_k, cout], arg) when pool_k > 0."""
+        bn = self.bn
+        P = x.shape[0]
+        wb = self._weight_rows()
+        y = gemm(x, wb)
+        s, q = colstats(y)
+        mean64 = s / P
+        var64 = torch.clamp(q / P - mean64 * mean64, min=0.0)
+        mean, var = mean64.float(), var64.float()
+        rstd = torch.rsqrt(var + bn.eps)
+        scale = bn.weight.detach() * rstd
+        shift = bn.bias.detach() - mean * scale
+        if bn.track_running_stats:  # torch.nn.BatchNorm semantics: momentum update, unbiased variance
+            m = bn.momentum
+            bn.running_mean.mul_(1 - m).add_(mean, alpha=m)
+            bn.running_var.mul_(1 - m).add_(var * (P / max(P - 1, 1)), alpha=m)
+            bn.num_batches_tracked += 1
+        dev = x.device
+        if pool_k:
+            G = P // pool_k
+            z = torch.empty((G, self.cout), dtype=BF16, device=dev)
+            arg = torch.empty((G, self.cout), dtype=torch.uint8, device=dev)
+            check(lib.s4g_train_bn_act_maxpool_bf16(ptr(y), ptr(scale), ptr(shift), ptr(z), ptr(arg), G, pool_k, self.cout, 1,
+                                                    stream_ptr(dev)), "train_bn_act_maxpool")
+        else:
+            arg = None
+            z = torch.empty((P, self.cout), dtype=BF16, device=dev)
+            check(lib.s4g_train_bn_act_bf16(ptr(y), ptr(scale), ptr(shift), ptr(z), P, self.cout, 1, seed, self.drop_p,
+                                            stream_ptr(dev)), "train_bn_act")
+        self.saved = (x, y, wb, mean, rstd, scale, shift, arg, pool_k, seed)
+        return (z, arg) if pool_k else z
+
+    def backward(self, dz, need_dx=True):
+        """dz: [P, cout] bf16 (or the pooled gradient [G, cout] when the forward pooled).  Accumulates the parameter
+        gradients; returns dx [P, Kp or Cf] bf16 (None when not needed)."""
+        x, y, wb, mean, rstd, scale, shift, arg, pool_k, seed = self.saved
+        self.saved = None
+        P, C = y.shape
+        dev = y.device
+        sums = torch.empty(2 * C, dtype=torch.float64, device=dev)
+        drop = 0.0 if pool_k else self.drop_p
+        check(lib.s4g_train_bn_bwd_reduce_bf16(ptr(dz), ptr(arg) if pool_k else None, pool_k, ptr(y), ptr(scale), ptr(shift),
+                                               ptr(mean), ptr(rstd), P, C, 1, seed, drop, ptr(sums), stream_ptr(dev)),
+              "train_bn_bwd_reduce")
+        sg, sgx = sums[:C].float(), sums[C:].float()
+        gamma = self.bn.weight.detach()
+        # dy = coef * (g - m1 - xhat * m2), folded per channel into ka * g + kb * y + kc
+        ka = (gamma * rstd).contiguous()
+        m1, m2 = sg / P, sgx / P
+        kb = (-ka * rstd * m2).contiguous()
+        kc = (ka * (rstd * m2 * mean - m1)).contiguous()
+        dy = torch.empty((P, C), dtype=BF16, device=dev)
+        check(lib.s4g_train_bn_bwd_apply_bf16(ptr(dz), ptr(arg) if pool_k else None, pool_k, ptr(y), ptr(scale), ptr(shift),
+                                              ptr(ka), ptr(kb), ptr(kc), P, C, 1, seed, drop, ptr(dy), stream_ptr(dev)),
+              "train_bn_bwd_apply")
+        _accumulate(self.bn.weight, sgx)
+        _accumulate(self.bn.bias, sg)
+        # dW = dY^T X: a plain library GEMM (bf16 operands, fp32 result)
+        dwb = torch.mm(dy.t(), x, out_dtype=torch.float32)
+        if self.cf is None:
+            dw = dwb[:, :self.cin]
+        else:
+            dw = torch.cat([dwb[:, self.cf:self.cf + 3], dwb[:, :self.cf]], dim=1)
+        _accumulate(self.conv.weight, dw.reshape(self.conv.weight.shape))
+        if not need_dx:
+            return None
+        cols = self.cf if self.cf is not None else wb.shape[1]
+        if cols == 0:
+            return None
+        return gemm(dy, wb[:, :cols].t().contiguous())  # dX = dY · W  (B operand = W^T rows)
+
+
+def _accumulate(param, grad):
+    grad = grad.to(param.dtype)
+    if param.grad is None:
+        param.grad = grad.clone().reshape(param.shape)
+    else:
+        param.grad.add_(grad.reshape(param.shape))
+
+
+class TrainEngine:
+    """forward + loss + backward of PN2_CLS on the fused training kernels.  ``model``: PointNet2_tcls.PointNet2 on CUDA
+    (a fusable configuration, see PointNet2.fusable); ``loss_fn``: PointNet2Loss."""
+
+    def __init__(self, model, loss_fn, seed=0):
+        if not model.fusable():
+            raise RuntimeError("TrainEngine: no fused plan for this configuration (PointNet2.fusable)")
+        self.model, self.loss_fn = model, loss_fn
+        self.cfg = model.config
+        self.step_count = 0
+        self.seed = int(seed)
+        cf = 0
+        self.sa = []
+        for m in model.sa_modules:
+            blocks = [Block(b, grouped_cf=cf if j == 0 else None) for j, b in enumerate(m.mlp)]
+            self.sa.append(blocks)
+            cf = blocks[-1].cout
+        self.fp = [[Block(b) for b in m.mlp] for m in model.fp_modules]
+        p = self.cfg["dropout_prob"]
+        self.heads = [([Block(b, drop_p=dp) for b in mlp], logit) for mlp, logit, dp in (
+            (model.mlp_seg, model.seg_logit, p), (model.mlp_R, model.R_logit, 0.0), (model.mlp_t, model.t_logit, 0.0),
+            (model.mlp_movable, model.movable_logit[0], p))]
+
+    def _seed(self, k):
+        return (self.seed * 1000003 + self.step_count * 7919 + k * 104729 + 1) & 0x7FFFFFFF
+
+    # ------------------------------------------------------------------ forward
+    def forward(self, points):
+        """points (B,3,N) fp32 CUDA -> predictions (fp32, autograd leaves underneath) ; keeps what backward needs."""
+        cfg = self.cfg
+        E = FusedPointNet2
+        xyz = points.float().contiguous()
+        B = xyz.shape[0]
+        dev = xyz.device
+        feat = None
+        lv_xyz, lv_feat, self._sa_ctx = [xyz], [None], []
+        for i, blocks in enumerate(self.sa):
+            M, K = cfg["num_centroids"][i], cfg["num_neighbours"][i]
+            N = xyz.shape[2]
+            idx = E.fps(xyz, M)
+            ctr = E.gather_xyz(xyz, idx)
+            nbr = E.ball_query(xyz, ctr, cfg["radius"][i], K)
+            cf = 0 if feat is None else feat.shape[1]
+            x0 = torch.empty((B * M * K, cf + 8), dtype=BF16, device=dev)
+            check(lib.s4g_train_group_rows_bf16(ptr(feat) if feat is not None else None, ptr(xyz), ptr(ctr), ptr(nbr), B, N, M,
+                                                K, cf, ptr(x0), stream_ptr(dev)), "train_group_rows")
+            h = x0
+            for j, blk in enumerate(blocks):
+                last = j == len(blocks) - 1
+                h = blk.forward(h, pool_k=K if last else 0)
+            feat, _ = h
+            self._sa_ctx.append((nbr, B, N, M, K, cf))
+            xyz = ctr
+            lv_xyz.append(xyz)
+            lv_feat.append(feat)
+        sparse_xyz, sparse = xyz, feat
+        self._fp_ctx = []
+        for i, blocks in enumerate(self.fp):
+            dense_xyz, dense = lv_xyz[-2 - i], lv_feat[-2 - i]
+            idx3, w = E.three_nn_weights(dense_xyz, sparse_xyz)
+            Nk, Nq = sparse_xyz.shape[2], dense_xyz.shape[2]
+            x = E.interp_concat(sparse, idx3, w, dense, B, Nk, Nq)
+            self._fp_ctx.append((idx3, w, B, Nk, Nq, sparse.shape[1], 0 if dense is None else dense.shape[1]))
+            h = x
+            for blk in blocks:
+                h = blk.forward(h)
+            sparse_xyz, sparse = dense_xyz, h
+        n = sparse_xyz.shape[2]
+        self._lv_shapes = [None if f is None else tuple(f.shape) for f in lv_feat]
+        self._point_feat_shape = tuple(sparse.shape)
+        outs, self._head_leaves = [], []
+        for k, (blocks, logit) in enumerate(self.heads):
+            h = sparse
+            for j, blk in enumerate(blocks):
+                h = blk.forward(h, seed=self._seed(10 * k + j))
+            leaf = h.float().requires_grad_(True)  # the biased 1x1 conv + loss run in torch: autograd returns d/d(leaf)
+            wl = logit.weight.reshape(logit.weight.shape[0], -1)
+            o = torch.addmm(logit.bias, leaf, wl.t()).reshape(B, n, -1).permute(0, 2, 1)
+            outs.append(o)
+            self._head_leaves.append(leaf)
+        return {"score": outs[0], "frame_R": outs[1], "frame_t": outs[2], "movable_logits": torch.sigmoid(outs[3])}
+
+    # ------------------------------------------------------------------ backward
+    def backward(self):
+        """after ``total_loss.backward()`` filled the head leaves' gradients"""
+        dev = self._head_leaves[0].device
+        d_point = None
+        for (blocks, _), leaf in zip(self.heads, self._head_leaves):
+            dz = leaf.grad.to(BF16)
+            for blk in reversed(blocks):
+                dz = blk.backward(dz)
+            d_point = dz.float() if d_point is None else d_point.add_(dz)
+        self._head_leaves = None
+        # gradient buffers of the level features (fp32: they receive scatter-adds), index = level
+        lv_grad = [None if s is None else torch.zeros(s, dtype=torch.float32, device=dev) for s in self._lv_shapes]
+        n_fp = len(self.fp)
+        d_out = d_point.to(BF16)  # gradient of the current propagation level's OUTPUT rows
+        for i in reversed(range(n_fp)):
+            dz = d_out
+            for blk in reversed(self.fp[i]):
+                dz = blk.backward(dz)
+            idx3, w, B, Nk, Nq, c2, c1 = self._fp_ctx[i]
+            # dz rows = [d interpolated (c2) | d dense skip (c1)]
+            if c1:
+                lv_grad[-2 - i].add_(dz[:, c2:c2 + c1])
+            d_sparse = torch.zeros((B * Nk, c2), dtype=torch.float32, device=dev)
+            check(lib.s4g_train_interp_rows_bwd(ptr(dz), dz.stride(0), ptr(idx3), ptr(w), B, Nk, Nq, c2, ptr(d_sparse),
+                                                stream_ptr(dev)), "train_interp_rows_bwd")
+            if i == 0:
+                lv_grad[-1].add_(d_sparse)  # the coarsest propagation level interpolates the last SA level's features
+            else:
+                d_out = d_sparse.to(BF16)
+        for i in reversed(range(len(self.sa))):
+            blocks = self.sa[i]
+            nbr, B, N, M, K, cf = self._sa_ctx[i]
+            dz = lv_grad[i + 1].to(BF16)  # pooled gradient [B*M, cout]
+            lv_grad[i + 1] = None
+            for j in reversed(range(len(blocks))):
+                dz = blocks[j].backward(dz, need_dx=(j > 0 or cf > 0))
+            if cf > 0:
+                check(lib.s4g_train_group_rows_bwd(ptr(dz), dz.stride(0), ptr(nbr), B, N, M, K, cf, ptr(lv_grad[i]),
+                                                   stream_ptr(dev)), "train_group_rows_bwd")
+        self._sa_ctx = self._fp_ctx = None
+
+    def step_loss(self, data_batch, labels):
+        """forward + loss + full backward; returns the (detached) loss dict.  Gradients accumulate in param.grad."""
+        self.step_count += 1
+        with torch.cuda.device(data_batch["scene_points"].device):
+            with torch.enable_grad():
+                preds = self.forward(data_batch["scene_points"])
+                losses = self.loss_fn(preds, labels)
+                total = sum(losses.values())
+                total.backward()
+            with torch.no_grad():
+                self.backward()
+        return {k: v.detach() for k, v in losses.items()}

@@ -67,6 +67,6 @@ def test_top_frames_against_the_oracle_collision_check(tmp_path):
     keep, _ = model_cpu.collision_filter(H, cloud.T)
     assert len(top_H) == len(keep) and len(score) == len(keep)
     if len(keep):
-        np.testing.assert_allclose(top_H, H[keep], atol=1e-9)
+        np.testing.assert_allclose(top_H, H[keep], atol=1e-5)  # the logger decodes in fp32 like the reference (:37-46)
         assert os.path.exists(tmp_path / "top_frames.npy")
     assert (tmp_path / "postprocess_time_ours.txt").exists()
