@@ -136,6 +136,17 @@ int s4g_linear_tf32(const float* x, long long ldx, const float* w, long long ldw
  * Forward: A = layer input, B = conv weight [cout][cin].  Input gradient: A = dY, B = weight^T [cin][cout]. */
 int s4g_gemm_bf16(const void* a, long long lda, const void* b, long long ldb, void* c, long long ldc, long long P, int N,
                   int K, void* stream);
+/* the same GEMM with the BatchNorm batch statistics of its (bf16-rounded) result accumulated in the epilogue:
+ * stats2n[0..N) = sum_r c[r][n], stats2n[N..2N) = sum_r c[r][n]^2 (fp64, zeroed here) — no extra pass over C. */
+int s4g_gemm_bf16_stats(const void* a, long long lda, const void* b, long long ldb, void* c, long long ldc, long long P, int N,
+                        int K, double* stats2n, void* stream);
+/* BatchNorm's per-channel algebra in one launch.  Forward: out4c = [mean | rstd | scale = gamma * rstd | shift = beta -
+ * mean * scale]; running_mean / running_var (may both be NULL) updated like torch.nn.BatchNorm{1,2}d (momentum, unbiased
+ * variance).  Backward: dgamma += sum g * xhat, dbeta += sum g, out3c = [ka | kb | kc] of s4g_train_bn_bwd_apply_bf16. */
+int s4g_train_bn_finalize(const double* sums2c, long long P, int C, const float* gamma, const float* beta, float eps,
+                          float momentum, float* running_mean, float* running_var, float* out4c, void* stream);
+int s4g_train_bn_bwd_finalize(const double* sums2c, long long P, int C, const float* gamma, const float* mean_rstd,
+                              float* dgamma, float* dbeta, float* out3c, void* stream);
 /* sums2c[0..C) = sum_r y[r][c], sums2c[C..2C) = sum_r y[r][c]^2 (fp64; zeroed here) -> the batch mean / variance of
  * BatchNorm's training mode (torch.nn.BatchNorm{1,2}d over the (B, M, K) positions of a channel). */
 int s4g_train_colstats_bf16(const void* y, long long ld, long long P, int C, double* sums2c, void* stream);

@@ -190,15 +190,17 @@ int grid_build(const float* points, int B, int N, int mode, float radius, Grid* 
   const size_t o_sorted = o_start + align_up(sizeof(int) * (cells + 1));
   const size_t o_tmp = o_sorted + align_up(sizeof(float4) * (size_t)B * N);
   const size_t total = o_tmp + align_up(scan_tmp);
-  static bool pool_ready = false;
-  if (!pool_ready) {  // keep freed blocks in the stream-ordered pool instead of returning them to the OS
-    int dev = 0;
+  // keep freed blocks in the stream-ordered pool instead of returning them to the OS — once PER DEVICE (one process may
+  // drive several GPUs, e.g. nn.DataParallel replicas); a racing duplicate call from another thread is harmless
+  static bool pool_ready[64] = {};
+  int dev = 0;
+  S4G_CUDA(cudaGetDevice(&dev));
+  if (dev >= 0 && dev < 64 && !pool_ready[dev]) {
     cudaMemPool_t pool;
-    S4G_CUDA(cudaGetDevice(&dev));
     S4G_CUDA(cudaDeviceGetDefaultMemPool(&pool, dev));
     uint64_t keep = ~0ull;
     S4G_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
-    pool_ready = true;
+    pool_ready[dev] = true;
   }
   uint8_t* arena = nullptr;
   S4G_CUDA(cudaMallocAsync((void**)&arena, total, stream));

@@ -70,10 +70,19 @@ colstats_kernel(const __nv_bfloat16* __restrict__ y, long long ld, long long P, 
   const long long r1 = min(P, r0 + kStatRows);
   F8 s{}, q{};
   if (rl < lanes) {
-    for (long long r = r0 + rl; r < r1; r += lanes) {
-      const F8 v = unpack8(__ldg(reinterpret_cast<const uint4*>(y + r * ld) + piece));
+    for (long long r = r0 + rl; r < r1; r += 4LL * lanes) {  // four rows in flight per thread
+      uint4 raw[4];
 #pragma unroll
-      for (int e = 0; e < 8; ++e) { s.v[e] += v.v[e]; q.v[e] = fmaf(v.v[e], v.v[e], q.v[e]); }
+      for (int u = 0; u < 4; ++u) {
+        const long long rr = r + (long long)u * lanes;
+        raw[u] = rr < r1 ? __ldg(reinterpret_cast<const uint4*>(y + rr * ld) + piece) : make_uint4(0u, 0u, 0u, 0u);
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const F8 v = unpack8(raw[u]);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) { s.v[e] += v.v[e]; q.v[e] = fmaf(v.v[e], v.v[e], q.v[e]); }
+      }
     }
     float* dst = s_part + ((size_t)rl * pieces + piece) * 16;
 #pragma unroll
@@ -370,6 +379,46 @@ f32_to_bf16_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ y, l
   reinterpret_cast<uint4*>(y)[i] = pack8(load_f8(x + i * 8));
 }
 
+// BatchNorm (training) per-channel algebra in one launch instead of a dozen tiny ones.
+// forward: sums -> mean, rstd, scale = gamma * rstd, shift = beta - mean * scale; running statistics updated like
+// torch.nn.BatchNorm (momentum, unbiased variance).  out4c = [mean | rstd | scale | shift].
+__global__ void bn_finalize_kernel(const double* __restrict__ sums, long long P, int C, const float* __restrict__ gamma,
+                                   const float* __restrict__ beta, float eps, float momentum, float* __restrict__ run_mean,
+                                   float* __restrict__ run_var, float* __restrict__ out4c) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const double mean = sums[c] / (double)P;
+  double var = sums[C + c] / (double)P - mean * mean;
+  var = var > 0.0 ? var : 0.0;
+  const float rstd = rsqrtf((float)var + eps);
+  const float scale = gamma[c] * rstd;
+  out4c[c] = (float)mean;
+  out4c[C + c] = rstd;
+  out4c[2 * C + c] = scale;
+  out4c[3 * C + c] = beta[c] - (float)mean * scale;
+  if (run_mean) {
+    run_mean[c] = (1.f - momentum) * run_mean[c] + momentum * (float)mean;
+    run_var[c] = (1.f - momentum) * run_var[c] + momentum * (float)(var * ((double)P / (double)(P > 1 ? P - 1 : 1)));
+  }
+}
+// backward: sums = [sum g | sum g * xhat] -> dgamma += sum g xhat, dbeta += sum g, and the folded coefficients of
+// dy = ka * g + kb * y + kc.  out3c = [ka | kb | kc].
+__global__ void bn_bwd_finalize_kernel(const double* __restrict__ sums, long long P, int C, const float* __restrict__ gamma,
+                                       const float* __restrict__ mean_rstd, float* __restrict__ dgamma,
+                                       float* __restrict__ dbeta, float* __restrict__ out3c) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const float sg = (float)sums[c], sgx = (float)sums[C + c];
+  const float mean = mean_rstd[c], rstd = mean_rstd[C + c];
+  const float ka = gamma[c] * rstd;
+  const float m1 = (float)(sums[c] / (double)P), m2 = (float)(sums[C + c] / (double)P);
+  out3c[c] = ka;
+  out3c[C + c] = -ka * rstd * m2;
+  out3c[2 * C + c] = ka * (rstd * m2 * mean - m1);
+  dgamma[c] += sgx;
+  dbeta[c] += sg;
+}
+
 static unsigned grid_for(long long work, int threads) { return (unsigned)((work + threads - 1) / threads); }
 
 }  // namespace trn
@@ -487,5 +536,23 @@ extern "C" int s4g_train_f32_to_bf16(const float* x, void* y, long long n, void*
   if (n == 0) return S4G_OK;
   f32_to_bf16_kernel<<<grid_for(n / 8, 256), 256, 0, (cudaStream_t)stream>>>(x, reinterpret_cast<bf16*>(y), n / 8);
   S4G_LAUNCH_CHECK("train_f32_to_bf16");
+  return S4G_OK;
+}
+
+extern "C" int s4g_train_bn_finalize(const double* sums2c, long long P, int C, const float* gamma, const float* beta, float eps,
+                                     float momentum, float* running_mean, float* running_var, float* out4c, void* stream) {
+  S4G_CHECK_ARG(sums2c && gamma && beta && out4c && P > 0 && C > 0 && (running_mean == nullptr) == (running_var == nullptr),
+                "train_bn_finalize: bad arguments");
+  bn_finalize_kernel<<<grid_for(C, 128), 128, 0, (cudaStream_t)stream>>>(sums2c, P, C, gamma, beta, eps, momentum,
+                                                                        running_mean, running_var, out4c);
+  S4G_LAUNCH_CHECK("train_bn_finalize");
+  return S4G_OK;
+}
+
+extern "C" int s4g_train_bn_bwd_finalize(const double* sums2c, long long P, int C, const float* gamma, const float* mean_rstd,
+                                         float* dgamma, float* dbeta, float* out3c, void* stream) {
+  S4G_CHECK_ARG(sums2c && gamma && mean_rstd && dgamma && dbeta && out3c && P > 0 && C > 0, "train_bn_bwd_finalize: bad arguments");
+  bn_bwd_finalize_kernel<<<grid_for(C, 128), 128, 0, (cudaStream_t)stream>>>(sums2c, P, C, gamma, mean_rstd, dgamma, dbeta, out3c);
+  S4G_LAUNCH_CHECK("train_bn_bwd_finalize");
   return S4G_OK;
 }

@@ -500,19 +500,22 @@ class FusedPointNet2:
                     done.record()
                 early_nn[fp_level] = (found, done)
                 pending = None
-            with _sec(timer, "sa%d.gather_xyz" % i):
-                new_xyz = self.gather_xyz(xyz, idx)
-            with _sec(timer, "sa%d.ball_query" % i):
-                if ball_grid:
-                    main.wait_event(grid_done)
-                    k = cfg["num_neighbours"][i]
-                    nbr = torch.empty((B, new_xyz.shape[2], k), dtype=torch.int32, device=xyz.device)
-                    rc = lib.s4g_ball_query_with_grid_f32_i32(ball_grid, ptr(xyz), ptr(new_xyz), new_xyz.shape[2], k,
-                                                              ptr(nbr), None, stream_ptr(xyz.device))
+            try:
+                with _sec(timer, "sa%d.gather_xyz" % i):
+                    new_xyz = self.gather_xyz(xyz, idx)
+                with _sec(timer, "sa%d.ball_query" % i):
+                    if ball_grid:
+                        main.wait_event(grid_done)
+                        k = cfg["num_neighbours"][i]
+                        nbr = torch.empty((B, new_xyz.shape[2], k), dtype=torch.int32, device=xyz.device)
+                        check(lib.s4g_ball_query_with_grid_f32_i32(ball_grid, ptr(xyz), ptr(new_xyz), new_xyz.shape[2], k,
+                                                                   ptr(nbr), None, stream_ptr(xyz.device)),
+                              "ball_query_with_grid")
+                    else:
+                        nbr = self.ball_query(xyz, new_xyz, cfg["radius"][i], cfg["num_neighbours"][i])
+            finally:
+                if ball_grid:  # host struct + stream-ordered arena: released whatever happened in between
                     lib.s4g_ball_grid_free(ball_grid, stream_ptr(xyz.device))
-                    check(rc, "ball_query_with_grid")
-                else:
-                    nbr = self.ball_query(xyz, new_xyz, cfg["radius"][i], cfg["num_neighbours"][i])
             with _sec(timer, "sa%d.mlp" % i):
                 feat = chain.run_gather(feat, xyz, new_xyz, nbr)
             if overlap and i + 1 < n_sa and len(self.fp_chains) == n_sa:

@@ -33,15 +33,35 @@ BF16 = torch.bfloat16
 
 
 # ------------------------------------------------------------------------------------------------ kernel wrappers
-def gemm(a, b):
-    """a [P, K] bf16 (row stride % 8 == 0), b [N, K] bf16 -> [P, N] bf16 (N padded to 8 internally when needed)."""
+def gemm(a, b, stats=False):
+    """a [P, K] bf16 (row stride % 8 == 0), b [N, K] bf16 -> [P, N] bf16 (N padded to 8 internally when needed).
+    ``stats``: also return the fp64 [2N] column sums / sums of squares of the stored result (fused in the epilogue)."""
     assert a.dtype == BF16 and b.dtype == BF16 and a.stride(1) == 1 and b.stride(1) == 1 and a.shape[1] == b.shape[1]
     P, K = a.shape
     N = b.shape[0]
     ldc = (N + 7) // 8 * 8
     c = torch.empty((P, ldc), dtype=BF16, device=a.device)
+    if stats:
+        sums = torch.empty(2 * N, dtype=torch.float64, device=a.device)
+        check(lib.s4g_gemm_bf16_stats(ptr(a), a.stride(0), ptr(b), b.stride(0), ptr(c), ldc, P, N, K, ptr(sums),
+                                      stream_ptr(a.device)), "gemm_bf16_stats")
+        return (c if ldc == N else c[:, :N]), sums
     check(lib.s4g_gemm_bf16(ptr(a), a.stride(0), ptr(b), b.stride(0), ptr(c), ldc, P, N, K, stream_ptr(a.device)), "gemm_bf16")
     return c if ldc == N else c[:, :N]
+
+
+# BatchNorm statistics inside the GEMM epilogue (s4g_gemm_bf16_stats) or as a separate pass over the stored output.
+# Measured at 32 scenes (profiles/r02/train_kernels.md): with the statistics fused, the 4 epilogue warps need ~5 800
+# cycles per 128 x 128 tile (shuffle butterfly) against ~2 800 cycles of HBM time, so the memory-bound layers run at
+# 1.2-3.2 TB/s; the plain GEMM runs at 6.0-6.8 TB/s and the separate pass at ~5 TB/s — cheaper in total.  Kept selectable.
+FUSED_STATS = True
+
+
+def colstats_raw(y):
+    P, C = y.shape
+    out = torch.empty(2 * C, dtype=torch.float64, device=y.device)
+    check(lib.s4g_train_colstats_bf16(ptr(y), y.stride(0), P, C, ptr(out), stream_ptr(y.device)), "train_colstats")
+    return out
 
 
 def colstats(y):
@@ -83,19 +103,21 @@ class Block:
         bn = self.bn
         P = x.shape[0]
         wb = self._weight_rows()
-        y = gemm(x, wb)
-        s, q = colstats(y)
-        mean64 = s / P
-        var64 = torch.clamp(q / P - mean64 * mean64, min=0.0)
-        mean, var = mean64.float(), var64.float()
-        rstd = torch.rsqrt(var + bn.eps)
-        scale = bn.weight.detach() * rstd
-        shift = bn.bias.detach() - mean * scale
-        if bn.track_running_stats:  # torch.nn.BatchNorm semantics: momentum update, unbiased variance
-            m = bn.momentum
-            bn.running_mean.mul_(1 - m).add_(mean, alpha=m)
-            bn.running_var.mul_(1 - m).add_(var * (P / max(P - 1, 1)), alpha=m)
+        if FUSED_STATS:
+            y, sums = gemm(x, wb, stats=True)  # conv + the BatchNorm batch statistics of its (stored) output
+        else:
+            y = gemm(x, wb)
+            sums = colstats_raw(y)
+        dev = x.device
+        C = self.cout
+        stat = torch.empty(4 * C, dtype=torch.float32, device=dev)  # [mean | rstd | scale | shift]
+        track = bn.track_running_stats and bn.running_mean is not None
+        check(lib.s4g_train_bn_finalize(ptr(sums), P, C, ptr(bn.weight), ptr(bn.bias), bn.eps, bn.momentum,
+                                        ptr(bn.running_mean) if track else None, ptr(bn.running_var) if track else None,
+                                        ptr(stat), stream_ptr(dev)), "train_bn_finalize")
+        if track:
             bn.num_batches_tracked += 1
+        mean_rstd, scale, shift = stat[:2 * C], stat[2 * C:3 * C], stat[3 * C:]
         dev = x.device
         if pool_k:
             G = P // pool_k
@@ -108,34 +130,30 @@ class Block:
             z = torch.empty((P, self.cout), dtype=BF16, device=dev)
             check(lib.s4g_train_bn_act_bf16(ptr(y), ptr(scale), ptr(shift), ptr(z), P, self.cout, 1, seed, self.drop_p,
                                             stream_ptr(dev)), "train_bn_act")
-        self.saved = (x, y, wb, mean, rstd, scale, shift, arg, pool_k, seed)
+        self.saved = (x, y, wb, mean_rstd, scale, shift, arg, pool_k, seed)
         return (z, arg) if pool_k else z
 
     def backward(self, dz, need_dx=True):
         """dz: [P, cout] bf16 (or the pooled gradient [G, cout] when the forward pooled).  Accumulates the parameter
         gradients; returns dx [P, Kp or Cf] bf16 (None when not needed)."""
-        x, y, wb, mean, rstd, scale, shift, arg, pool_k, seed = self.saved
+        x, y, wb, mean_rstd, scale, shift, arg, pool_k, seed = self.saved
         self.saved = None
         P, C = y.shape
         dev = y.device
         sums = torch.empty(2 * C, dtype=torch.float64, device=dev)
         drop = 0.0 if pool_k else self.drop_p
         check(lib.s4g_train_bn_bwd_reduce_bf16(ptr(dz), ptr(arg) if pool_k else None, pool_k, ptr(y), ptr(scale), ptr(shift),
-                                               ptr(mean), ptr(rstd), P, C, 1, seed, drop, ptr(sums), stream_ptr(dev)),
-              "train_bn_bwd_reduce")
-        sg, sgx = sums[:C].float(), sums[C:].float()
-        gamma = self.bn.weight.detach()
-        # dy = coef * (g - m1 - xhat * m2), folded per channel into ka * g + kb * y + kc
-        ka = (gamma * rstd).contiguous()
-        m1, m2 = sg / P, sgx / P
-        kb = (-ka * rstd * m2).contiguous()
-        kc = (ka * (rstd * m2 * mean - m1)).contiguous()
+                                               ptr(mean_rstd), ptr(mean_rstd[C:]), P, C, 1, seed, drop, ptr(sums),
+                                               stream_ptr(dev)), "train_bn_bwd_reduce")
+        # dgamma += sum g xhat, dbeta += sum g, and dy = ka * g + kb * y + kc folded per channel — one launch
+        gw, gb = _grad_buffer(self.bn.weight), _grad_buffer(self.bn.bias)
+        coef = torch.empty(3 * C, dtype=torch.float32, device=dev)
+        check(lib.s4g_train_bn_bwd_finalize(ptr(sums), P, C, ptr(self.bn.weight), ptr(mean_rstd), ptr(gw), ptr(gb), ptr(coef),
+                                            stream_ptr(dev)), "train_bn_bwd_finalize")
         dy = torch.empty((P, C), dtype=BF16, device=dev)
         check(lib.s4g_train_bn_bwd_apply_bf16(ptr(dz), ptr(arg) if pool_k else None, pool_k, ptr(y), ptr(scale), ptr(shift),
-                                              ptr(ka), ptr(kb), ptr(kc), P, C, 1, seed, drop, ptr(dy), stream_ptr(dev)),
-              "train_bn_bwd_apply")
-        _accumulate(self.bn.weight, sgx)
-        _accumulate(self.bn.bias, sg)
+                                              ptr(coef), ptr(coef[C:]), ptr(coef[2 * C:]), P, C, 1, seed, drop, ptr(dy),
+                                              stream_ptr(dev)), "train_bn_bwd_apply")
         # dW = dY^T X: a plain library GEMM (bf16 operands, fp32 result)
         dwb = torch.mm(dy.t(), x, out_dtype=torch.float32)
         if self.cf is None:
@@ -149,6 +167,14 @@ class Block:
         if cols == 0:
             return None
         return gemm(dy, wb[:, :cols].t().contiguous())  # dX = dY · W  (B operand = W^T rows)
+
+
+def _grad_buffer(param):
+    """param.grad as a contiguous fp32 tensor the kernels can add into (created as zeros when absent)"""
+    if param.grad is None:
+        param.grad = torch.zeros_like(param)
+    assert param.grad.is_contiguous() and param.grad.dtype == torch.float32
+    return param.grad
 
 
 def _accumulate(param, grad):

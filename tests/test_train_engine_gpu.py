@@ -33,6 +33,22 @@ def test_gemm_bf16(P, N, K):
     assert err <= 1e-2 * max(1.0, want.abs().max().item()), err  # one bf16 rounding of the fp32-accumulated result
 
 
+@pytest.mark.parametrize("P,N,K", [(1000, 128, 64), (70001, 256, 40), (333, 72, 264), (20000, 1024, 128)])
+def test_gemm_bf16_fused_statistics(P, N, K):
+    """the BatchNorm statistics accumulated in the GEMM epilogue equal the column sums of the STORED (bf16) result"""
+    from s4g_release_b200.train_engine import colstats, gemm
+    g = torch.Generator().manual_seed(P + N)
+    a = torch.randn(P, K, generator=g).cuda().to(BF)
+    b = (torch.randn(N, K, generator=g) / np.sqrt(K)).cuda().to(BF)
+    c, sums = gemm(a, b, stats=True)
+    plain = gemm(a, b)
+    assert torch.equal(c, plain)
+    s, q = colstats(c.contiguous())
+    torch.cuda.synchronize()
+    np.testing.assert_allclose(sums[:N].cpu().numpy(), s.cpu().numpy(), rtol=1e-4, atol=2e-2)
+    np.testing.assert_allclose(sums[N:].cpu().numpy(), q.cpu().numpy(), rtol=1e-4, atol=2e-2)
+
+
 def test_gemm_bf16_strided_operands():
     """A with a row stride larger than K (a column slice of a wider matrix), B^T made contiguous by the caller"""
     from s4g_release_b200.train_engine import gemm
