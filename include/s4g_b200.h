@@ -182,6 +182,13 @@ int s4g_train_group_rows_bwd(const void* dx, long long ld, const int* nbr, int B
 int s4g_train_interp_rows_bwd(const void* dx, long long ld, const int* index, const float* weight, int B, int Nk, int Nq,
                               int C2, float* dsparse, void* stream);
 int s4g_train_f32_to_bf16(const float* x, void* y, long long n, void* stream);
+/* The final biased 1x1 conv of a head (reference PointNet2_tcls.py:84-95, nn.Conv1d(C, k, 1), k <= 16) from the bf16 rows
+ * h [P][C] straight into the reference's fp32 channel-first logits (P / n_points, k, n_points), and its input gradient
+ * dh [P][C] bf16 = dlogits · w.  (dw / dbias are a plain reduction over P: left to the caller's library GEMM.) */
+int s4g_train_head_logits_fwd(const void* h, const float* w, const float* bias, float* out, long long P, int C, int k,
+                              int n_points, void* stream);
+int s4g_train_head_logits_bwd(const float* dlogits, const float* w, void* dh, long long P, int C, int k, int n_points,
+                              void* stream);
 
 /* ---- fused inference path (channel-last bf16 features, int32 indices) ---------------------- */
 

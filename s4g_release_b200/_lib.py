@@ -72,6 +72,8 @@ _SIGNATURES = {
     "s4g_train_group_rows_bwd": ([_vp, _ll, _vp, _i, _i, _i, _i, _i, _vp, _vp], _i),
     "s4g_train_interp_rows_bwd": ([_vp, _ll, _vp, _vp, _i, _i, _i, _i, _vp, _vp], _i),
     "s4g_train_f32_to_bf16": ([_vp, _vp, _ll, _vp], _i),
+    "s4g_train_head_logits_fwd": ([_vp, _vp, _vp, _vp, _ll, _i, _i, _i, _vp], _i),
+    "s4g_train_head_logits_bwd": ([_vp, _vp, _vp, _ll, _i, _i, _i, _vp], _i),
     "s4g_chain_create": ([_i, _ip, _ip, _ip, _i, _i, _i, _i, _i, _i], _vp),
     "s4g_chain_create_slots": ([_i, _ip, _ip, _ip, _i, _i, _i, _i, _i, _i, _i], _vp),
     "s4g_chain_create_tuned": ([_i, _ip, _ip, _ip, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i], _vp),

@@ -419,6 +419,70 @@ __global__ void bn_bwd_finalize_kernel(const double* __restrict__ sums, long lon
   dbeta[c] += sg;
 }
 
+// ---------------------------------------------------------------------------------------------- head logits
+// The final biased 1x1 conv of a head (reference PointNet2_tcls.py:84-95: nn.Conv1d(C, k, 1), k <= 16) straight from
+// the bf16 rows into the reference's fp32 channel-first layout (B, k, n_points), and its input gradient.  One thread
+// per row; the k x C weight matrix lives in shared memory (broadcast reads).
+constexpr int kMaxLogits = 16;
+
+__global__ void __launch_bounds__(256)
+head_logits_fwd_kernel(const __nv_bfloat16* __restrict__ h, const float* __restrict__ w, const float* __restrict__ bias,
+                       float* __restrict__ out, long long P, int C, int k, int n_points) {
+  extern __shared__ float s_w[];  // [k][C]
+  for (int i = threadIdx.x; i < k * C; i += blockDim.x) s_w[i] = w[i];
+  __syncthreads();
+  const long long row = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (row >= P) return;
+  float acc[kMaxLogits];
+#pragma unroll
+  for (int j = 0; j < kMaxLogits; ++j) acc[j] = j < k ? __ldg(bias + j) : 0.f;
+  const uint4* src = reinterpret_cast<const uint4*>(h + row * C);
+  for (int p = 0; p < (C >> 3); ++p) {
+    const F8 v = unpack8(__ldg(src + p));
+#pragma unroll
+    for (int j = 0; j < kMaxLogits; ++j) {
+      if (j < k) {
+        const float* wj = s_w + j * C + p * 8;
+#pragma unroll
+        for (int e = 0; e < 8; ++e) acc[j] = fmaf(v.v[e], wj[e], acc[j]);
+      }
+    }
+  }
+  const long long b = row / n_points, n = row - b * n_points;
+  float* o = out + (b * k) * n_points + n;
+#pragma unroll
+  for (int j = 0; j < kMaxLogits; ++j)
+    if (j < k) o[(long long)j * n_points] = acc[j];
+}
+
+// dh[row][c] = sum_j dlogits[b][j][n] * w[j][c]   (bf16 rows out)
+__global__ void __launch_bounds__(256)
+head_logits_bwd_kernel(const float* __restrict__ dl, const float* __restrict__ w, __nv_bfloat16* __restrict__ dh, long long P,
+                       int C, int k, int n_points) {
+  extern __shared__ float s_w[];  // [k][C]
+  for (int i = threadIdx.x; i < k * C; i += blockDim.x) s_w[i] = w[i];
+  __syncthreads();
+  const long long row = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (row >= P) return;
+  const long long b = row / n_points, n = row - b * n_points;
+  float g[kMaxLogits];
+#pragma unroll
+  for (int j = 0; j < kMaxLogits; ++j) g[j] = j < k ? __ldg(dl + (b * k + j) * n_points + n) : 0.f;
+  uint4* dst = reinterpret_cast<uint4*>(dh + row * C);
+  for (int p = 0; p < (C >> 3); ++p) {
+    F8 o{};
+#pragma unroll
+    for (int j = 0; j < kMaxLogits; ++j) {
+      if (j < k) {
+        const float* wj = s_w + j * C + p * 8;
+#pragma unroll
+        for (int e = 0; e < 8; ++e) o.v[e] = fmaf(g[j], wj[e], o.v[e]);
+      }
+    }
+    dst[p] = pack8(o);
+  }
+}
+
 static unsigned grid_for(long long work, int threads) { return (unsigned)((work + threads - 1) / threads); }
 
 }  // namespace trn
@@ -554,5 +618,27 @@ extern "C" int s4g_train_bn_bwd_finalize(const double* sums2c, long long P, int 
   S4G_CHECK_ARG(sums2c && gamma && mean_rstd && dgamma && dbeta && out3c && P > 0 && C > 0, "train_bn_bwd_finalize: bad arguments");
   bn_bwd_finalize_kernel<<<grid_for(C, 128), 128, 0, (cudaStream_t)stream>>>(sums2c, P, C, gamma, mean_rstd, dgamma, dbeta, out3c);
   S4G_LAUNCH_CHECK("train_bn_bwd_finalize");
+  return S4G_OK;
+}
+
+extern "C" int s4g_train_head_logits_fwd(const void* h, const float* w, const float* bias, float* out, long long P, int C, int k,
+                                         int n_points, void* stream) {
+  S4G_CHECK_ARG(h && w && bias && out && P > 0 && k > 0 && k <= kMaxLogits && n_points > 0 && P % n_points == 0,
+                "train_head_logits_fwd: bad arguments");
+  TRN_CHECK_C(C);
+  head_logits_fwd_kernel<<<grid_for(P, 256), 256, sizeof(float) * k * C, (cudaStream_t)stream>>>(
+      reinterpret_cast<const bf16*>(h), w, bias, out, P, C, k, n_points);
+  S4G_LAUNCH_CHECK("train_head_logits_fwd");
+  return S4G_OK;
+}
+
+extern "C" int s4g_train_head_logits_bwd(const float* dlogits, const float* w, void* dh, long long P, int C, int k, int n_points,
+                                         void* stream) {
+  S4G_CHECK_ARG(dlogits && w && dh && P > 0 && k > 0 && k <= kMaxLogits && n_points > 0 && P % n_points == 0,
+                "train_head_logits_bwd: bad arguments");
+  TRN_CHECK_C(C);
+  head_logits_bwd_kernel<<<grid_for(P, 256), 256, sizeof(float) * k * C, (cudaStream_t)stream>>>(
+      dlogits, w, reinterpret_cast<bf16*>(dh), P, C, k, n_points);
+  S4G_LAUNCH_CHECK("train_head_logits_bwd");
   return S4G_OK;
 }

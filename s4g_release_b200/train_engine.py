@@ -196,6 +196,7 @@ class TrainEngine:
         self.cfg = model.config
         self.step_count = 0
         self.seed = int(seed)
+        self.sequential_heads = True
         cf = 0
         self.sa = []
         for m in model.sa_modules:
@@ -212,8 +213,11 @@ class TrainEngine:
         return (self.seed * 1000003 + self.step_count * 7919 + k * 104729 + 1) & 0x7FFFFFFF
 
     # ------------------------------------------------------------------ forward
-    def forward(self, points):
-        """points (B,3,N) fp32 CUDA -> predictions (fp32, autograd leaves underneath) ; keeps what backward needs."""
+    PRED_KEYS = ("score", "frame_R", "frame_t", "movable_logits")
+    LOSS_KEYS = ("cls_loss", "R_loss", "t_loss", "mov_loss")  # PointNet2Loss: term k depends on head k only
+
+    def _trunk_forward(self, points):
+        """set abstraction + feature propagation: points (B,3,N) fp32 -> per-point features [B*N, C] bf16"""
         cfg = self.cfg
         E = FusedPointNet2
         xyz = points.float().contiguous()
@@ -252,36 +256,69 @@ class TrainEngine:
             for blk in blocks:
                 h = blk.forward(h)
             sparse_xyz, sparse = dense_xyz, h
-        n = sparse_xyz.shape[2]
         self._lv_shapes = [None if f is None else tuple(f.shape) for f in lv_feat]
-        self._point_feat_shape = tuple(sparse.shape)
-        outs, self._head_leaves = [], []
-        for k, (blocks, logit) in enumerate(self.heads):
-            h = sparse
-            for j, blk in enumerate(blocks):
-                h = blk.forward(h, seed=self._seed(10 * k + j))
-            leaf = h.float().requires_grad_(True)  # the biased 1x1 conv + loss run in torch: autograd returns d/d(leaf)
-            wl = logit.weight.reshape(logit.weight.shape[0], -1)
-            o = torch.addmm(logit.bias, leaf, wl.t()).reshape(B, n, -1).permute(0, 2, 1)
-            outs.append(o)
-            self._head_leaves.append(leaf)
-        return {"score": outs[0], "frame_R": outs[1], "frame_t": outs[2], "movable_logits": torch.sigmoid(outs[3])}
+        self._n_points = sparse_xyz.shape[2]
+        self._batch = B
+        return sparse
+
+    def _head_forward(self, k, point_feat):
+        """head k: 4 blocks + the biased 1x1 conv -> fp32 logits (B, c, N), an autograd LEAF (the loss runs in torch)"""
+        blocks, logit = self.heads[k]
+        h = point_feat
+        for j, blk in enumerate(blocks):
+            h = blk.forward(h, seed=self._seed(10 * k + j))
+        B, n = self._batch, self._n_points
+        c = logit.weight.shape[0]
+        w = logit.weight.detach().reshape(c, -1).contiguous()
+        out = torch.empty((B, c, n), dtype=torch.float32, device=h.device)
+        check(lib.s4g_train_head_logits_fwd(ptr(h), ptr(w), ptr(logit.bias), ptr(out), h.shape[0], h.shape[1], c, n,
+                                            stream_ptr(h.device)), "train_head_logits_fwd")
+        self._head_saved[k] = (h, w)
+        return out.requires_grad_(True)
+
+    def _head_backward(self, k, leaf):
+        """leaf.grad (B, c, N) -> gradients of head k's parameters; returns d(point features) [B*N, C] bf16"""
+        blocks, logit = self.heads[k]
+        h, w = self._head_saved.pop(k)
+        dl = leaf.grad
+        B, c, n = dl.shape
+        dz = torch.empty_like(h)
+        check(lib.s4g_train_head_logits_bwd(ptr(dl), ptr(w), ptr(dz), h.shape[0], h.shape[1], c, n, stream_ptr(h.device)),
+              "train_head_logits_bwd")
+        dl_rows = dl.permute(0, 2, 1).reshape(B * n, c)
+        _accumulate(logit.weight, torch.mm(dl_rows.t().to(BF16), h, out_dtype=torch.float32).reshape(logit.weight.shape))
+        _accumulate(logit.bias, dl_rows.sum(0))
+        for blk in reversed(blocks):
+            dz = blk.backward(dz)
+        return dz
+
+    def _predictions(self, leaves):
+        return {"score": leaves[0], "frame_R": leaves[1], "frame_t": leaves[2], "movable_logits": torch.sigmoid(leaves[3])}
+
+    def forward(self, points):
+        """points (B,3,N) fp32 CUDA -> predictions (fp32 (B, c, N) autograd leaves underneath); keeps what backward needs."""
+        self._head_saved = {}
+        self._point_feat = self._trunk_forward(points)
+        self._head_leaves = [self._head_forward(k, self._point_feat) for k in range(4)]
+        return self._predictions(self._head_leaves)
 
     # ------------------------------------------------------------------ backward
     def backward(self):
         """after ``total_loss.backward()`` filled the head leaves' gradients"""
-        dev = self._head_leaves[0].device
         d_point = None
-        for (blocks, _), leaf in zip(self.heads, self._head_leaves):
-            dz = leaf.grad.to(BF16)
-            for blk in reversed(blocks):
-                dz = blk.backward(dz)
+        for k, leaf in enumerate(self._head_leaves):
+            dz = self._head_backward(k, leaf)
             d_point = dz.float() if d_point is None else d_point.add_(dz)
-        self._head_leaves = None
+        self._head_leaves = self._point_feat = None
+        self._trunk_backward(d_point)
+
+    def _trunk_backward(self, d_point):
+        dev = d_point.device
         # gradient buffers of the level features (fp32: they receive scatter-adds), index = level
         lv_grad = [None if s is None else torch.zeros(s, dtype=torch.float32, device=dev) for s in self._lv_shapes]
         n_fp = len(self.fp)
         d_out = d_point.to(BF16)  # gradient of the current propagation level's OUTPUT rows
+        del d_point
         for i in reversed(range(n_fp)):
             dz = d_out
             for blk in reversed(self.fp[i]):
@@ -309,15 +346,45 @@ class TrainEngine:
                                                    stream_ptr(dev)), "train_group_rows_bwd")
         self._sa_ctx = self._fp_ctx = None
 
+    def _separable(self):
+        """PointNet2Loss's four terms depend on one head each (cls <- score, R <- frame_R, t <- frame_t, mov <-
+        movable_logits, reference :162-219): the heads can then run forward + loss term + backward ONE AFTER THE OTHER,
+        so only one head's activations are alive at a time (-13 GB at 32 scenes)."""
+        from .network_models.models.PointNet2_tcls import PointNet2Loss
+        return self.sequential_heads and type(self.loss_fn) is PointNet2Loss
+
     def step_loss(self, data_batch, labels):
         """forward + loss + full backward; returns the (detached) loss dict.  Gradients accumulate in param.grad."""
         self.step_count += 1
-        with torch.cuda.device(data_batch["scene_points"].device):
-            with torch.enable_grad():
-                preds = self.forward(data_batch["scene_points"])
-                losses = self.loss_fn(preds, labels)
-                total = sum(losses.values())
-                total.backward()
+        points = data_batch["scene_points"]
+        with torch.cuda.device(points.device):
+            if not self._separable():
+                with torch.enable_grad():
+                    preds = self.forward(points)
+                    losses = self.loss_fn(preds, labels)
+                    sum(losses.values()).backward()
+                with torch.no_grad():
+                    self.backward()
+                return {k: v.detach() for k, v in losses.items()}
+            self._head_saved = {}
             with torch.no_grad():
-                self.backward()
-        return {k: v.detach() for k, v in losses.items()}
+                point_feat = self._trunk_forward(points)
+            B, n = self._batch, self._n_points
+            zeros = [torch.zeros((B, logit.weight.shape[0], n), dtype=torch.float32, device=points.device)
+                     for _, logit in self.heads]
+            losses, d_point = {}, None
+            for k in range(4):
+                with torch.no_grad():
+                    leaf = self._head_forward(k, point_feat)
+                with torch.enable_grad():
+                    leaves = [leaf if j == k else zeros[j] for j in range(4)]
+                    term = self.loss_fn(self._predictions(leaves), labels)[self.LOSS_KEYS[k]]
+                    term.backward()
+                losses[self.LOSS_KEYS[k]] = term.detach()
+                with torch.no_grad():
+                    dz = self._head_backward(k, leaf)
+                    d_point = dz.float() if d_point is None else d_point.add_(dz)
+                del leaf, dz
+            with torch.no_grad():
+                self._trunk_backward(d_point)
+        return losses

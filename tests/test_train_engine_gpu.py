@@ -137,6 +137,48 @@ def test_dropout_mask_is_reproduced_in_backward():
     assert torch.isfinite(dx.float()).all()
 
 
+@pytest.mark.parametrize("k", [3, 9, 5])
+def test_head_logits_kernels(k):
+    from s4g_release_b200._lib import check, lib, ptr, stream_ptr
+    B, n, C = 3, 1000, 128
+    g = torch.Generator().manual_seed(k)
+    h = torch.randn(B * n, C, generator=g).cuda().to(BF)
+    w = (torch.randn(k, C, generator=g) / 11).cuda()
+    b = torch.randn(k, generator=g).cuda()
+    out = torch.empty((B, k, n), device="cuda")
+    check(lib.s4g_train_head_logits_fwd(ptr(h), ptr(w), ptr(b), ptr(out), B * n, C, k, n, stream_ptr(h.device)), "f")
+    want = (h.float() @ w.t() + b).reshape(B, n, k).permute(0, 2, 1)
+    assert torch.allclose(out, want, atol=1e-4, rtol=1e-5)
+    dl = torch.randn(B, k, n, generator=g).cuda()
+    dh = torch.empty_like(h)
+    check(lib.s4g_train_head_logits_bwd(ptr(dl), ptr(w), ptr(dh), B * n, C, k, n, stream_ptr(h.device)), "b")
+    want_dh = dl.permute(0, 2, 1).reshape(B * n, k) @ w
+    assert (dh.float() - want_dh).abs().max().item() <= 1e-2 * want_dh.abs().max().item()
+
+
+def test_sequential_heads_equal_the_joint_step():
+    """forward + loss term + backward head by head (one head's activations alive at a time) gives the gradients of the
+    joint step: PointNet2Loss's terms depend on one head each"""
+    from s4g_release_b200.network_models.models.PointNet2_tcls import PointNet2, PointNet2Loss
+    from s4g_release_b200.train import synthetic_labels
+    from s4g_release_b200.train_engine import TrainEngine
+    torch.manual_seed(0)
+    a = PointNet2(**SHALLOW).cuda().train()
+    b = PointNet2(**SHALLOW).cuda().train()
+    b.load_state_dict(a.state_dict())
+    pts = torch.rand(2, 3, 2048, generator=torch.Generator().manual_seed(1)).cuda()
+    labels = synthetic_labels(2, 2048, num_frame=500, first_seed=7, device="cuda")
+    ea, eb = TrainEngine(a, PointNet2Loss(neg_weight=0.5)), TrainEngine(b, PointNet2Loss(neg_weight=0.5))
+    ea.sequential_heads = False
+    la, lb = ea.step_loss({"scene_points": pts}, labels), eb.step_loss({"scene_points": pts}, labels)
+    for k in la:
+        assert torch.allclose(la[k], lb[k], rtol=1e-5, atol=1e-6), k
+    for (name, pa), (_, pb) in zip(a.named_parameters(), b.named_parameters()):
+        # (not bit-identical: the scatter-adds use atomics)
+        rel = (pa.grad - pb.grad).norm().item() / max(pa.grad.norm().item(), 1e-12)
+        assert rel <= 2e-2, (name, rel)
+
+
 def test_group_rows_and_scatter_backward():
     from s4g_release_b200._lib import check, lib, ptr, stream_ptr
     B, N, M, K, Cf = 2, 500, 60, 16, 32
