@@ -78,12 +78,16 @@ def import_reference_model(pn2_ext_module):
                "point_search", "interpolate_forward", "interpolate_backward"):
         setattr(shim, fn, getattr(pn2_ext_module, fn))
     sys.modules[PN2_EXT] = shim
-    import grasp_proposal.network_models.models.pointnet2_utils as pkg
-    pkg.pn2_ext = shim
-    fmod = sys.modules.get("grasp_proposal.network_models.models.pointnet2_utils.functions")
-    if fmod is not None:  # already imported with another extension: rebind the name its functions look up
-        fmod.pn2_ext = shim
-    from grasp_proposal.network_models.models.PointNet2_tcls import PointNet2
+    import contextlib
+    # (the reference prints "Please compile source files ..." to stdout when its optional dgcnn_ext is absent,
+    # functions/gather_knn.py:4-7 — keep stdout clean for callers that print one JSON line)
+    with contextlib.redirect_stdout(sys.stderr):
+        import grasp_proposal.network_models.models.pointnet2_utils as pkg
+        pkg.pn2_ext = shim
+        fmod = sys.modules.get("grasp_proposal.network_models.models.pointnet2_utils.functions")
+        if fmod is not None:  # already imported with another extension: rebind the name its functions look up
+            fmod.pn2_ext = shim
+        from grasp_proposal.network_models.models.PointNet2_tcls import PointNet2
     return PointNet2
 
 
