@@ -38,8 +38,11 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--scenes", type=int, default=4096, help="whole-job scene count (strong scaling over --gpus)")
-    ap.add_argument("--chunk", type=int, default=64)
-    ap.add_argument("--pool", type=int, default=64, help="distinct synthetic scenes per rank")
+    ap.add_argument("--chunk", type=int, default=74,
+                    help="scenes per chunk; 74 = 148 SMs / 2: the level-0 farthest point sampling runs one 2-CTA cluster per "
+                         "cloud, so 74 clouds fill the GPU where 64 leave 20 SMs idle for a quarter of the chunk "
+                         "(measured: 2 906 vs 2 572 scenes/s on the same box, profiles/r02/bench_large_chunk_ab.json)")
+    ap.add_argument("--pool", type=int, default=74, help="distinct synthetic scenes per rank")
     ap.add_argument("--num-selected", type=int, default=5)
     ap.add_argument("--nms", type=float, default=0.01, help="L1 translation de-duplication distance in m (0 = off)")
     ap.add_argument("--score-threshold", type=float, default=None)

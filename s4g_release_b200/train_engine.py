@@ -112,7 +112,9 @@ class Block:
         C = self.cout
         stat = torch.empty(4 * C, dtype=torch.float32, device=dev)  # [mean | rstd | scale | shift]
         track = bn.track_running_stats and bn.running_mean is not None
-        check(lib.s4g_train_bn_finalize(ptr(sums), P, C, ptr(bn.weight), ptr(bn.bias), bn.eps, bn.momentum,
+        # (momentum None = torch's cumulative moving average: 1 / number of batches seen so far)
+        momentum = bn.momentum if bn.momentum is not None else 1.0 / float(int(bn.num_batches_tracked) + 1) if track else 0.0
+        check(lib.s4g_train_bn_finalize(ptr(sums), P, C, ptr(bn.weight), ptr(bn.bias), bn.eps, momentum,
                                         ptr(bn.running_mean) if track else None, ptr(bn.running_var) if track else None,
                                         ptr(stat), stream_ptr(dev)), "train_bn_finalize")
         if track:

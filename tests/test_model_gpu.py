@@ -108,6 +108,20 @@ def test_host_out_streams_identical_predictions():
         assert torch.equal(got[k], ref[k]) and torch.equal(host[k], ref[k].cpu()), k
 
 
+def test_host_out_accepts_bf16_buffers():
+    """pinned result buffers in bf16: the streamed copies convert on the device (half the D2H bytes)"""
+    import bench
+    net = bench.seeded_model().cuda()
+    x = bench.synthetic_scenes(2, 1000)[:, :, :8192].contiguous().cuda()
+    with torch.no_grad():
+        ref = net({"scene_points": x})
+        host = {k: torch.empty(v.shape, dtype=torch.bfloat16).pin_memory() for k, v in ref.items()}
+        net({"scene_points": x}, host_out=host)
+        torch.cuda.synchronize()
+    for k in ref:
+        assert torch.equal(host[k], ref[k].to(torch.bfloat16).cpu()), k
+
+
 def test_side_stream_three_nn_is_bit_identical():
     """the 3-NN searches that run on a side stream beside the next level's sampling (engine.overlap_geometry) produce
     exactly the serial schedule's predictions, call after call"""
