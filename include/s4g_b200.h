@@ -136,6 +136,10 @@ int s4g_linear_tf32(const float* x, long long ldx, const float* w, long long ldw
  * Forward: A = layer input, B = conv weight [cout][cin].  Input gradient: A = dY, B = weight^T [cin][cout]. */
 int s4g_gemm_bf16(const void* a, long long lda, const void* b, long long ldb, void* c, long long ldc, long long P, int N,
                   int K, void* stream);
+/* A/B switch (measurements): 1 (default) = weight-stationary schedule where it applies (K <= 512 and enough row tiles: a
+ * CTA keeps one 128-column slice of B in shared memory for all its row tiles), 0 = always stream B.  Returns the
+ * previous setting.  Both schedules compute the same bits. */
+int s4g_gemm_bf16_set_weight_stationary(int on);
 /* the same GEMM with the BatchNorm batch statistics of its (bf16-rounded) result accumulated in the epilogue:
  * stats2n[0..N) = sum_r c[r][n], stats2n[N..2N) = sum_r c[r][n]^2 (fp64, zeroed here) — no extra pass over C. */
 int s4g_gemm_bf16_stats(const void* a, long long lda, const void* b, long long ldb, void* c, long long ldc, long long P, int N,
@@ -158,12 +162,13 @@ int s4g_train_bn_act_bf16(const void* y, const float* scale, const float* shift,
  * out [G][C] bf16, arg [G][C] uint8 = the row of the (first) maximum inside its group, kept for the backward. */
 int s4g_train_bn_act_maxpool_bf16(const void* y, const float* scale, const float* shift, void* out, uint8_t* arg,
                                   long long G, int K, int C, int relu, void* stream);
-/* BatchNorm backward, pass 1: sums2c[0..C) = sum_r g, sums2c[C..2C) = sum_r g * xhat, with g = dz * relu'(.) * dropout
- * mask and xhat = (y - mean) * rstd.  Upstream gradient: dz [P][C] (K = 0), or the pooled gradient [P/K][C] routed to
- * the arg-max row of each group (K > 0, arg from s4g_train_bn_act_maxpool_bf16). */
+/* BatchNorm backward, pass 1: sums2c[0..C) = sum_r g, sums2c[C..2C) = sum_r g * y, with g = dz * relu'(.) * dropout mask
+ * (s4g_train_bn_bwd_finalize turns the second into sum g * xhat = rstd * (sum g y - mean * sum g) in fp64).  Upstream
+ * gradient: dz [P][C] (K = 0), or the pooled gradient [P/K][C] routed to the arg-max row of each group (K > 0, arg from
+ * s4g_train_bn_act_maxpool_bf16). */
 int s4g_train_bn_bwd_reduce_bf16(const void* dz, const uint8_t* arg, int K, const void* y, const float* scale,
-                                 const float* shift, const float* mean, const float* rstd, long long P, int C, int relu,
-                                 unsigned seed, float drop_p, double* sums2c, void* stream);
+                                 const float* shift, long long P, int C, int relu, unsigned seed, float drop_p,
+                                 double* sums2c, void* stream);
 /* pass 2: dy = coef * (g - m1 - xhat * m2) with coef = gamma * rstd, m1 = mean(g), m2 = mean(g * xhat), handed in folded
  * per channel as dy = ka * g + kb * y + kc  (ka = coef, kb = -coef * rstd * m2, kc = coef * (rstd * m2 * mean - m1)). */
 int s4g_train_bn_bwd_apply_bf16(const void* dz, const uint8_t* arg, int K, const void* y, const float* scale,

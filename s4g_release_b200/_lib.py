@@ -60,13 +60,14 @@ _SIGNATURES = {
     "s4g_linear_tf32": ([_vp, ctypes.c_longlong, _vp, ctypes.c_longlong, _vp, _vp, ctypes.c_longlong, ctypes.c_longlong,
                          _i, _i, _i, _i, _vp], _i),
     "s4g_gemm_bf16": ([_vp, _ll, _vp, _ll, _vp, _ll, _ll, _i, _i, _vp], _i),
+    "s4g_gemm_bf16_set_weight_stationary": ([_i], _i),
     "s4g_gemm_bf16_stats": ([_vp, _ll, _vp, _ll, _vp, _ll, _ll, _i, _i, _vp, _vp], _i),
     "s4g_train_bn_finalize": ([_vp, _ll, _i, _vp, _vp, _f, _f, _vp, _vp, _vp, _vp], _i),
     "s4g_train_bn_bwd_finalize": ([_vp, _ll, _i, _vp, _vp, _vp, _vp, _vp, _vp], _i),
     "s4g_train_colstats_bf16": ([_vp, _ll, _ll, _i, _vp, _vp], _i),
     "s4g_train_bn_act_bf16": ([_vp, _vp, _vp, _vp, _ll, _i, _i, ctypes.c_uint, _f, _vp], _i),
     "s4g_train_bn_act_maxpool_bf16": ([_vp, _vp, _vp, _vp, _vp, _ll, _i, _i, _i, _vp], _i),
-    "s4g_train_bn_bwd_reduce_bf16": ([_vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _ll, _i, _i, ctypes.c_uint, _f, _vp, _vp], _i),
+    "s4g_train_bn_bwd_reduce_bf16": ([_vp, _vp, _i, _vp, _vp, _vp, _ll, _i, _i, ctypes.c_uint, _f, _vp, _vp], _i),
     "s4g_train_bn_bwd_apply_bf16": ([_vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _ll, _i, _i, ctypes.c_uint, _f, _vp, _vp], _i),
     "s4g_train_group_rows_bf16": ([_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp], _i),
     "s4g_train_group_rows_bwd": ([_vp, _ll, _vp, _i, _i, _i, _i, _i, _vp, _vp], _i),

@@ -17,6 +17,14 @@
 //     columns >= N are clipped by the tensor map) while the tensor pipe fills the next accumulator.  (First version:
 //     every thread stored its own row with 16-byte st.global — 32 half-filled sectors per warp instruction; the store
 //     path, not HBM, bounded the memory-bound layers: 25.8 ms of GEMM per training step against ~14 ms of traffic.)
+//
+// WS (weight-stationary, K <= 384: the slice must leave room for >= 5 A stages): a CTA keeps ONE n-tile for all its m-tiles and loads that [128][K] slice of B into
+// shared memory once; the ring then only carries A slabs (16 KB each, up to 6 in flight).  Without it every 128 x 128
+// tile re-reads its B slice from L2 — ncu on the 264 -> 256 layer of the second set-abstraction level (2.1 M rows):
+// 30 % of the DRAM peak, tensor pipe 22 %, stalls `long_scoreboard`, 6.3 TB/s of L2 -> SM traffic, i.e. L2-bound
+// (profiles/r02/ncu_training.txt).  Measured per launch (profiles/r02/train_kernels_v5.txt): 3 -> 128 layer on 10.5 M rows
+// 2.24 -> 0.80 ms, 264 -> 256 on 2.1 M rows 0.85 -> 0.46 ms; K = 512 layers got 20-30 % slower with only 3 A stages and stay
+// on the streaming schedule.
 #include <cuda.h>
 #include <cuda_bf16.h>
 
@@ -26,7 +34,9 @@ namespace s4g {
 namespace gemm {
 
 constexpr int kThreads = 192;
-constexpr int kStages = 5;
+constexpr int kStages = 5;                         // streaming mode: stages of A + B slabs (32 KB)
+constexpr int kMaxStagesA = 6;                     // weight-stationary mode: stages of A slabs (16 KB)
+constexpr int kMaxSlabsWS = 8;                     // K <= 512
 constexpr int kTile = 128;
 constexpr int kSlab = 64;                          // K elements per stage: 64 bf16 = 128 B
 constexpr int kOperandBytes = kTile * kSlab * 2;   // 16 KB
@@ -108,27 +118,42 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
 // the sums per CTA over all its tiles, one fp64 global atomic per column and CTA at the end.  Rows >= P and columns >= N
 // are zero-filled operands: they add nothing.  (A register-level shuffle butterfly was measured first: ~5 800 cycles per
 // tile for the 4 epilogue warps against ~2 800 cycles of HBM time.)
-template <bool STATS>
+template <bool STATS, bool WS>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
-                 const __grid_constant__ CUtensorMap map_c, int P, int N, int K, double* __restrict__ stats) {
+                 const __grid_constant__ CUtensorMap map_c, int P, int N, int K, int stages_a, double* __restrict__ stats) {
   extern __shared__ uint8_t smem_raw[];
-  __shared__ __align__(8) uint64_t full[kStages], empty[kStages], acc_full[2], acc_empty[2];
+  __shared__ __align__(8) uint64_t full[kMaxStagesA], empty[kMaxStagesA], acc_full[2], acc_empty[2], w_full;
   __shared__ uint32_t tmem_slot;
-  uint8_t* ring = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);  // swizzle atoms are 1024-byte aligned
-  uint8_t* staging = ring + (size_t)kStages * kStageBytes;                           // 1024-byte aligned like the ring
-  float* s_stat = reinterpret_cast<float*>(staging + kStagingBytes);                 // STATS: [2][tiles_n * 128]
-
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int tiles_n = (N + kTile - 1) / kTile;
-  const int n_tiles = ((P + kTile - 1) / kTile) * tiles_n;
+  const int tiles_m = (P + kTile - 1) / kTile;
   const int n_slabs = (K + kSlab - 1) / kSlab;
+  // shared memory: [WS: B slice, n_slabs x 16 KB][ring][staging 32 KB][STATS: 2 x tiles_n x 128 floats]
+  uint8_t* base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);  // swizzle atoms are 1024-byte aligned
+  uint8_t* wreg = base;
+  uint8_t* ring = base + (WS ? (size_t)n_slabs * kOperandBytes : 0);
+  const int n_stages = WS ? stages_a : kStages;
+  const int stage_bytes = WS ? kOperandBytes : kStageBytes;
+  uint8_t* staging = ring + (size_t)n_stages * stage_bytes;
+  float* s_stat = reinterpret_cast<float*>(staging + kStagingBytes);
+  // this CTA's tiles: streaming = every gridDim-th tile, n fastest; WS = one n-tile, every (gridDim / tiles_n)-th m-tile
+  const int per_n = WS ? (int)gridDim.x / tiles_n : 0;
+  const int my_n = WS ? (int)blockIdx.x % tiles_n : 0;
+  const int my_m0 = WS ? (int)blockIdx.x / tiles_n : 0;
+  const int n_my = WS ? (((int)blockIdx.x < per_n * tiles_n && my_m0 < tiles_m) ? (tiles_m - my_m0 + per_n - 1) / per_n : 0)
+                      : (((int)blockIdx.x < tiles_m * tiles_n) ? (tiles_m * tiles_n - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0);
+  auto tile_of = [&](int i, int& row0, int& col0) {
+    if (WS) { row0 = (my_m0 + i * per_n) * kTile; col0 = my_n * kTile; }
+    else { const int t = (int)blockIdx.x + i * (int)gridDim.x; row0 = (t / tiles_n) * kTile; col0 = (t % tiles_n) * kTile; }
+  };
 
   if constexpr (STATS) {
     for (int i = threadIdx.x; i < 2 * tiles_n * kTile; i += kThreads) s_stat[i] = 0.f;
   }
   if (threadIdx.x == 0) {
-    for (int s = 0; s < kStages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    for (int s = 0; s < kMaxStagesA; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    mbar_init(&w_full, 1);
     for (int a = 0; a < 2; ++a) { mbar_init(&acc_full[a], 1); mbar_init(&acc_empty[a], 4); }  // 4 epilogue warps
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -143,16 +168,21 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
   const uint32_t tmem = tmem_slot;
 
   if (warp == 0) {
-    if (elect_one()) {
+    if (elect_one() && n_my > 0) {
+      if (WS) {  // the CTA's B slice, once
+        mbar_expect_tx(&w_full, (unsigned)n_slabs * kOperandBytes);
+        for (int k = 0; k < n_slabs; ++k) tma_load_2d(wreg + (size_t)k * kOperandBytes, &map_b, k * kSlab, my_n * kTile, &w_full);
+      }
       unsigned g = 0;  // running slab index over all of this CTA's tiles
-      for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
-        const int row0 = (t / tiles_n) * kTile, col0 = (t % tiles_n) * kTile;
+      for (int i = 0; i < n_my; ++i) {
+        int row0, col0;
+        tile_of(i, row0, col0);
         for (int k = 0; k < n_slabs; ++k, ++g) {
-          const unsigned s = g % kStages, use = g / kStages;
+          const unsigned s = g % (unsigned)n_stages, use = g / (unsigned)n_stages;
           if (use > 0) mbar_wait(&empty[s], (use - 1) & 1u);
-          mbar_expect_tx(&full[s], kStageBytes);  // zero-filled out-of-range elements count as transferred bytes
-          tma_load_2d(ring + (size_t)s * kStageBytes, &map_a, k * kSlab, row0, &full[s]);
-          tma_load_2d(ring + (size_t)s * kStageBytes + kOperandBytes, &map_b, k * kSlab, col0, &full[s]);
+          mbar_expect_tx(&full[s], (unsigned)stage_bytes);  // zero-filled out-of-range elements count as transferred bytes
+          tma_load_2d(ring + (size_t)s * stage_bytes, &map_a, k * kSlab, row0, &full[s]);
+          if (!WS) tma_load_2d(ring + (size_t)s * stage_bytes + kOperandBytes, &map_b, k * kSlab, col0, &full[s]);
         }
       }
     }
@@ -161,19 +191,20 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(kTile >> 3) << 17) | ((uint32_t)(kTile >> 4) << 24);
     // shared-memory descriptor of a 128-byte-swizzled K-major tile: SBO = 1024 B (8 rows), version 1, layout 2; LBO unused
     const uint64_t desc_hi = (uint64_t)((1024u >> 4) | (1u << 14) | (2u << 29)) << 32;
-    unsigned g = 0, i = 0;
-    for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++i) {
-      const unsigned a = i & 1u, ause = i >> 1;
+    unsigned g = 0;
+    if (WS && n_my > 0) mbar_wait(&w_full, 0u);
+    for (int i = 0; i < n_my; ++i) {
+      const unsigned a = (unsigned)i & 1u, ause = (unsigned)i >> 1;
       if (ause > 0) mbar_wait(&acc_empty[a], (ause - 1) & 1u);  // the epilogue has drained this accumulator's previous tile
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const uint32_t d_addr = tmem + a * (uint32_t)kTile;
       for (int k = 0; k < n_slabs; ++k, ++g) {
-        const unsigned s = g % kStages;
-        mbar_wait(&full[s], (g / kStages) & 1u);
+        const unsigned s = g % (unsigned)n_stages;
+        mbar_wait(&full[s], (g / (unsigned)n_stages) & 1u);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         if (elect_one()) {
-          const uint32_t a16 = smem_u32(ring + (size_t)s * kStageBytes) >> 4;
-          const uint32_t b16 = a16 + (kOperandBytes >> 4);
+          const uint32_t a16 = smem_u32(ring + (size_t)s * stage_bytes) >> 4;
+          const uint32_t b16 = WS ? (smem_u32(wreg + (size_t)k * kOperandBytes) >> 4) : a16 + (kOperandBytes >> 4);
 #pragma unroll
           for (int j = 0; j < kSlab / 16; ++j)  // K = 16 per MMA = 32 B inside the 128-byte row: +2 in 16-byte units
             umma_bf16(d_addr, desc_hi | (uint64_t)((a16 + 2u * j) | (1u << 16)), desc_hi | (uint64_t)((b16 + 2u * j) | (1u << 16)),
@@ -188,11 +219,11 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     const int qd = warp & 3;  // the TMEM lane quadrant a warp may read is fixed by warp id % 4
     const int r = qd * 32 + lane;  // this thread's row of the tile (= TMEM lane)
     const bool issuer = (warp == 2 && lane == 0);
-    unsigned i = 0;
-    for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++i) {
-      const unsigned a = i & 1u;
-      const int row0 = (t / tiles_n) * kTile, col0 = (t % tiles_n) * kTile;
-      mbar_wait(&acc_full[a], (i >> 1) & 1u);
+    for (int i = 0; i < n_my; ++i) {
+      const unsigned a = (unsigned)i & 1u;
+      int row0, col0;
+      tile_of(i, row0, col0);
+      mbar_wait(&acc_full[a], ((unsigned)i >> 1) & 1u);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       // the previous tile's stores must have finished READING the staging tile before it is overwritten
       if (issuer) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
@@ -249,7 +280,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
   __syncthreads();
   if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(256u) : "memory");
   if constexpr (STATS) {
-    if ((int)blockIdx.x < n_tiles) {
+    if (n_my > 0) {
       for (int i = threadIdx.x; i < 2 * tiles_n * kTile; i += kThreads) {
         const int half = i / (tiles_n * kTile), col = i - half * tiles_n * kTile;
         if (col < N) atomicAdd(stats + (size_t)half * N + col, (double)s_stat[i]);
@@ -284,6 +315,14 @@ static int encode_bf16_map(CUtensorMap* map, const void* base, long long width, 
 }  // namespace gemm
 }  // namespace s4g
 
+static bool g_gemm_ws = true;
+// A/B switch for measurements: 0 = always stream B through the ring, 1 = weight-stationary where it applies (default).
+extern "C" int s4g_gemm_bf16_set_weight_stationary(int on) {
+  const int prev = g_gemm_ws ? 1 : 0;
+  g_gemm_ws = on != 0;
+  return prev;
+}
+
 static int gemm_launch(const void* a, long long lda, const void* b, long long ldb, void* c, long long ldc, long long P, int N,
                        int K, double* stats, void* stream) {
   using namespace s4g::gemm;
@@ -303,24 +342,41 @@ static int gemm_launch(const void* a, long long lda, const void* b, long long ld
   rc = encode_bf16_map(&mc, c, N, ldc, P);
   if (rc != S4G_OK) return rc;
   const int tiles_n = (N + kTile - 1) / kTile;
-  const size_t smem = kSmemBytes + (stats ? sizeof(float) * 2 * tiles_n * kTile : 0);
+  const long long tiles_m = (P + kTile - 1) / kTile;
+  const int n_slabs = (K + kSlab - 1) / kSlab;
+  const size_t stat_bytes = stats ? sizeof(float) * 2 * tiles_n * kTile : 0;
   constexpr int kMaxDynSmem = 220 * 1024;  // (the kernel also has a few hundred bytes of static shared memory)
+  // weight-stationary when the B slice fits beside >= 3 A stages and every CTA gets >= 2 m-tiles
+  const int sms = s4g::num_sms();
+  int stages_a = 0;
+  bool ws = false;
+  if (g_gemm_ws && n_slabs <= kMaxSlabsWS && tiles_n <= sms) {
+    const long long room = (long long)kMaxDynSmem - 1024 - kStagingBytes - (long long)stat_bytes - (long long)n_slabs * kOperandBytes;
+    stages_a = (int)(room / kOperandBytes);
+    if (stages_a > kMaxStagesA) stages_a = kMaxStagesA;
+    // (K = 512 leaves only 3 A stages beside its 128 KB slice: measured 20-30 % SLOWER than streaming; K <= 384 keeps >= 5)
+    ws = stages_a >= 5 && tiles_m >= 2LL * (sms / tiles_n);
+  }
+  const size_t smem = 1024 + kStagingBytes + stat_bytes +
+                      (ws ? (size_t)(n_slabs + stages_a) * kOperandBytes : (size_t)kStages * kStageBytes);
   S4G_CHECK_ARG(smem <= (size_t)kMaxDynSmem, "gemm_bf16: too many output columns for the fused statistics");
   static bool attr_set = false;
   if (!attr_set) {
-    S4G_CUDA(cudaFuncSetAttribute(gemm_bf16_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
-    S4G_CUDA(cudaFuncSetAttribute(gemm_bf16_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
+    S4G_CUDA(cudaFuncSetAttribute(gemm_bf16_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
+    S4G_CUDA(cudaFuncSetAttribute(gemm_bf16_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
+    S4G_CUDA(cudaFuncSetAttribute(gemm_bf16_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
+    S4G_CUDA(cudaFuncSetAttribute(gemm_bf16_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
     attr_set = true;
   }
-  const long long tiles = ((P + kTile - 1) / kTile) * tiles_n;
-  const int grid = (int)(tiles < s4g::num_sms() ? tiles : s4g::num_sms());
+  const long long tiles = tiles_m * tiles_n;
+  int grid = (int)(tiles < sms ? tiles : sms);
+  if (ws) grid = (sms / tiles_n) * tiles_n;  // every n-tile gets the same number of CTAs
   cudaStream_t st = (cudaStream_t)stream;
-  if (stats) {
-    S4G_CUDA(cudaMemsetAsync(stats, 0, sizeof(double) * 2 * N, st));
-    gemm_bf16_kernel<true><<<grid, kThreads, smem, st>>>(ma, mb, mc, (int)P, N, K, stats);
-  } else {
-    gemm_bf16_kernel<false><<<grid, kThreads, smem, st>>>(ma, mb, mc, (int)P, N, K, nullptr);
-  }
+  if (stats) S4G_CUDA(cudaMemsetAsync(stats, 0, sizeof(double) * 2 * N, st));
+  if (stats && ws) gemm_bf16_kernel<true, true><<<grid, kThreads, smem, st>>>(ma, mb, mc, (int)P, N, K, stages_a, stats);
+  else if (stats) gemm_bf16_kernel<true, false><<<grid, kThreads, smem, st>>>(ma, mb, mc, (int)P, N, K, 0, stats);
+  else if (ws) gemm_bf16_kernel<false, true><<<grid, kThreads, smem, st>>>(ma, mb, mc, (int)P, N, K, stages_a, nullptr);
+  else gemm_bf16_kernel<false, false><<<grid, kThreads, smem, st>>>(ma, mb, mc, (int)P, N, K, 0, nullptr);
   S4G_LAUNCH_CHECK("gemm_bf16");
   return S4G_OK;
 }

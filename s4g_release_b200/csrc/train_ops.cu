@@ -17,6 +17,7 @@
 // threads touch adjacent pieces.  Dropout is a counter-based hash of (seed, row, channel): the backward recomputes the
 // mask instead of storing it.
 #include <cuda_bf16.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -202,10 +203,13 @@ __device__ __forceinline__ F8 upstream_route(const UpRaw& r) {
   return d;
 }
 
-__global__ void __launch_bounds__(kStatThreads, 2)
+// sums = [sum_r g | sum_r g * y]; the caller turns the second into sum g * xhat = rstd * (sum g y - mean * sum g) in fp64
+// (keeps mean / rstd out of the loop: 16 registers less, a third block per SM)
+template <int U, int MINB>  // U rows in flight per thread, MINB resident blocks per SM
+__global__ void __launch_bounds__(kStatThreads, MINB)
 bn_bwd_reduce_kernel(Upstream up, const __nv_bfloat16* __restrict__ y, const float* __restrict__ scale,
-                     const float* __restrict__ shift, const float* __restrict__ mean, const float* __restrict__ rstd,
-                     long long P, int C, int relu, unsigned seed, unsigned thresh, float keep_scale, double* __restrict__ out) {
+                     const float* __restrict__ shift, long long P, int C, int relu, unsigned seed, unsigned thresh,
+                     float keep_scale, double* __restrict__ out) {
   extern __shared__ float s_part[];
   const int pieces = C >> 3;
   const int lanes = kStatThreads / pieces;
@@ -214,13 +218,12 @@ bn_bwd_reduce_kernel(Upstream up, const __nv_bfloat16* __restrict__ y, const flo
   const long long r1 = min(P, r0 + kStatRows);
   F8 s{}, q{};
   if (rl < lanes) {
-    const F8 a = load_f8(scale + piece * 8), b = load_f8(shift + piece * 8), mu = load_f8(mean + piece * 8),
-             rs = load_f8(rstd + piece * 8);
-    for (long long r = r0 + rl; r < r1; r += 4LL * lanes) {
-      uint4 raw[4];
-      UpRaw ur[4];
+    const F8 a = load_f8(scale + piece * 8), b = load_f8(shift + piece * 8);
+    for (long long r = r0 + rl; r < r1; r += (long long)U * lanes) {
+      uint4 raw[U];
+      UpRaw ur[U];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
+      for (int u = 0; u < U; ++u) {
         const long long rr = r + (long long)u * lanes;
         if (rr < r1) {
           raw[u] = __ldg(reinterpret_cast<const uint4*>(y + rr * C) + piece);
@@ -228,7 +231,7 @@ bn_bwd_reduce_kernel(Upstream up, const __nv_bfloat16* __restrict__ y, const flo
         }
       }
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
+      for (int u = 0; u < U; ++u) {
         const long long rr = r + (long long)u * lanes;
         if (rr >= r1) break;
         const F8 v = unpack8(raw[u]);
@@ -239,7 +242,7 @@ bn_bwd_reduce_kernel(Upstream up, const __nv_bfloat16* __restrict__ y, const flo
           if (relu && !(fmaf(v.v[e], a.v[e], b.v[e]) > 0.f)) g = 0.f;
           if (thresh) g = keep_elem(seed, rr, piece * 8 + e, C, thresh) ? g * keep_scale : 0.f;
           s.v[e] += g;
-          q.v[e] = fmaf(g, (v.v[e] - mu.v[e]) * rs.v[e], q.v[e]);
+          q.v[e] = fmaf(g, v.v[e], q.v[e]);
         }
       }
     }
@@ -401,17 +404,18 @@ __global__ void bn_finalize_kernel(const double* __restrict__ sums, long long P,
     run_var[c] = (1.f - momentum) * run_var[c] + momentum * (float)(var * ((double)P / (double)(P > 1 ? P - 1 : 1)));
   }
 }
-// backward: sums = [sum g | sum g * xhat] -> dgamma += sum g xhat, dbeta += sum g, and the folded coefficients of
+// backward: sums = [sum g | sum g * y] (bn_bwd_reduce) -> dgamma += sum g xhat, dbeta += sum g, and the folded coefficients of
 // dy = ka * g + kb * y + kc.  out3c = [ka | kb | kc].
 __global__ void bn_bwd_finalize_kernel(const double* __restrict__ sums, long long P, int C, const float* __restrict__ gamma,
                                        const float* __restrict__ mean_rstd, float* __restrict__ dgamma,
                                        float* __restrict__ dbeta, float* __restrict__ out3c) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
-  const float sg = (float)sums[c], sgx = (float)sums[C + c];
   const float mean = mean_rstd[c], rstd = mean_rstd[C + c];
+  const double sgx_d = (double)rstd * (sums[C + c] - (double)mean * sums[c]);  // sum g * xhat from [sum g | sum g * y]
+  const float sg = (float)sums[c], sgx = (float)sgx_d;
   const float ka = gamma[c] * rstd;
-  const float m1 = (float)(sums[c] / (double)P), m2 = (float)(sums[C + c] / (double)P);
+  const float m1 = (float)(sums[c] / (double)P), m2 = (float)(sgx_d / (double)P);
   out3c[c] = ka;
   out3c[C + c] = -ka * rstd * m2;
   out3c[2 * C + c] = ka * (rstd * m2 * mean - m1);
@@ -529,9 +533,9 @@ extern "C" int s4g_train_bn_act_maxpool_bf16(const void* y, const float* scale, 
 
 // upstream gradient: dz [P][C] when K == 0; pooled dz [P/K][C] + arg-max [P/K][C] when K > 0
 extern "C" int s4g_train_bn_bwd_reduce_bf16(const void* dz, const uint8_t* arg, int K, const void* y, const float* scale,
-                                            const float* shift, const float* mean, const float* rstd, long long P, int C,
-                                            int relu, unsigned seed, float drop_p, double* sums2c, void* stream) {
-  S4G_CHECK_ARG(dz && y && scale && shift && mean && rstd && sums2c && P > 0 && (K == 0 || (arg && P % K == 0)),
+                                            const float* shift, long long P, int C, int relu, unsigned seed, float drop_p,
+                                            double* sums2c, void* stream) {
+  S4G_CHECK_ARG(dz && y && scale && shift && sums2c && P > 0 && (K == 0 || (arg && P % K == 0)),
                 "train_bn_bwd_reduce: bad arguments");
   TRN_CHECK_C(C);
   cudaStream_t s = (cudaStream_t)stream;
@@ -540,8 +544,15 @@ extern "C" int s4g_train_bn_bwd_reduce_bf16(const void* dz, const uint8_t* arg, 
   S4G_CHECK_ARG(lanes >= 1, "train_bn_bwd_reduce: too many channels");
   const unsigned thresh = drop_p > 0.f ? (unsigned)((double)drop_p * 4294967296.0) : 0u;
   const Upstream up{reinterpret_cast<const bf16*>(dz), arg, K};
-  bn_bwd_reduce_kernel<<<grid_for(P, kStatRows), kStatThreads, (size_t)lanes * pieces * 16 * sizeof(float), s>>>(
-      up, reinterpret_cast<const bf16*>(y), scale, shift, mean, rstd, P, C, relu, seed, thresh, 1.f / (1.f - drop_p), sums2c);
+  static int variant = -1;  // S4G_BWD_REDUCE_VARIANT=1: 2 rows in flight x 3 blocks per SM instead of 4 x 2 (A/B measurements)
+  if (variant < 0) { const char* e = getenv("S4G_BWD_REDUCE_VARIANT"); variant = e ? atoi(e) : 0; }
+  const size_t sm = (size_t)lanes * pieces * 16 * sizeof(float);
+  if (variant == 1)
+    bn_bwd_reduce_kernel<2, 3><<<grid_for(P, kStatRows), kStatThreads, sm, s>>>(
+        up, reinterpret_cast<const bf16*>(y), scale, shift, P, C, relu, seed, thresh, 1.f / (1.f - drop_p), sums2c);
+  else
+    bn_bwd_reduce_kernel<4, 2><<<grid_for(P, kStatRows), kStatThreads, sm, s>>>(
+        up, reinterpret_cast<const bf16*>(y), scale, shift, P, C, relu, seed, thresh, 1.f / (1.f - drop_p), sums2c);
   S4G_LAUNCH_CHECK("train_bn_bwd_reduce");
   return S4G_OK;
 }

@@ -24,7 +24,6 @@ Activations are bf16, so this is the numerical regime of bf16 autocast training,
 (tests/test_train_engine_gpu.py) states the tolerance.  There is no CPU path.
 """
 import torch
-import torch.nn.functional as F
 
 from ._lib import check, lib, ptr, stream_ptr
 from .engine import FusedPointNet2
@@ -145,8 +144,7 @@ class Block:
         sums = torch.empty(2 * C, dtype=torch.float64, device=dev)
         drop = 0.0 if pool_k else self.drop_p
         check(lib.s4g_train_bn_bwd_reduce_bf16(ptr(dz), ptr(arg) if pool_k else None, pool_k, ptr(y), ptr(scale), ptr(shift),
-                                               ptr(mean_rstd), ptr(mean_rstd[C:]), P, C, 1, seed, drop, ptr(sums),
-                                               stream_ptr(dev)), "train_bn_bwd_reduce")
+                                               P, C, 1, seed, drop, ptr(sums), stream_ptr(dev)), "train_bn_bwd_reduce")
         # dgamma += sum g xhat, dbeta += sum g, and dy = ka * g + kb * y + kc folded per channel — one launch
         gw, gb = _grad_buffer(self.bn.weight), _grad_buffer(self.bn.bias)
         coef = torch.empty(3 * C, dtype=torch.float32, device=dev)

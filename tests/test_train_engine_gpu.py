@@ -49,6 +49,31 @@ def test_gemm_bf16_fused_statistics(P, N, K):
     np.testing.assert_allclose(sums[N:].cpu().numpy(), q.cpu().numpy(), rtol=1e-4, atol=2e-2)
 
 
+@pytest.mark.parametrize("P,N,K", [(148 * 2 * 128 + 77, 128, 128), (148 * 128 + 5, 256, 264), (60000, 512, 512),
+                                   (148 * 3 * 128, 128, 8), (50000, 384, 520)])
+def test_gemm_weight_stationary_schedule_is_bit_identical(P, N, K):
+    """the weight-stationary schedule (B slice resident in shared memory, K <= 512) and the streaming schedule issue the
+    same MMAs in the same order per tile: identical bits, identical fused statistics up to summation order"""
+    from s4g_release_b200._lib import lib
+    from s4g_release_b200.train_engine import gemm
+    g = torch.Generator().manual_seed(P % 1000 + N + K)
+    a = torch.randn(P, K, generator=g).cuda().to(BF)
+    b = (torch.randn(N, K, generator=g) / np.sqrt(K)).cuda().to(BF)
+    prev = lib.s4g_gemm_bf16_set_weight_stationary(0)
+    try:
+        c0, s0 = gemm(a, b, stats=True)
+        lib.s4g_gemm_bf16_set_weight_stationary(1)
+        c1, s1 = gemm(a, b, stats=True)
+        c2 = gemm(a, b)
+    finally:
+        lib.s4g_gemm_bf16_set_weight_stationary(prev)
+    torch.cuda.synchronize()
+    assert torch.equal(c0, c1) and torch.equal(c0, c2)
+    np.testing.assert_allclose(s0.cpu().numpy(), s1.cpu().numpy(), rtol=1e-5, atol=1e-2)
+    want = a.double() @ b.double().t()
+    assert (c1.double() - want).abs().max().item() <= 1e-2 * max(1.0, want.abs().max().item())
+
+
 def test_gemm_bf16_strided_operands():
     """A with a row stride larger than K (a column slice of a wider matrix), B^T made contiguous by the caller"""
     from s4g_release_b200.train_engine import gemm
