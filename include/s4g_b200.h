@@ -76,6 +76,9 @@ int s4g_ball_grid_free(s4g_ball_grid* grid, void* stream);
  * fwd: input (B,C,N), index (B,M,K) -> out (B,C,M,K).   bwd: grad_out (B,C,M,K) -> grad_in (B,C,N). */
 int s4g_group_points_forward_f32(const float* input, const int64_t* index, int B, int C, int N, int M, int K,
                                  float* out, void* stream);
+/* A/B switch (measurements): 1 (default) = the forward stages channel planes in shared memory with bulk copies when they
+ * fit (gathers from shared memory, all global traffic coalesced), 0 = always the plain gather.  Same results. */
+int s4g_group_points_set_staged(int on);
 int s4g_group_points_backward_f32(const float* grad_out, const int64_t* index, int B, int C, int N, int M, int K,
                                   float* grad_in, void* stream);
 

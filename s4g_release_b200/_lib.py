@@ -40,6 +40,7 @@ _SIGNATURES = {
     "s4g_ball_grid_build_f32": ([_vp, _i, _i, _f, _vp], _vp),
     "s4g_ball_query_with_grid_f32_i32": ([_vp, _vp, _vp, _i, _i, _vp, _vp, _vp], _i),
     "s4g_ball_grid_free": ([_vp, _vp], _i),
+    "s4g_group_points_set_staged": ([_i], _i),
     "s4g_group_points_forward_f32": ([_vp, _vp, _i, _i, _i, _i, _i, _vp, _vp], _i),
     "s4g_group_points_backward_f32": ([_vp, _vp, _i, _i, _i, _i, _i, _vp, _vp], _i),
     "s4g_point_search_f32": ([_vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp], _i),

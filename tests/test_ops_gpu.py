@@ -312,3 +312,23 @@ def test_gather_points_kernel_equals_torch_gather(ext, B, C, N, M):
     out = F_.gather_points(p2, idx)
     out.sum().backward()
     assert torch.equal(out, want) and p2.grad is not None
+
+
+@pytest.mark.parametrize("B,C,N,M,K", [(8, 3, 16384, 2048, 32), (4, 40, 5120, 1024, 64), (16, 256, 5120, 1024, 64), (3, 67, 1000, 4096, 8),
+                                       (8, 512, 1024, 256, 64), (2, 35, 16386, 2048, 32)])
+def test_group_points_forward_staged_equals_plain(ext, B, C, N, M, K):
+    """the shared-memory-staged forward (bulk-copied channel planes, gathers from shared memory) and the plain gather kernel
+    produce identical tensors (= torch.gather); N % 4 != 0 falls back to the plain kernel"""
+    from s4g_release_b200._lib import lib
+    g = torch.Generator().manual_seed(N + M)
+    x = torch.randn(B, C, N, generator=g).cuda()
+    idx = torch.randint(0, N, (B, M, K), generator=g).cuda()
+    prev = lib.s4g_group_points_set_staged(0)
+    try:
+        plain = ext.group_points_forward(x, idx)
+        lib.s4g_group_points_set_staged(1)
+        staged = ext.group_points_forward(x, idx)
+    finally:
+        lib.s4g_group_points_set_staged(prev)
+    want = torch.gather(x.unsqueeze(2).expand(-1, -1, M, -1), 3, idx.unsqueeze(1).expand(-1, C, -1, -1))
+    assert torch.equal(plain, want) and torch.equal(staged, want)
