@@ -40,6 +40,9 @@ def main():
     ap.add_argument("--precision", default="tf32", choices=["tf32", "fp32"],
                     help="tf32 = torch's default for cuDNN convolutions, i.e. what the unmodified reference runs on this "
                          "GPU (SURVEY.md §8a6); fp32 = IEEE")
+    ap.add_argument("--fused-bwd-reduce", action="store_true", help="A/B: BatchNorm-backward sums in the dX GEMM's epilogue")
+    ap.add_argument("--no-sparse-pool-reduce", action="store_true", help="A/B: pooled blocks reduce over all G*K rows")
+    ap.add_argument("--epilogue-groups", type=int, default=0, choices=[0, 1, 2], help="A/B: GEMM epilogue warp groups")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
 
@@ -61,6 +64,11 @@ def main():
     torch.backends.cuda.matmul.allow_tf32 = args.precision == "tf32"
     torch.backends.cudnn.benchmark = True
 
+    from s4g_release_b200 import train_engine
+    train_engine.FUSED_BWD_REDUCE = args.fused_bwd_reduce
+    train_engine.SPARSE_POOL_REDUCE = not args.no_sparse_pool_reduce
+    if args.epilogue_groups:
+        _lib.lib.s4g_gemm_bf16_set_epilogue_groups(args.epilogue_groups)
     B = args.batch
     torch.manual_seed(0)
     model = PointNet2(**PN2_CLS_CONFIG).to(dev)

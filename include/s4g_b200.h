@@ -143,6 +143,18 @@ int s4g_gemm_bf16(const void* a, long long lda, const void* b, long long ldb, vo
  * CTA keeps one 128-column slice of B in shared memory for all its row tiles), 0 = always stream B.  Returns the
  * previous setting.  Both schedules compute the same bits. */
 int s4g_gemm_bf16_set_weight_stationary(int on);
+/* A/B switch (measurements): number of epilogue warp groups, 1 or 2 (one group per TMEM accumulator / tile parity, a
+ * staging tile each), 0 (default) = chosen per launch (2 when K <= 128).  Returns the previous setting.  Same bits. */
+int s4g_gemm_bf16_set_epilogue_groups(int groups);
+/* Input-gradient GEMM whose RESULT is the upstream gradient of the block that produced y_prev (its rows [P][N] before
+ * BatchNorm; scale / shift = its folded BatchNorm; relu / seed / drop_p = its activation and dropout):
+ *   c = (a · b^T) * relu'(y_prev * scale + shift) * dropout mask     (stored MASKED, bf16)
+ *   sums2n[0..N) = sum_r c[r][n],  sums2n[N..2N) = sum_r c[r][n] * y_prev[r][n]   (fp64, zeroed here)
+ * i.e. s4g_train_bn_bwd_reduce_bf16 of that block done in this GEMM's epilogue (no pass over c and y_prev); hand c to
+ * s4g_train_bn_bwd_apply_bf16 with relu = 0, drop_p = 0.  (reference: the autograd backward of conv.py:30-36,70-76.) */
+int s4g_gemm_bf16_bwd(const void* a, long long lda, const void* b, long long ldb, void* c, long long ldc, long long P, int N,
+                      int K, const void* y_prev, long long ldy, const float* scale, const float* shift, int relu,
+                      unsigned seed, float drop_p, double* sums2n, void* stream);
 /* the same GEMM with the BatchNorm batch statistics of its (bf16-rounded) result accumulated in the epilogue:
  * stats2n[0..N) = sum_r c[r][n], stats2n[N..2N) = sum_r c[r][n]^2 (fp64, zeroed here) — no extra pass over C. */
 int s4g_gemm_bf16_stats(const void* a, long long lda, const void* b, long long ldb, void* c, long long ldc, long long P, int N,
@@ -162,9 +174,11 @@ int s4g_train_colstats_bf16(const void* y, long long ld, long long P, int C, dou
 int s4g_train_bn_act_bf16(const void* y, const float* scale, const float* shift, void* z, long long P, int C, int relu,
                           unsigned seed, float drop_p, void* stream);
 /* the same followed by torch.max over each group of K consecutive rows (pointnet2_utils/modules.py:243):
- * out [G][C] bf16, arg [G][C] uint8 = the row of the (first) maximum inside its group, kept for the backward. */
+ * out [G][C] bf16, arg [G][C] uint8 = the row of the (first) maximum inside its group, kept for the backward; ymax
+ * (may be NULL) [G][C] bf16 = y at that row: the backward's reduce of a pooled block only needs these G rows (the
+ * gradient is zero everywhere else) — s4g_train_bn_bwd_reduce_bf16(dz_pooled, NULL, 0, ymax, ..., G, ...). */
 int s4g_train_bn_act_maxpool_bf16(const void* y, const float* scale, const float* shift, void* out, uint8_t* arg,
-                                  long long G, int K, int C, int relu, void* stream);
+                                  void* ymax, long long G, int K, int C, int relu, void* stream);
 /* BatchNorm backward, pass 1: sums2c[0..C) = sum_r g, sums2c[C..2C) = sum_r g * y, with g = dz * relu'(.) * dropout mask
  * (s4g_train_bn_bwd_finalize turns the second into sum g * xhat = rstd * (sum g y - mean * sum g) in fp64).  Upstream
  * gradient: dz [P][C] (K = 0), or the pooled gradient [P/K][C] routed to the arg-max row of each group (K > 0, arg from
@@ -197,6 +211,13 @@ int s4g_train_head_logits_fwd(const void* h, const float* w, const float* bias, 
                               int n_points, void* stream);
 int s4g_train_head_logits_bwd(const float* dlogits, const float* w, void* dh, long long P, int C, int k, int n_points,
                               void* stream);
+/* ... and its parameter gradients: dw[j][c] += sum_rows dlogits[b][j][n] * h[row][c], dbias[j] += sum_rows dlogits[b][j][n]
+ * (fp32 atomics INTO dw [k][C] / dbias [k]: the caller's param.grad buffers). */
+int s4g_train_head_logits_dw(const float* dlogits, const void* h, float* dw, float* dbias, long long P, int C, int k,
+                             int n_points, void* stream);
+/* out = a + b (+ c) (+ d): bf16 vectors of n elements (n % 8 == 0) summed in fp32 and rounded once — the sum of the four
+ * heads' gradients w.r.t. the shared per-point features (autograd's accumulation at PointNet2_tcls.py:131-141). */
+int s4g_train_sum_bf16(const void* a, const void* b, const void* c, const void* d, void* out, long long n, void* stream);
 
 /* ---- fused inference path (channel-last bf16 features, int32 indices) ---------------------- */
 

@@ -62,12 +62,14 @@ _SIGNATURES = {
                          _i, _i, _i, _i, _vp], _i),
     "s4g_gemm_bf16": ([_vp, _ll, _vp, _ll, _vp, _ll, _ll, _i, _i, _vp], _i),
     "s4g_gemm_bf16_set_weight_stationary": ([_i], _i),
+    "s4g_gemm_bf16_set_epilogue_groups": ([_i], _i),
+    "s4g_gemm_bf16_bwd": ([_vp, _ll, _vp, _ll, _vp, _ll, _ll, _i, _i, _vp, _ll, _vp, _vp, _i, ctypes.c_uint, _f, _vp, _vp], _i),
     "s4g_gemm_bf16_stats": ([_vp, _ll, _vp, _ll, _vp, _ll, _ll, _i, _i, _vp, _vp], _i),
     "s4g_train_bn_finalize": ([_vp, _ll, _i, _vp, _vp, _f, _f, _vp, _vp, _vp, _vp], _i),
     "s4g_train_bn_bwd_finalize": ([_vp, _ll, _i, _vp, _vp, _vp, _vp, _vp, _vp], _i),
     "s4g_train_colstats_bf16": ([_vp, _ll, _ll, _i, _vp, _vp], _i),
     "s4g_train_bn_act_bf16": ([_vp, _vp, _vp, _vp, _ll, _i, _i, ctypes.c_uint, _f, _vp], _i),
-    "s4g_train_bn_act_maxpool_bf16": ([_vp, _vp, _vp, _vp, _vp, _ll, _i, _i, _i, _vp], _i),
+    "s4g_train_bn_act_maxpool_bf16": ([_vp, _vp, _vp, _vp, _vp, _vp, _ll, _i, _i, _i, _vp], _i),
     "s4g_train_bn_bwd_reduce_bf16": ([_vp, _vp, _i, _vp, _vp, _vp, _ll, _i, _i, ctypes.c_uint, _f, _vp, _vp], _i),
     "s4g_train_bn_bwd_apply_bf16": ([_vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _ll, _i, _i, ctypes.c_uint, _f, _vp, _vp], _i),
     "s4g_train_group_rows_bf16": ([_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp], _i),
@@ -76,6 +78,8 @@ _SIGNATURES = {
     "s4g_train_f32_to_bf16": ([_vp, _vp, _ll, _vp], _i),
     "s4g_train_head_logits_fwd": ([_vp, _vp, _vp, _vp, _ll, _i, _i, _i, _vp], _i),
     "s4g_train_head_logits_bwd": ([_vp, _vp, _vp, _ll, _i, _i, _i, _vp], _i),
+    "s4g_train_head_logits_dw": ([_vp, _vp, _vp, _vp, _ll, _i, _i, _i, _vp], _i),
+    "s4g_train_sum_bf16": ([_vp, _vp, _vp, _vp, _vp, _ll, _vp], _i),
     "s4g_chain_create": ([_i, _ip, _ip, _ip, _i, _i, _i, _i, _i, _i], _vp),
     "s4g_chain_create_slots": ([_i, _ip, _ip, _ip, _i, _i, _i, _i, _i, _i, _i], _vp),
     "s4g_chain_create_tuned": ([_i, _ip, _ip, _ip, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i], _vp),

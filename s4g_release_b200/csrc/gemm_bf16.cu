@@ -18,6 +18,22 @@
 //     every thread stored its own row with 16-byte st.global — 32 half-filled sectors per warp instruction; the store
 //     path, not HBM, bounded the memory-bound layers: 25.8 ms of GEMM per training step against ~14 ms of traffic.)
 //
+//   * the epilogue comes in TWO groups of 4 warps (tile parity = accumulator = group, one staging tile each): with one
+//     group every layer of this model ran at the epilogue's pace — ncu (profiles/r02/ncu_training.txt): 128 -> 128 and
+//     128 -> 256 on 10.5 M rows both at 34.3 % issue-active and ~3 000 cycles per tile, i.e. 75 % resp. 58 % of the DRAM
+//     peak although the tile's traffic differs by 1.35 x.
+//
+// BWD (input-gradient GEMM of block l, dX = dY W): the output tile IS the upstream gradient of block l-1, so the epilogue
+// also does what the first pass of that block's BatchNorm backward would do: the producer warp fetches the matching
+// 128 x 128 tile of block l-1's pre-activations y into shared memory (TMA, same swizzle as the staging tile); after the
+// accumulator is staged, the epilogue threads walk the tile COLUMN-wise (2 columns x 64 rows per thread, conflict-free),
+// mask the staged gradient with ReLU' / dropout of block l-1 in place, and accumulate sum g and sum g*y per column;
+// the MASKED tile goes out through the TMA store — s4g_train_bn_bwd_reduce never runs for a block whose gradient comes
+// out of a GEMM.  One epilogue group, two y tiles (so that the producer can run two tiles ahead).  First version, measured and replaced (profiles/r02/
+// gemm_layers_v1.txt): every thread read its own ROW of y from global memory and the column sums were a register
+// transpose-reduce over the warp (31 shuffles per 32 columns and quantity) — ~2 300 instructions per thread and tile,
+// 2.6 ms for the 128 -> 128 layer on 10.5 M rows against 0.87 ms for the plain GEMM + 0.9 ms for the separate pass.
+//
 // WS (weight-stationary, K <= 384: the slice must leave room for >= 5 A stages): a CTA keeps ONE n-tile for all its m-tiles and loads that [128][K] slice of B into
 // shared memory once; the ring then only carries A slabs (16 KB each, up to 6 in flight).  Without it every 128 x 128
 // tile re-reads its B slice from L2 — ncu on the 264 -> 256 layer of the second set-abstraction level (2.1 M rows):
@@ -33,8 +49,8 @@
 namespace s4g {
 namespace gemm {
 
-constexpr int kThreads = 192;
-constexpr int kStages = 5;                         // streaming mode: stages of A + B slabs (32 KB)
+constexpr int kMaxThreads = 64 + 2 * 128;         // producer warp, MMA warp, 1 or 2 epilogue groups of 4 warps
+constexpr int kStages = 5;                         // streaming mode: at most this many stages of A + B slabs (32 KB)
 constexpr int kMaxStagesA = 6;                     // weight-stationary mode: stages of A slabs (16 KB)
 constexpr int kMaxSlabsWS = 8;                     // K <= 512
 constexpr int kTile = 128;
@@ -42,7 +58,6 @@ constexpr int kSlab = 64;                          // K elements per stage: 64 b
 constexpr int kOperandBytes = kTile * kSlab * 2;   // 16 KB
 constexpr int kStageBytes = 2 * kOperandBytes;
 constexpr int kStagingBytes = kTile * kTile * 2;    // 32 KB: the bf16 output tile as two {64 columns, 128 rows} swizzled halves
-constexpr int kSmemBytes = kStages * kStageBytes + kStagingBytes + 1024;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t* bar, unsigned count) {
@@ -106,7 +121,7 @@ __device__ __forceinline__ void tma_store_2d(const void* map, const void* src, i
   asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(map), "r"(smem_u32(src)),
                "r"(c0), "r"(c1) : "memory");
 }
-__device__ __forceinline__ void epi_barrier() { asm volatile("bar.sync 1, 128;" ::: "memory"); }  // the 4 epilogue warps
+__device__ __forceinline__ void epi_barrier(int id) { asm volatile("bar.sync %0, 128;" ::"r"(id) : "memory"); }  // one group
 __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
   __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
   return *reinterpret_cast<uint32_t*>(&h);
@@ -118,25 +133,48 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
 // the sums per CTA over all its tiles, one fp64 global atomic per column and CTA at the end.  Rows >= P and columns >= N
 // are zero-filled operands: they add nothing.  (A register-level shuffle butterfly was measured first: ~5 800 cycles per
 // tile for the 4 epilogue warps against ~2 800 cycles of HBM time.)
-template <bool STATS, bool WS>
-__global__ void __launch_bounds__(kThreads, 1)
+// what the BWD epilogue needs of block l-1 (the block whose output this GEMM's result is the gradient of)
+struct BwdEpilogue {
+  const __nv_bfloat16* y;   // its pre-BatchNorm rows [P][N], leading dimension ldy
+  long long ldy;
+  const float* scale;       // its folded BatchNorm scale / shift [N]
+  const float* shift;
+  int relu;
+  unsigned seed, thresh;    // its dropout (thresh 0 = none): same counter hash as csrc/train_ops.cu
+  float keep_scale;
+};
+__device__ __forceinline__ bool keep_elem(unsigned seed, long long row, int ch, int C, unsigned thresh) {
+  unsigned long long idx = (unsigned long long)row * (unsigned)C + (unsigned)ch;
+  unsigned h = (unsigned)idx ^ (unsigned)(idx >> 32) * 0x9E3779B9u ^ seed;
+  h ^= h >> 16; h *= 0x85EBCA6Bu; h ^= h >> 13; h *= 0xC2B2AE35u; h ^= h >> 16;
+  return h >= thresh;
+}
+
+constexpr int kPlain = 0, kStats = 1, kBwd = 2;
+
+template <int MODE, bool WS>
+__global__ void __launch_bounds__(kMaxThreads, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
-                 const __grid_constant__ CUtensorMap map_c, int P, int N, int K, int stages_a, double* __restrict__ stats) {
+                 const __grid_constant__ CUtensorMap map_c, const __grid_constant__ CUtensorMap map_y, int P, int N, int K,
+                 int n_stages, int groups, double* __restrict__ stats, const BwdEpilogue bw) {
+  constexpr bool STATS = MODE != kPlain;  // per-column sums collected in shared memory, fp64 global atomics at the end
+  const int kThreads = (int)blockDim.x;
   extern __shared__ uint8_t smem_raw[];
-  __shared__ __align__(8) uint64_t full[kMaxStagesA], empty[kMaxStagesA], acc_full[2], acc_empty[2], w_full;
+  __shared__ __align__(8) uint64_t full[kMaxStagesA], empty[kMaxStagesA], acc_full[2], acc_empty[2], w_full, y_full[2], y_empty[2];
   __shared__ uint32_t tmem_slot;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int tiles_n = (N + kTile - 1) / kTile;
   const int tiles_m = (P + kTile - 1) / kTile;
   const int n_slabs = (K + kSlab - 1) / kSlab;
-  // shared memory: [WS: B slice, n_slabs x 16 KB][ring][staging 32 KB][STATS: 2 x tiles_n x 128 floats]
+  // shared memory: [WS: B slice, n_slabs x 16 KB][ring][staging: groups x 32 KB][BWD: 2 y tiles of 32 KB]
+  //                [STATS / BWD: 2 x tiles_n x 128 floats of column sums]
   uint8_t* base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);  // swizzle atoms are 1024-byte aligned
   uint8_t* wreg = base;
   uint8_t* ring = base + (WS ? (size_t)n_slabs * kOperandBytes : 0);
-  const int n_stages = WS ? stages_a : kStages;
   const int stage_bytes = WS ? kOperandBytes : kStageBytes;
-  uint8_t* staging = ring + (size_t)n_stages * stage_bytes;
-  float* s_stat = reinterpret_cast<float*>(staging + kStagingBytes);
+  uint8_t* staging_all = ring + (size_t)n_stages * stage_bytes;
+  uint8_t* ytile = staging_all + (size_t)groups * kStagingBytes;
+  float* s_stat = reinterpret_cast<float*>(ytile + (MODE == kBwd ? 2 * kStagingBytes : 0));
   // this CTA's tiles: streaming = every gridDim-th tile, n fastest; WS = one n-tile, every (gridDim / tiles_n)-th m-tile
   const int per_n = WS ? (int)gridDim.x / tiles_n : 0;
   const int my_n = WS ? (int)blockIdx.x % tiles_n : 0;
@@ -154,6 +192,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
   if (threadIdx.x == 0) {
     for (int s = 0; s < kMaxStagesA; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
     mbar_init(&w_full, 1);
+    for (int a = 0; a < 2; ++a) { mbar_init(&y_full[a], 1); mbar_init(&y_empty[a], 1); }
     for (int a = 0; a < 2; ++a) { mbar_init(&acc_full[a], 1); mbar_init(&acc_empty[a], 4); }  // 4 epilogue warps
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -183,6 +222,17 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
           mbar_expect_tx(&full[s], (unsigned)stage_bytes);  // zero-filled out-of-range elements count as transferred bytes
           tma_load_2d(ring + (size_t)s * stage_bytes, &map_a, k * kSlab, row0, &full[s]);
           if (!WS) tma_load_2d(ring + (size_t)s * stage_bytes + kOperandBytes, &map_b, k * kSlab, col0, &full[s]);
+        }
+        if constexpr (MODE == kBwd) {  // the previous block's pre-activation tile, for this tile's epilogue
+          // (two buffers: with one, the producer could not run more than a tile ahead of the epilogue — 8 150 cycles per
+          // tile, latency-bound, on the 128 -> 128 layer)
+          const int yb = i & 1;
+          if (i >= 2) mbar_wait(&y_empty[yb], (unsigned)((i >> 1) - 1) & 1u);
+          const bool two = col0 + 64 < N;
+          uint8_t* yt = ytile + (size_t)yb * kStagingBytes;
+          mbar_expect_tx(&y_full[yb], two ? (unsigned)kStagingBytes : (unsigned)kStagingBytes / 2);
+          tma_load_2d(yt, &map_y, col0, row0, &y_full[yb]);
+          if (two) tma_load_2d(yt + kStagingBytes / 2, &map_y, col0 + 64, row0, &y_full[yb]);
         }
       }
     }
@@ -218,16 +268,19 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
   } else {
     const int qd = warp & 3;  // the TMEM lane quadrant a warp may read is fixed by warp id % 4
     const int r = qd * 32 + lane;  // this thread's row of the tile (= TMEM lane)
-    const bool issuer = (warp == 2 && lane == 0);
-    for (int i = 0; i < n_my; ++i) {
+    const int grp = (warp - 2) >> 2;  // epilogue group: tiles i = grp, grp + groups, ...
+    const int bar_id = 1 + grp;
+    const bool issuer = (((warp - 2) & 3) == 0 && lane == 0);
+    uint8_t* staging = staging_all + (size_t)grp * kStagingBytes;
+    for (int i = grp; i < n_my; i += groups) {
       const unsigned a = (unsigned)i & 1u;
       int row0, col0;
       tile_of(i, row0, col0);
       mbar_wait(&acc_full[a], ((unsigned)i >> 1) & 1u);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      // the previous tile's stores must have finished READING the staging tile before it is overwritten
+      // the group's previous tile's stores must have finished READING the staging tile before it is overwritten
       if (issuer) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-      epi_barrier();
+      epi_barrier(bar_id);
       const uint32_t t_addr = tmem + ((uint32_t)(qd * 32) << 16) + a * (uint32_t)kTile;
 #pragma unroll 1
       for (int cc = 0; cc < kTile; cc += 32) {
@@ -245,20 +298,84 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
       }
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       __syncwarp();
-      if (lane == 0) mbar_arrive(&acc_empty[a]);  // the accumulator is in registers / shared memory now
+      if (lane == 0) mbar_arrive(&acc_empty[a]);  // the accumulator is in shared memory now
+      // column walk: thread = (column half h, 64-row half rh, 32-bit word w = 2 columns); a warp reads the 32 words of one
+      // 128-byte line per step: conflict-free in spite of the swizzle
+      const int tid = ((warp - 2) & 3) * 32 + lane;
+      const int h = tid >> 6, rh = (tid >> 5) & 1, w = tid & 31;
+      const size_t half_off = (size_t)h * (kStagingBytes / 2);
+      if constexpr (MODE == kBwd) {
+        const int c0 = col0 + h * 64 + 2 * w;  // this thread's two columns (N is even)
+        const bool cok = c0 < N;
+        const float sc0 = cok ? __ldg(bw.scale + c0) : 0.f, sc1 = cok ? __ldg(bw.scale + c0 + 1) : 0.f;
+        const float sh0 = cok ? __ldg(bw.shift + c0) : 0.f, sh1 = cok ? __ldg(bw.shift + c0 + 1) : 0.f;
+        mbar_wait(&y_full[i & 1], ((unsigned)i >> 1) & 1u);
+        epi_barrier(bar_id);  // every row of the staged tile is written
+        const uint8_t* yt = ytile + (size_t)(i & 1) * kStagingBytes;
+        float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
+        // 8 rows per batch, the next batch's words loaded BEFORE this batch's write-backs: the compiler cannot prove that
+        // the in-place stores do not alias later loads, so a plain row loop ran one shared-memory latency per row
+        // (~7 800 cycles per tile measured)
+        const uint32_t col_off = (uint32_t)half_off + (uint32_t)(w & 3) * 4u;
+        auto word_off = [&](int rr) { return col_off + (uint32_t)rr * 128u + ((uint32_t)((w >> 2) ^ (rr & 7)) << 4); };
+        uint32_t gw[8], yw[8], gn[8], yn[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const uint32_t off = word_off(rh * 64 + u);
+          gw[u] = *reinterpret_cast<const uint32_t*>(staging + off);
+          yw[u] = *reinterpret_cast<const uint32_t*>(yt + off);
+        }
+#pragma unroll 1
+        for (int r8 = rh * 64; r8 < rh * 64 + 64; r8 += 8) {
+          if (r8 + 8 < rh * 64 + 64) {
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+              const uint32_t off = word_off(r8 + 8 + u);
+              gn[u] = *reinterpret_cast<const uint32_t*>(staging + off);
+              yn[u] = *reinterpret_cast<const uint32_t*>(yt + off);
+            }
+          }
+#pragma unroll
+          for (int u = 0; u < 8; ++u) {
+            const float y0 = __uint_as_float(yw[u] << 16), y1 = __uint_as_float(yw[u] & 0xffff0000u);
+            float g0 = __uint_as_float(gw[u] << 16), g1 = __uint_as_float(gw[u] & 0xffff0000u);
+            if (bw.relu) {
+              if (!(fmaf(y0, sc0, sh0) > 0.f)) g0 = 0.f;
+              if (!(fmaf(y1, sc1, sh1) > 0.f)) g1 = 0.f;
+            }
+            uint32_t out = (__float_as_uint(g0) >> 16) | (__float_as_uint(g1) & 0xffff0000u);  // exact: bf16 values or 0
+            if (bw.thresh) {
+              const long long grow = (long long)row0 + r8 + u;
+              g0 = keep_elem(bw.seed, grow, c0, N, bw.thresh) ? g0 * bw.keep_scale : 0.f;
+              g1 = keep_elem(bw.seed, grow, c0 + 1, N, bw.thresh) ? g1 * bw.keep_scale : 0.f;
+              out = pack_bf16(g0, g1);  // the sums are those of the STORED gradient
+              g0 = __uint_as_float(out << 16);
+              g1 = __uint_as_float(out & 0xffff0000u);
+            }
+            *reinterpret_cast<uint32_t*>(staging + word_off(r8 + u)) = out;
+            s0 += g0; s1 += g1;
+            q0 = fmaf(g0, y0, q0); q1 = fmaf(g1, y1, q1);
+          }
+#pragma unroll
+          for (int u = 0; u < 8; ++u) { gw[u] = gn[u]; yw[u] = yn[u]; }
+        }
+        float* dst = s_stat + col0 + h * 64 + 2 * w;
+        atomicAdd(dst, s0);
+        atomicAdd(dst + 1, s1);
+        atomicAdd(dst + tiles_n * kTile, q0);
+        atomicAdd(dst + tiles_n * kTile + 1, q1);
+      }
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // staging writes -> visible to the copy engine
-      epi_barrier();
+      epi_barrier(bar_id);
       if (issuer) {
         tma_store_2d(&map_c, staging, col0, row0);
         if (col0 + 64 < N) tma_store_2d(&map_c, staging + kStagingBytes / 2, col0 + 64, row0);
         asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        if constexpr (MODE == kBwd) mbar_arrive(&y_empty[i & 1]);  // (after the barrier: every thread is done with the y tile)
       }
-      if constexpr (STATS) {
-        // column sums of the STAGED (bf16) tile: thread = (column half, 64-row half, 32-bit word = 2 columns); a warp
-        // reads the 32 words of one 128-byte line per step: conflict-free in spite of the swizzle
-        const int tid = (warp - 2) * 32 + lane;
-        const int h = tid >> 6, rh = (tid >> 5) & 1, w = tid & 31;
-        const uint8_t* base = staging + (size_t)h * (kStagingBytes / 2);
+      if constexpr (MODE == kStats) {
+        // column sums of the STAGED (bf16) tile
+        const uint8_t* base = staging + half_off;
         float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
 #pragma unroll 8
         for (int rr = rh * 64; rr < rh * 64 + 64; ++rr) {
@@ -316,15 +433,23 @@ static int encode_bf16_map(CUtensorMap* map, const void* base, long long width, 
 }  // namespace s4g
 
 static bool g_gemm_ws = true;
-// A/B switch for measurements: 0 = always stream B through the ring, 1 = weight-stationary where it applies (default).
+static int g_epi_groups = 0;
+// A/B switches for measurements.  weight_stationary: 0 = always stream B through the ring, 1 = weight-stationary where it
+// applies (default).  epilogue_groups: 1 or 2 groups of 4 epilogue warps, 0 (default) = chosen per launch.  Both return
+// the previous value.
 extern "C" int s4g_gemm_bf16_set_weight_stationary(int on) {
   const int prev = g_gemm_ws ? 1 : 0;
   g_gemm_ws = on != 0;
   return prev;
 }
+extern "C" int s4g_gemm_bf16_set_epilogue_groups(int groups) {
+  const int prev = g_epi_groups;
+  if (groups >= 0 && groups <= 2) g_epi_groups = groups;
+  return prev;
+}
 
 static int gemm_launch(const void* a, long long lda, const void* b, long long ldb, void* c, long long ldc, long long P, int N,
-                       int K, double* stats, void* stream) {
+                       int K, int mode, double* stats, const s4g::gemm::BwdEpilogue& bw, void* stream) {
   using namespace s4g::gemm;
   S4G_CHECK_ARG(a && b && c, "gemm_bf16: null pointer");
   S4G_CHECK_ARG(P >= 0 && P < (1ll << 31) - kTile && N > 0 && K > 0, "gemm_bf16: bad shape");
@@ -344,46 +469,65 @@ static int gemm_launch(const void* a, long long lda, const void* b, long long ld
   const int tiles_n = (N + kTile - 1) / kTile;
   const long long tiles_m = (P + kTile - 1) / kTile;
   const int n_slabs = (K + kSlab - 1) / kSlab;
-  const size_t stat_bytes = stats ? sizeof(float) * 2 * tiles_n * kTile : 0;
-  constexpr int kMaxDynSmem = 220 * 1024;  // (the kernel also has a few hundred bytes of static shared memory)
-  // weight-stationary when the B slice fits beside >= 3 A stages and every CTA gets >= 2 m-tiles
+  CUtensorMap my = mc;
+  if (mode == kBwd) {
+    rc = encode_bf16_map(&my, bw.y, N, bw.ldy, P);
+    if (rc != S4G_OK) return rc;
+  }
+  // epilogue groups: two pay where the epilogue, not HBM or the tensor pipe, sets the pace — short K (<= 2 slabs: measured
+  // 3 -> 128 on 10.5 M rows 0.82 -> 0.55 ms, 128 -> 256 1.63 -> 1.28 ms); with more slabs per tile the second staging tile
+  // only costs ring stages (264 -> 256 on 2.1 M rows 0.49 -> 0.64 ms: it loses the weight-stationary schedule).  The BWD
+  // epilogue has one group (its y tile takes the second staging tile's place).
+  const int groups = mode == kBwd ? 1 : g_epi_groups ? g_epi_groups : (n_slabs <= 2 ? 2 : 1);
+  // per-column sums in shared memory
+  const size_t table_bytes = sizeof(float) * (size_t)tiles_n * kTile * (mode == kPlain ? 0 : 2);
+  constexpr int kMaxDynSmem = 226 * 1024;  // (the kernel also has ~170 bytes of static shared memory; the limit is 227 KB)
+  const long long room = (long long)kMaxDynSmem - 1024 - (long long)(groups + (mode == kBwd ? 2 : 0)) * kStagingBytes -
+                         (long long)table_bytes;
+  S4G_CHECK_ARG(room >= 2LL * kStageBytes, "gemm_bf16: too many output columns for the fused statistics");
+  // weight-stationary when the B slice fits beside >= 5 A stages and every CTA gets >= 2 m-tiles
+  // (K = 512 with 3 A stages beside its 128 KB slice: measured 20-30 % SLOWER than streaming)
   const int sms = s4g::num_sms();
-  int stages_a = 0;
+  int n_stages = (int)(room / kStageBytes);
+  if (n_stages > kStages) n_stages = kStages;
   bool ws = false;
   if (g_gemm_ws && n_slabs <= kMaxSlabsWS && tiles_n <= sms) {
-    const long long room = (long long)kMaxDynSmem - 1024 - kStagingBytes - (long long)stat_bytes - (long long)n_slabs * kOperandBytes;
-    stages_a = (int)(room / kOperandBytes);
+    int stages_a = (int)(room / kOperandBytes) - n_slabs;
     if (stages_a > kMaxStagesA) stages_a = kMaxStagesA;
-    // (K = 512 leaves only 3 A stages beside its 128 KB slice: measured 20-30 % SLOWER than streaming; K <= 384 keeps >= 5)
     ws = stages_a >= 5 && tiles_m >= 2LL * (sms / tiles_n);
+    if (ws) n_stages = stages_a;
   }
-  const size_t smem = 1024 + kStagingBytes + stat_bytes +
-                      (ws ? (size_t)(n_slabs + stages_a) * kOperandBytes : (size_t)kStages * kStageBytes);
-  S4G_CHECK_ARG(smem <= (size_t)kMaxDynSmem, "gemm_bf16: too many output columns for the fused statistics");
+  const size_t smem = 1024 + (size_t)(groups + (mode == kBwd ? 2 : 0)) * kStagingBytes + table_bytes +
+                      (ws ? (size_t)(n_slabs + n_stages) * kOperandBytes : (size_t)n_stages * kStageBytes);
   static bool attr_set = false;
   if (!attr_set) {
-    S4G_CUDA(cudaFuncSetAttribute(gemm_bf16_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
-    S4G_CUDA(cudaFuncSetAttribute(gemm_bf16_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
-    S4G_CUDA(cudaFuncSetAttribute(gemm_bf16_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
-    S4G_CUDA(cudaFuncSetAttribute(gemm_bf16_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
+    S4G_CUDA(cudaFuncSetAttribute(gemm_bf16_kernel<kPlain, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
+    S4G_CUDA(cudaFuncSetAttribute(gemm_bf16_kernel<kPlain, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
+    S4G_CUDA(cudaFuncSetAttribute(gemm_bf16_kernel<kStats, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
+    S4G_CUDA(cudaFuncSetAttribute(gemm_bf16_kernel<kStats, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
+    S4G_CUDA(cudaFuncSetAttribute(gemm_bf16_kernel<kBwd, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
+    S4G_CUDA(cudaFuncSetAttribute(gemm_bf16_kernel<kBwd, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
     attr_set = true;
   }
   const long long tiles = tiles_m * tiles_n;
   int grid = (int)(tiles < sms ? tiles : sms);
   if (ws) grid = (sms / tiles_n) * tiles_n;  // every n-tile gets the same number of CTAs
+  const int threads = 64 + 128 * groups;
   cudaStream_t st = (cudaStream_t)stream;
   if (stats) S4G_CUDA(cudaMemsetAsync(stats, 0, sizeof(double) * 2 * N, st));
-  if (stats && ws) gemm_bf16_kernel<true, true><<<grid, kThreads, smem, st>>>(ma, mb, mc, (int)P, N, K, stages_a, stats);
-  else if (stats) gemm_bf16_kernel<true, false><<<grid, kThreads, smem, st>>>(ma, mb, mc, (int)P, N, K, 0, stats);
-  else if (ws) gemm_bf16_kernel<false, true><<<grid, kThreads, smem, st>>>(ma, mb, mc, (int)P, N, K, stages_a, nullptr);
-  else gemm_bf16_kernel<false, false><<<grid, kThreads, smem, st>>>(ma, mb, mc, (int)P, N, K, 0, nullptr);
+#define S4G_GEMM_GO(MODE_, WS_) \
+  gemm_bf16_kernel<MODE_, WS_><<<grid, threads, smem, st>>>(ma, mb, mc, my, (int)P, N, K, n_stages, groups, stats, bw)
+  if (mode == kBwd) { if (ws) S4G_GEMM_GO(kBwd, true); else S4G_GEMM_GO(kBwd, false); }
+  else if (mode == kStats) { if (ws) S4G_GEMM_GO(kStats, true); else S4G_GEMM_GO(kStats, false); }
+  else { if (ws) S4G_GEMM_GO(kPlain, true); else S4G_GEMM_GO(kPlain, false); }
+#undef S4G_GEMM_GO
   S4G_LAUNCH_CHECK("gemm_bf16");
   return S4G_OK;
 }
 
 extern "C" int s4g_gemm_bf16(const void* a, long long lda, const void* b, long long ldb, void* c, long long ldc, long long P,
                              int N, int K, void* stream) {
-  return gemm_launch(a, lda, b, ldb, c, ldc, P, N, K, nullptr, stream);
+  return gemm_launch(a, lda, b, ldb, c, ldc, P, N, K, s4g::gemm::kPlain, nullptr, s4g::gemm::BwdEpilogue{}, stream);
 }
 
 // the same with the per-column sum / sum of squares of the stored (bf16-rounded) result: stats2n[0..N) = sum_r c[r][n],
@@ -391,5 +535,27 @@ extern "C" int s4g_gemm_bf16(const void* a, long long lda, const void* b, long l
 extern "C" int s4g_gemm_bf16_stats(const void* a, long long lda, const void* b, long long ldb, void* c, long long ldc,
                                    long long P, int N, int K, double* stats2n, void* stream) {
   S4G_CHECK_ARG(stats2n != nullptr, "gemm_bf16_stats: null statistics buffer");
-  return gemm_launch(a, lda, b, ldb, c, ldc, P, N, K, stats2n, stream);
+  return gemm_launch(a, lda, b, ldb, c, ldc, P, N, K, s4g::gemm::kStats, stats2n, s4g::gemm::BwdEpilogue{}, stream);
+}
+
+// input-gradient GEMM whose result is the upstream gradient of the block that produced y_prev = the rows [P][N] BEFORE its
+// BatchNorm: c = (a · b^T) * relu'(y_prev * scale + shift) * dropout mask  (stored masked, bf16), and
+// sums2n[0..N) = sum_r c[r][n], sums2n[N..2N) = sum_r c[r][n] * y_prev[r][n]  (fp64, zeroed here) — what
+// s4g_train_bn_bwd_reduce_bf16 would compute from c and y_prev in another pass.
+extern "C" int s4g_gemm_bf16_bwd(const void* a, long long lda, const void* b, long long ldb, void* c, long long ldc, long long P,
+                                 int N, int K, const void* y_prev, long long ldy, const float* scale, const float* shift,
+                                 int relu, unsigned seed, float drop_p, double* sums2n, void* stream) {
+  S4G_CHECK_ARG(y_prev && scale && shift && sums2n, "gemm_bf16_bwd: null pointer");
+  S4G_CHECK_ARG(ldy >= N && ldy % 8 == 0 && N % 8 == 0 && ((uintptr_t)y_prev & 15) == 0 && drop_p >= 0.f && drop_p < 1.f,
+                "gemm_bf16_bwd: y_prev rows must be 16-byte aligned, N a multiple of 8");
+  s4g::gemm::BwdEpilogue bw;
+  bw.y = reinterpret_cast<const __nv_bfloat16*>(y_prev);
+  bw.ldy = ldy;
+  bw.scale = scale;
+  bw.shift = shift;
+  bw.relu = relu;
+  bw.seed = seed;
+  bw.thresh = drop_p > 0.f ? (unsigned)((double)drop_p * 4294967296.0) : 0u;
+  bw.keep_scale = 1.f / (1.f - drop_p);
+  return gemm_launch(a, lda, b, ldb, c, ldc, P, N, K, s4g::gemm::kBwd, sums2n, bw, stream);
 }

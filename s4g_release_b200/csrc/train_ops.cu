@@ -140,17 +140,18 @@ bn_act_kernel(const __nv_bfloat16* __restrict__ y, const float* __restrict__ sca
 
 __global__ void __launch_bounds__(256)
 bn_act_maxpool_kernel(const __nv_bfloat16* __restrict__ y, const float* __restrict__ scale, const float* __restrict__ shift,
-                      __nv_bfloat16* __restrict__ out, uint8_t* __restrict__ arg, long long G, int K, int C, int relu) {
+                      __nv_bfloat16* __restrict__ out, uint8_t* __restrict__ arg, __nv_bfloat16* __restrict__ ymax, long long G,
+                      int K, int C, int relu) {
   const int pieces = C >> 3;
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= G * pieces) return;
   const long long g = i / pieces;
   const int piece = (int)(i - g * pieces);
   const F8 a = load_f8(scale + piece * 8), b = load_f8(shift + piece * 8);
-  F8 best;
+  F8 best, raw;  // raw: the pre-BatchNorm value at the arg-max (what the backward's reduce needs of this group)
   int bi[8];
 #pragma unroll
-  for (int e = 0; e < 8; ++e) { best.v[e] = -3.4e38f; bi[e] = 0; }
+  for (int e = 0; e < 8; ++e) { best.v[e] = -3.4e38f; raw.v[e] = 0.f; bi[e] = 0; }
   const uint4* src = reinterpret_cast<const uint4*>(y + g * K * C) + piece;
   for (int k = 0; k < K; ++k) {
     const F8 v = unpack8(__ldg(src + (size_t)k * pieces));
@@ -158,10 +159,11 @@ bn_act_maxpool_kernel(const __nv_bfloat16* __restrict__ y, const float* __restri
     for (int e = 0; e < 8; ++e) {
       float t = fmaf(v.v[e], a.v[e], b.v[e]);
       if (relu) t = fmaxf(t, 0.f);
-      if (t > best.v[e]) { best.v[e] = t; bi[e] = k; }  // first maximum wins, like torch.max
+      if (t > best.v[e]) { best.v[e] = t; raw.v[e] = v.v[e]; bi[e] = k; }  // first maximum wins, like torch.max
     }
   }
   reinterpret_cast<uint4*>(out + g * C)[piece] = pack8(best);
+  if (ymax) reinterpret_cast<uint4*>(ymax + g * C)[piece] = pack8(raw);  // exact: raw holds bf16 values
   uint2 packed;
   packed.x = (unsigned)bi[0] | ((unsigned)bi[1] << 8) | ((unsigned)bi[2] << 16) | ((unsigned)bi[3] << 24);
   packed.y = (unsigned)bi[4] | ((unsigned)bi[5] << 8) | ((unsigned)bi[6] << 16) | ((unsigned)bi[7] << 24);
@@ -259,6 +261,124 @@ bn_bwd_reduce_kernel(Upstream up, const __nv_bfloat16* __restrict__ y, const flo
   }
 }
 
+// ---- the same reduction with the rows STAGED through shared memory by the copy engine ----------------------------------
+// The register version above keeps 4 rows x 2 x 16 B per thread in flight, 64 KB per SM at its 24 % occupancy — about one
+// bandwidth-delay product, and ncu showed it at 59-67 % of the DRAM peak with 43 % of the stalls on the loads.  Here a
+// producer lane streams row tiles of both operands (dz, y: contiguous [P][C], so a tile is ONE 1-D bulk copy each) into a
+// 3-stage ring (up to 192 KB in flight per SM, independent of the register file) and 16 consumer warps read them back
+// with conflict-free 16-byte shared loads (thread t reads bytes [16 t, 16 t + 16) of a 4-row-lane slab).
+__device__ __forceinline__ uint32_t stg_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void stg_wait(uint64_t* bar, unsigned parity) {
+  unsigned ok = 0, spins = 0;
+  while (!ok) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok) : "r"(stg_u32(bar)), "r"(parity) : "memory");
+    if (!ok && ++spins > (1u << 26)) __trap();  // a protocol bug traps instead of hanging the GPU
+  }
+}
+constexpr int kStgConsumers = 512;
+constexpr int kStgThreads = kStgConsumers + 32;  // + the producer warp
+constexpr int kStgStages = 3;
+constexpr int kStgRowsPerLane = 4;
+
+__global__ void __launch_bounds__(kStgThreads, 1)
+bn_bwd_reduce_staged_kernel(const __nv_bfloat16* __restrict__ dz, const __nv_bfloat16* __restrict__ y,
+                            const float* __restrict__ scale, const float* __restrict__ shift, long long P, int C, int relu,
+                            unsigned seed, unsigned thresh, float keep_scale, double* __restrict__ out) {
+  extern __shared__ __align__(128) uint8_t stg_smem[];  // [stages][dz tile | y tile]; re-used for the final reduction
+  __shared__ __align__(8) uint64_t full[kStgStages], empty[kStgStages];
+  const int pieces = C >> 3;
+  const int lanes = kStgConsumers / pieces;
+  const int R = kStgRowsPerLane * lanes;                 // rows per tile
+  const unsigned tile_bytes = (unsigned)R * (unsigned)C * 2u;  // <= 32 KB
+  const long long n_tiles = (P + R - 1) / R;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kStgStages; ++s) {
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(stg_u32(&full[s])));
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(stg_u32(&empty[s])), "r"(kStgConsumers / 32));
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  if (warp == kStgConsumers / 32) {
+    if (lane == 0) {
+      unsigned i = 0;
+      for (long long t = blockIdx.x; t < n_tiles; t += gridDim.x, ++i) {
+        const unsigned s = i % kStgStages, use = i / kStgStages;
+        if (use > 0) stg_wait(&empty[s], (use - 1) & 1u);
+        const long long row0 = t * R;
+        const unsigned bytes = (unsigned)(min((long long)R, P - row0) * C * 2);
+        uint8_t* dst = stg_smem + (size_t)s * 2 * tile_bytes;
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(stg_u32(&full[s])), "r"(2u * bytes) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(stg_u32(dst)),
+                     "l"(dz + row0 * C), "r"(bytes), "r"(stg_u32(&full[s])) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                         stg_u32(dst + tile_bytes)), "l"(y + row0 * C), "r"(bytes), "r"(stg_u32(&full[s])) : "memory");
+      }
+    }
+    return;
+  }
+  const int piece = threadIdx.x % pieces, rl = threadIdx.x / pieces;
+  const bool active = rl < lanes;
+  F8 sg{}, sq{};
+  const F8 a = load_f8(scale + piece * 8), b = load_f8(shift + piece * 8);
+  unsigned i = 0;
+  for (long long t = blockIdx.x; t < n_tiles; t += gridDim.x, ++i) {
+    const unsigned s = i % kStgStages, use = i / kStgStages;
+    const long long row0 = t * R;
+    const int rows = (int)min((long long)R, P - row0);
+    stg_wait(&full[s], use & 1u);
+    if (active) {
+      const uint4* gt = reinterpret_cast<const uint4*>(stg_smem + (size_t)s * 2 * tile_bytes) + threadIdx.x;
+      const uint4* yt = reinterpret_cast<const uint4*>(stg_smem + (size_t)s * 2 * tile_bytes + tile_bytes) + threadIdx.x;
+      uint4 gr[kStgRowsPerLane], yr[kStgRowsPerLane];
+#pragma unroll
+      for (int u = 0; u < kStgRowsPerLane; ++u) {
+        if (rl + u * lanes < rows) {
+          gr[u] = gt[(size_t)u * lanes * pieces];
+          yr[u] = yt[(size_t)u * lanes * pieces];
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < kStgRowsPerLane; ++u) {
+        const int rr = rl + u * lanes;
+        if (rr >= rows) break;
+        const F8 v = unpack8(yr[u]);
+        const F8 d = unpack8(gr[u]);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          float g = d.v[e];
+          if (relu && !(fmaf(v.v[e], a.v[e], b.v[e]) > 0.f)) g = 0.f;
+          if (thresh) g = keep_elem(seed, row0 + rr, piece * 8 + e, C, thresh) ? g * keep_scale : 0.f;
+          sg.v[e] += g;
+          sq.v[e] = fmaf(g, v.v[e], sq.v[e]);
+        }
+      }
+    }
+    __syncwarp();
+    if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(stg_u32(&empty[s])) : "memory");
+  }
+  // every consumer is done with the ring (and every copy has been waited for): re-use it for the block reduction
+  asm volatile("bar.sync 1, %0;" ::"n"(kStgConsumers) : "memory");
+  float* s_part = reinterpret_cast<float*>(stg_smem);
+  if (active) {
+    float* dst = s_part + ((size_t)rl * pieces + piece) * 16;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) { dst[e] = sg.v[e]; dst[8 + e] = sq.v[e]; }
+  }
+  asm volatile("bar.sync 1, %0;" ::"n"(kStgConsumers) : "memory");
+  for (int t = threadIdx.x; t < pieces * 16; t += kStgConsumers) {
+    double acc = 0.0;
+    for (int l = 0; l < lanes; ++l) acc += (double)s_part[(size_t)l * pieces * 16 + t];
+    const int pc = t >> 4, e = t & 15;
+    atomicAdd(out + (e < 8 ? 0 : C) + pc * 8 + (e & 7), acc);
+  }
+}
+
 // dy = coef * (g - m1 - xhat * m2) = ka * g + kb * y + kc per channel, with ka = coef, kb = -coef * rstd * m2,
 // kc = coef * (rstd * m2 * mean - m1) folded by the host wrapper (coef = gamma * rstd, m1 = mean(g), m2 = mean(g * xhat))
 __global__ void __launch_bounds__(256, 2)
@@ -300,6 +420,102 @@ bn_bwd_apply_kernel(Upstream up, const __nv_bfloat16* __restrict__ y, const floa
       }
       reinterpret_cast<uint4*>(dy + rr * C)[piece] = pack8(o);
     }
+  }
+}
+
+// the second pass, rows staged by the copy engine like bn_bwd_reduce_staged_kernel: y always, dz when it is dense (a pooled
+// upstream gradient is G x C, K times smaller than y, and stays on the read-only path); dy leaves with 16-byte stores
+// (RPL rows per thread and tile, STAGES tiles in flight, CONS consumer threads: 15 consumer warps + the producer warp = 512
+// threads get 128 registers each; with 16 + 1 warps ptxas allots 96 and the five per-channel parameter vectors spill)
+template <int RPL, int STAGES, int CONS>
+__global__ void __launch_bounds__(CONS + 32, 1)
+bn_bwd_apply_staged_kernel(Upstream up, const __nv_bfloat16* __restrict__ y, const float* __restrict__ scale,
+                           const float* __restrict__ shift, const float* __restrict__ ka, const float* __restrict__ kb,
+                           const float* __restrict__ kc, long long P, int C, int relu, unsigned seed, unsigned thresh,
+                           float keep_scale, __nv_bfloat16* __restrict__ dy) {
+  extern __shared__ __align__(128) uint8_t stg_smem[];  // [stages][y tile | dz tile]
+  __shared__ __align__(8) uint64_t full[STAGES], empty[STAGES];
+  const int pieces = C >> 3;
+  const int lanes = CONS / pieces;
+  const int R = RPL * lanes;
+  const unsigned tile_bytes = (unsigned)R * (unsigned)C * 2u;
+  const long long n_tiles = (P + R - 1) / R;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const bool dense = up.K == 0;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(stg_u32(&full[s])));
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(stg_u32(&empty[s])), "r"(CONS / 32));
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  if (warp == CONS / 32) {
+    if (lane == 0) {
+      unsigned i = 0;
+      for (long long t = blockIdx.x; t < n_tiles; t += gridDim.x, ++i) {
+        const unsigned s = i % STAGES, use = i / STAGES;
+        if (use > 0) stg_wait(&empty[s], (use - 1) & 1u);
+        const long long row0 = t * R;
+        const unsigned bytes = (unsigned)(min((long long)R, P - row0) * C * 2);
+        uint8_t* dst = stg_smem + (size_t)s * 2 * tile_bytes;
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(stg_u32(&full[s])), "r"(dense ? 2u * bytes : bytes)
+                     : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(stg_u32(dst)),
+                     "l"(y + row0 * C), "r"(bytes), "r"(stg_u32(&full[s])) : "memory");
+        if (dense)
+          asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                           stg_u32(dst + tile_bytes)), "l"(up.dz + row0 * C), "r"(bytes), "r"(stg_u32(&full[s])) : "memory");
+      }
+    }
+    return;
+  }
+  const int piece = threadIdx.x % pieces, rl = threadIdx.x / pieces;
+  const bool active = rl < lanes;
+  const F8 a = load_f8(scale + piece * 8), b = load_f8(shift + piece * 8), A = load_f8(ka + piece * 8),
+           Bc = load_f8(kb + piece * 8), Cc = load_f8(kc + piece * 8);
+  unsigned i = 0;
+  for (long long t = blockIdx.x; t < n_tiles; t += gridDim.x, ++i) {
+    const unsigned s = i % STAGES, use = i / STAGES;
+    const long long row0 = t * R;
+    const int rows = (int)min((long long)R, P - row0);
+    UpRaw ur[RPL];
+    if (active && !dense) {  // (before the wait: these come from L2)
+#pragma unroll
+      for (int u = 0; u < RPL; ++u)
+        if (rl + u * lanes < rows) ur[u] = upstream_load(up, row0 + rl + u * lanes, piece, C);
+    }
+    stg_wait(&full[s], use & 1u);
+    if (active) {
+      const uint4* yt = reinterpret_cast<const uint4*>(stg_smem + (size_t)s * 2 * tile_bytes) + threadIdx.x;
+      const uint4* gt = reinterpret_cast<const uint4*>(stg_smem + (size_t)s * 2 * tile_bytes + tile_bytes) + threadIdx.x;
+      uint4 yr[RPL];
+#pragma unroll
+      for (int u = 0; u < RPL; ++u) {
+        if (rl + u * lanes < rows) {
+          yr[u] = yt[(size_t)u * lanes * pieces];
+          if (dense) { ur[u].d = gt[(size_t)u * lanes * pieces]; ur[u].a = make_uint2(0u, 0u); ur[u].k = -1; }
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < RPL; ++u) {
+        const int rr = rl + u * lanes;
+        if (rr >= rows) break;
+        const F8 v = unpack8(yr[u]);
+        const F8 d = upstream_route(ur[u]);
+        F8 o;
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          float g = d.v[e];
+          if (relu && !(fmaf(v.v[e], a.v[e], b.v[e]) > 0.f)) g = 0.f;
+          if (thresh) g = keep_elem(seed, row0 + rr, piece * 8 + e, C, thresh) ? g * keep_scale : 0.f;
+          o.v[e] = fmaf(A.v[e], g, fmaf(Bc.v[e], v.v[e], Cc.v[e]));
+        }
+        reinterpret_cast<uint4*>(dy + (row0 + rr) * C)[piece] = pack8(o);
+      }
+    }
+    __syncwarp();
+    if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(stg_u32(&empty[s])) : "memory");
   }
 }
 
@@ -487,6 +703,94 @@ head_logits_bwd_kernel(const float* __restrict__ dl, const float* __restrict__ w
   }
 }
 
+// out = a + b (+ c) (+ d), bf16 rows summed in fp32, one rounding: the four heads' gradients of the per-point features
+__global__ void __launch_bounds__(256)
+sum_bf16_kernel(const uint4* __restrict__ a, const uint4* __restrict__ b, const uint4* __restrict__ c, const uint4* __restrict__ d,
+                uint4* __restrict__ out, long long n8) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n8) return;
+  const uint4 ra = __ldg(a + i), rb = __ldg(b + i);
+  const uint4 rc = c ? __ldg(c + i) : make_uint4(0u, 0u, 0u, 0u), rd = d ? __ldg(d + i) : make_uint4(0u, 0u, 0u, 0u);
+  const F8 fa = unpack8(ra), fb = unpack8(rb), fc = unpack8(rc), fd = unpack8(rd);
+  F8 o;
+#pragma unroll
+  for (int e = 0; e < 8; ++e) o.v[e] = (fa.v[e] + fb.v[e]) + (fc.v[e] + fd.v[e]);
+  out[i] = pack8(o);
+}
+
+// dw[j][c] += sum_row dlogits[b][j][n] * h[row][c],  dbias[j] += sum_row dlogits[b][j][n]   (fp32 atomics, k <= KT)
+// thread = (16-byte piece of h, row lane); a block walks kDwRows rows, reduces over its row lanes in shared memory
+constexpr int kDwRows = 512;  // (2048: 400 blocks on 296 slots, one latency-bound row at a time -> 0.5 ms per head)
+template <int KT>
+__global__ void __launch_bounds__(256)
+head_logits_dw_kernel(const float* __restrict__ dl, const __nv_bfloat16* __restrict__ h, float* __restrict__ dw,
+                      float* __restrict__ dbias, long long P, int C, int k, int n_points) {
+  extern __shared__ float s_red[];  // [lanes][C]
+  __shared__ float s_b[256];
+  const int pieces = C >> 3;
+  const int lanes = 256 / pieces;
+  const int piece = threadIdx.x % pieces, rl = threadIdx.x / pieces;
+  const long long r0 = (long long)blockIdx.x * kDwRows, r1 = min(P, r0 + kDwRows);
+  float acc[KT][8];
+  float accb[KT];
+#pragma unroll
+  for (int j = 0; j < KT; ++j) {
+    accb[j] = 0.f;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) acc[j][e] = 0.f;
+  }
+  if (rl < lanes) {
+    for (long long r = r0 + rl; r < r1; r += 2LL * lanes) {  // two rows in flight
+      const long long rb = r + lanes;
+      const bool two = rb < r1;
+      const uint4 raw0 = __ldg(reinterpret_cast<const uint4*>(h + r * C) + piece);
+      const uint4 raw1 = two ? __ldg(reinterpret_cast<const uint4*>(h + rb * C) + piece) : make_uint4(0u, 0u, 0u, 0u);
+      const long long b0 = r / n_points, n0 = r - b0 * n_points;
+      const long long b1 = two ? rb / n_points : b0, n1 = two ? rb - b1 * n_points : n0;
+      const float* g0 = dl + (b0 * k) * n_points + n0;
+      const float* g1 = dl + (b1 * k) * n_points + n1;
+      float gj0[KT], gj1[KT];
+#pragma unroll
+      for (int j = 0; j < KT; ++j) {
+        gj0[j] = j < k ? __ldg(g0 + (long long)j * n_points) : 0.f;
+        gj1[j] = (j < k && two) ? __ldg(g1 + (long long)j * n_points) : 0.f;
+      }
+      const F8 v0 = unpack8(raw0), v1 = unpack8(raw1);
+#pragma unroll
+      for (int j = 0; j < KT; ++j) {
+        if (j < k) {
+          accb[j] += gj0[j] + gj1[j];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) acc[j][e] = fmaf(gj0[j], v0.v[e], fmaf(gj1[j], v1.v[e], acc[j][e]));
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < KT; ++j) {
+    if (j < k) {  // (k is block-uniform: the barriers below are reached by every thread)
+      if (rl < lanes) {
+        float* dst = s_red + (size_t)rl * C + piece * 8;
+#pragma unroll
+        for (int e = 0; e < 8; ++e) dst[e] = acc[j][e];
+      }
+      if (piece == 0 && rl < lanes) s_b[rl] = accb[j];
+      __syncthreads();
+      for (int c = threadIdx.x; c < C; c += 256) {
+        float t = 0.f;
+        for (int l = 0; l < lanes; ++l) t += s_red[(size_t)l * C + c];
+        atomicAdd(dw + (size_t)j * C + c, t);
+      }
+      if (threadIdx.x == 0) {
+        float t = 0.f;
+        for (int l = 0; l < lanes; ++l) t += s_b[l];
+        atomicAdd(dbias + j, t);
+      }
+      __syncthreads();
+    }
+  }
+}
+
 static unsigned grid_for(long long work, int threads) { return (unsigned)((work + threads - 1) / threads); }
 
 }  // namespace trn
@@ -522,11 +826,12 @@ extern "C" int s4g_train_bn_act_bf16(const void* y, const float* scale, const fl
 }
 
 extern "C" int s4g_train_bn_act_maxpool_bf16(const void* y, const float* scale, const float* shift, void* out, uint8_t* arg,
-                                             long long G, int K, int C, int relu, void* stream) {
+                                             void* ymax, long long G, int K, int C, int relu, void* stream) {
   S4G_CHECK_ARG(y && scale && shift && out && arg && G > 0 && K > 0 && K <= 255, "train_bn_act_maxpool: bad arguments");
   TRN_CHECK_C(C);
   bn_act_maxpool_kernel<<<grid_for(G * (C >> 3), 256), 256, 0, (cudaStream_t)stream>>>(
-      reinterpret_cast<const bf16*>(y), scale, shift, reinterpret_cast<bf16*>(out), arg, G, K, C, relu);
+      reinterpret_cast<const bf16*>(y), scale, shift, reinterpret_cast<bf16*>(out), arg, reinterpret_cast<bf16*>(ymax), G, K, C,
+      relu);
   S4G_LAUNCH_CHECK("train_bn_act_maxpool");
   return S4G_OK;
 }
@@ -544,10 +849,28 @@ extern "C" int s4g_train_bn_bwd_reduce_bf16(const void* dz, const uint8_t* arg, 
   S4G_CHECK_ARG(lanes >= 1, "train_bn_bwd_reduce: too many channels");
   const unsigned thresh = drop_p > 0.f ? (unsigned)((double)drop_p * 4294967296.0) : 0u;
   const Upstream up{reinterpret_cast<const bf16*>(dz), arg, K};
-  static int variant = -1;  // S4G_BWD_REDUCE_VARIANT=1: 2 rows in flight x 3 blocks per SM instead of 4 x 2 (A/B measurements)
+  // S4G_BWD_REDUCE_VARIANT (A/B measurements): 0 (default) = rows staged by the copy engine for dense upstream gradients,
+  // 1 = registers, 2 rows in flight x 3 blocks per SM, 2 = registers, 4 x 2
+  static int variant = -1;
   if (variant < 0) { const char* e = getenv("S4G_BWD_REDUCE_VARIANT"); variant = e ? atoi(e) : 0; }
   const size_t sm = (size_t)lanes * pieces * 16 * sizeof(float);
-  if (variant == 1)
+  if (variant == 0 && K == 0 && C <= 2048 && (((uintptr_t)dz | (uintptr_t)y) & 15) == 0) {
+    const int lanes_s = kStgConsumers / pieces;
+    const int R = kStgRowsPerLane * lanes_s;
+    const size_t tile_bytes = (size_t)R * C * 2;
+    const size_t smem = kStgStages * 2 * tile_bytes;  // (>= the 32 KB the final reduction needs)
+    static bool attr = false;
+    if (!attr) {
+      S4G_CUDA(cudaFuncSetAttribute(bn_bwd_reduce_staged_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+      attr = true;
+    }
+    const long long n_tiles = (P + R - 1) / R;
+    const int sms = s4g::num_sms();
+    const unsigned grid = (unsigned)(n_tiles < sms ? n_tiles : sms);
+    bn_bwd_reduce_staged_kernel<<<grid, kStgThreads, smem, s>>>(reinterpret_cast<const bf16*>(dz), reinterpret_cast<const bf16*>(y),
+                                                                scale, shift, P, C, relu, seed, thresh, 1.f / (1.f - drop_p),
+                                                                sums2c);
+  } else if (variant == 1)
     bn_bwd_reduce_kernel<2, 3><<<grid_for(P, kStatRows), kStatThreads, sm, s>>>(
         up, reinterpret_cast<const bf16*>(y), scale, shift, P, C, relu, seed, thresh, 1.f / (1.f - drop_p), sums2c);
   else
@@ -565,9 +888,28 @@ extern "C" int s4g_train_bn_bwd_apply_bf16(const void* dz, const uint8_t* arg, i
   TRN_CHECK_C(C);
   const unsigned thresh = drop_p > 0.f ? (unsigned)((double)drop_p * 4294967296.0) : 0u;
   const Upstream up{reinterpret_cast<const bf16*>(dz), arg, K};
-  bn_bwd_apply_kernel<<<grid_for(P, kEltRows), 256, 0, (cudaStream_t)stream>>>(
-      up, reinterpret_cast<const bf16*>(y), scale, shift, ka, kb, kc, P, C, relu, seed, thresh, 1.f / (1.f - drop_p),
-      reinterpret_cast<bf16*>(dy));
+  static int variant = -1;  // S4G_BWD_APPLY_VARIANT (A/B measurements): 0 (default) = rows staged by the copy engine, 1 = registers
+  if (variant < 0) { const char* e = getenv("S4G_BWD_APPLY_VARIANT"); variant = e ? atoi(e) : 0; }
+  if (variant == 0 && (((uintptr_t)dz | (uintptr_t)y | (uintptr_t)dy) & 15) == 0) {
+    constexpr int kRpl = 4, kStages = 3, kCons = 480;
+    const int pieces = C >> 3, lanes_s = kCons / pieces;
+    const int R = kRpl * lanes_s;
+    const size_t smem = (size_t)kStages * 2 * R * C * 2;
+    static bool attr = false;
+    if (!attr) {
+      S4G_CUDA(cudaFuncSetAttribute(bn_bwd_apply_staged_kernel<kRpl, kStages, kCons>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+      attr = true;
+    }
+    const long long n_tiles = (P + R - 1) / R;
+    const int sms = s4g::num_sms();
+    bn_bwd_apply_staged_kernel<kRpl, kStages, kCons><<<(unsigned)(n_tiles < sms ? n_tiles : sms), kCons + 32, smem, (cudaStream_t)stream>>>(
+        up, reinterpret_cast<const bf16*>(y), scale, shift, ka, kb, kc, P, C, relu, seed, thresh, 1.f / (1.f - drop_p),
+        reinterpret_cast<bf16*>(dy));
+  } else {
+    bn_bwd_apply_kernel<<<grid_for(P, kEltRows), 256, 0, (cudaStream_t)stream>>>(
+        up, reinterpret_cast<const bf16*>(y), scale, shift, ka, kb, kc, P, C, relu, seed, thresh, 1.f / (1.f - drop_p),
+        reinterpret_cast<bf16*>(dy));
+  }
   S4G_LAUNCH_CHECK("train_bn_bwd_apply");
   return S4G_OK;
 }
@@ -651,5 +993,32 @@ extern "C" int s4g_train_head_logits_bwd(const float* dlogits, const float* w, v
   head_logits_bwd_kernel<<<grid_for(P, 256), 256, sizeof(float) * k * C, (cudaStream_t)stream>>>(
       dlogits, w, reinterpret_cast<bf16*>(dh), P, C, k, n_points);
   S4G_LAUNCH_CHECK("train_head_logits_bwd");
+  return S4G_OK;
+}
+
+extern "C" int s4g_train_sum_bf16(const void* a, const void* b, const void* c, const void* d, void* out, long long n,
+                                  void* stream) {
+  S4G_CHECK_ARG(a && b && out && n >= 0 && n % 8 == 0 && (c || !d), "train_sum_bf16: element count must be a multiple of 8");
+  if (n == 0) return S4G_OK;
+  sum_bf16_kernel<<<grid_for(n / 8, 256), 256, 0, (cudaStream_t)stream>>>(
+      reinterpret_cast<const uint4*>(a), reinterpret_cast<const uint4*>(b), reinterpret_cast<const uint4*>(c),
+      reinterpret_cast<const uint4*>(d), reinterpret_cast<uint4*>(out), n / 8);
+  S4G_LAUNCH_CHECK("train_sum_bf16");
+  return S4G_OK;
+}
+
+extern "C" int s4g_train_head_logits_dw(const float* dlogits, const void* h, float* dw, float* dbias, long long P, int C, int k,
+                                        int n_points, void* stream) {
+  S4G_CHECK_ARG(dlogits && h && dw && dbias && P > 0 && k > 0 && k <= kMaxLogits && n_points > 0 && P % n_points == 0,
+                "train_head_logits_dw: bad arguments");
+  TRN_CHECK_C(C);
+  const size_t smem = sizeof(float) * 2048;  // lanes * C = (256 / pieces) * pieces * 8 <= 2048
+  const unsigned grid = grid_for(P, kDwRows);
+  cudaStream_t st = (cudaStream_t)stream;
+  const bf16* hh = reinterpret_cast<const bf16*>(h);
+  if (k <= 4) head_logits_dw_kernel<4><<<grid, 256, smem, st>>>(dlogits, hh, dw, dbias, P, C, k, n_points);
+  else if (k <= 9) head_logits_dw_kernel<9><<<grid, 256, smem, st>>>(dlogits, hh, dw, dbias, P, C, k, n_points);
+  else head_logits_dw_kernel<kMaxLogits><<<grid, 256, smem, st>>>(dlogits, hh, dw, dbias, P, C, k, n_points);
+  S4G_LAUNCH_CHECK("train_head_logits_dw");
   return S4G_OK;
 }

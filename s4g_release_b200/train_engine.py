@@ -49,11 +49,32 @@ def gemm(a, b, stats=False):
     return c if ldc == N else c[:, :N]
 
 
+def gemm_bwd(a, b, prev_y, prev_scale, prev_shift, relu=True, seed=0, drop_p=0.0):
+    """Input-gradient GEMM of block l whose result is the upstream gradient of block l-1 (``prev_*``: that block's
+    pre-BatchNorm rows [P, N] and folded scale / shift): returns (g [P, N] bf16, MASKED with block l-1's ReLU' / dropout,
+    sums fp64 [2N] = [sum g | sum g * prev_y]) — the first pass of block l-1's BatchNorm backward done in the epilogue."""
+    assert a.dtype == BF16 and b.dtype == BF16 and a.stride(1) == 1 and b.stride(1) == 1 and a.shape[1] == b.shape[1]
+    P, K = a.shape
+    N = b.shape[0]
+    assert prev_y.shape == (P, N) and prev_y.stride(1) == 1 and N % 8 == 0
+    c = torch.empty((P, N), dtype=BF16, device=a.device)
+    sums = torch.empty(2 * N, dtype=torch.float64, device=a.device)
+    check(lib.s4g_gemm_bf16_bwd(ptr(a), a.stride(0), ptr(b), b.stride(0), ptr(c), N, P, N, K, ptr(prev_y), prev_y.stride(0),
+                                ptr(prev_scale), ptr(prev_shift), 1 if relu else 0, seed, drop_p, ptr(sums),
+                                stream_ptr(a.device)), "gemm_bf16_bwd")
+    return c, sums
+
+
 # BatchNorm statistics inside the GEMM epilogue (s4g_gemm_bf16_stats) or as a separate pass over the stored output.
 # Measured at 32 scenes (profiles/r02/train_kernels.md): with the statistics fused, the 4 epilogue warps need ~5 800
 # cycles per 128 x 128 tile (shuffle butterfly) against ~2 800 cycles of HBM time, so the memory-bound layers run at
 # 1.2-3.2 TB/s; the plain GEMM runs at 6.0-6.8 TB/s and the separate pass at ~5 TB/s — cheaper in total.  Kept selectable.
 FUSED_STATS = True
+# backward, pass 1 of a block's BatchNorm (sum g, sum g*y): (a) for a block whose upstream gradient comes out of the next
+# block's input-gradient GEMM, in that GEMM's epilogue (gemm_bwd); (b) for a pooled block, over the G pooled rows only
+# (the gradient is zero off the arg-max rows; the forward keeps y at the arg-max).  Both selectable for A/B measurements.
+FUSED_BWD_REDUCE = False  # (measured: 79.0 vs 78.6 ms per step — the fused epilogue is instruction-bound, see csrc/gemm_bf16.cu)
+SPARSE_POOL_REDUCE = True
 
 
 def colstats_raw(y):
@@ -124,27 +145,40 @@ class Block:
             G = P // pool_k
             z = torch.empty((G, self.cout), dtype=BF16, device=dev)
             arg = torch.empty((G, self.cout), dtype=torch.uint8, device=dev)
-            check(lib.s4g_train_bn_act_maxpool_bf16(ptr(y), ptr(scale), ptr(shift), ptr(z), ptr(arg), G, pool_k, self.cout, 1,
+            ymax = torch.empty((G, self.cout), dtype=BF16, device=dev) if SPARSE_POOL_REDUCE else None
+            check(lib.s4g_train_bn_act_maxpool_bf16(ptr(y), ptr(scale), ptr(shift), ptr(z), ptr(arg),
+                                                    ptr(ymax) if ymax is not None else None, G, pool_k, self.cout, 1,
                                                     stream_ptr(dev)), "train_bn_act_maxpool")
         else:
-            arg = None
+            arg = ymax = None
             z = torch.empty((P, self.cout), dtype=BF16, device=dev)
             check(lib.s4g_train_bn_act_bf16(ptr(y), ptr(scale), ptr(shift), ptr(z), P, self.cout, 1, seed, self.drop_p,
                                             stream_ptr(dev)), "train_bn_act")
-        self.saved = (x, y, wb, mean_rstd, scale, shift, arg, pool_k, seed)
+        self.saved = (x, y, wb, mean_rstd, scale, shift, arg, pool_k, seed, ymax)
         return (z, arg) if pool_k else z
 
-    def backward(self, dz, need_dx=True):
+    def backward(self, dz, need_dx=True, prev=None, pre=None):
         """dz: [P, cout] bf16 (or the pooled gradient [G, cout] when the forward pooled).  Accumulates the parameter
-        gradients; returns dx [P, Kp or Cf] bf16 (None when not needed)."""
-        x, y, wb, mean_rstd, scale, shift, arg, pool_k, seed = self.saved
+        gradients; returns dx [P, Kp or Cf] bf16 (None when not needed).
+        ``pre``: dz is already masked and these are its sums (it came out of gemm_bwd).  ``prev``: the block that produced
+        this block's input — dx is then returned as (masked dx, sums) for prev.backward(..., pre=sums)."""
+        x, y, wb, mean_rstd, scale, shift, arg, pool_k, seed, ymax = self.saved
         self.saved = None
         P, C = y.shape
         dev = y.device
-        sums = torch.empty(2 * C, dtype=torch.float64, device=dev)
         drop = 0.0 if pool_k else self.drop_p
-        check(lib.s4g_train_bn_bwd_reduce_bf16(ptr(dz), ptr(arg) if pool_k else None, pool_k, ptr(y), ptr(scale), ptr(shift),
-                                               P, C, 1, seed, drop, ptr(sums), stream_ptr(dev)), "train_bn_bwd_reduce")
+        relu = 1
+        if pre is not None:
+            sums, relu, drop = pre, 0, 0.0
+        else:
+            sums = torch.empty(2 * C, dtype=torch.float64, device=dev)
+            if pool_k and ymax is not None:  # the G arg-max rows carry the whole gradient
+                check(lib.s4g_train_bn_bwd_reduce_bf16(ptr(dz), None, 0, ptr(ymax), ptr(scale), ptr(shift), P // pool_k, C, 1,
+                                                       seed, 0.0, ptr(sums), stream_ptr(dev)), "train_bn_bwd_reduce")
+            else:
+                check(lib.s4g_train_bn_bwd_reduce_bf16(ptr(dz), ptr(arg) if pool_k else None, pool_k, ptr(y), ptr(scale),
+                                                       ptr(shift), P, C, 1, seed, drop, ptr(sums), stream_ptr(dev)),
+                      "train_bn_bwd_reduce")
         # dgamma += sum g xhat, dbeta += sum g, and dy = ka * g + kb * y + kc folded per channel — one launch
         gw, gb = _grad_buffer(self.bn.weight), _grad_buffer(self.bn.bias)
         coef = torch.empty(3 * C, dtype=torch.float32, device=dev)
@@ -152,7 +186,7 @@ class Block:
                                             stream_ptr(dev)), "train_bn_bwd_finalize")
         dy = torch.empty((P, C), dtype=BF16, device=dev)
         check(lib.s4g_train_bn_bwd_apply_bf16(ptr(dz), ptr(arg) if pool_k else None, pool_k, ptr(y), ptr(scale), ptr(shift),
-                                              ptr(coef), ptr(coef[C:]), ptr(coef[2 * C:]), P, C, 1, seed, drop, ptr(dy),
+                                              ptr(coef), ptr(coef[C:]), ptr(coef[2 * C:]), P, C, relu, seed, drop, ptr(dy),
                                               stream_ptr(dev)), "train_bn_bwd_apply")
         # dW = dY^T X: a plain library GEMM (bf16 operands, fp32 result)
         dwb = torch.mm(dy.t(), x, out_dtype=torch.float32)
@@ -166,7 +200,30 @@ class Block:
         cols = self.cf if self.cf is not None else wb.shape[1]
         if cols == 0:
             return None
-        return gemm(dy, wb[:, :cols].t().contiguous())  # dX = dY · W  (B operand = W^T rows)
+        wt = wb[:, :cols].t().contiguous()  # dX = dY · W  (B operand = W^T rows)
+        if prev is None:
+            return gemm(dy, wt)
+        py, pscale, pshift, pseed = prev.saved[1], prev.saved[4], prev.saved[5], prev.saved[8]
+        return gemm_bwd(dy, wt, py, pscale, pshift, relu=True, seed=pseed, drop_p=prev.drop_p)
+
+
+def chain_backward(blocks, dz, need_dx=True):
+    """backward through the blocks of one shared MLP, last to first; returns the gradient of the chain's input rows"""
+    pre = None
+    for j in reversed(range(len(blocks))):
+        prev = blocks[j - 1] if (j > 0 and FUSED_BWD_REDUCE) else None
+        out = blocks[j].backward(dz, need_dx=(j > 0 or need_dx), prev=prev, pre=pre)
+        dz, pre = out if prev is not None else (out, None)
+    return dz
+
+
+def _sum_rows(parts):
+    """sum of 2-4 equally shaped contiguous bf16 row matrices in one pass (fp32 sums, one rounding)"""
+    assert 2 <= len(parts) <= 4 and all(p.dtype == BF16 and p.is_contiguous() and p.shape == parts[0].shape for p in parts)
+    out = torch.empty_like(parts[0])
+    q = [ptr(p) for p in parts] + [None] * (4 - len(parts))
+    check(lib.s4g_train_sum_bf16(q[0], q[1], q[2], q[3], ptr(out), out.numel(), stream_ptr(out.device)), "train_sum_bf16")
+    return out
 
 
 def _grad_buffer(param):
@@ -285,12 +342,11 @@ class TrainEngine:
         dz = torch.empty_like(h)
         check(lib.s4g_train_head_logits_bwd(ptr(dl), ptr(w), ptr(dz), h.shape[0], h.shape[1], c, n, stream_ptr(h.device)),
               "train_head_logits_bwd")
-        dl_rows = dl.permute(0, 2, 1).reshape(B * n, c)
-        _accumulate(logit.weight, torch.mm(dl_rows.t().to(BF16), h, out_dtype=torch.float32).reshape(logit.weight.shape))
-        _accumulate(logit.bias, dl_rows.sum(0))
-        for blk in reversed(blocks):
-            dz = blk.backward(dz)
-        return dz
+        # dW [c][C] and dbias [c] of the final conv: one pass over h with fp32 atomics into param.grad (as library calls:
+        # four skinny GEMMs of 0.2-0.5 ms each for 0.03 ms of traffic)
+        check(lib.s4g_train_head_logits_dw(ptr(dl), ptr(h), ptr(_grad_buffer(logit.weight)), ptr(_grad_buffer(logit.bias)),
+                                           h.shape[0], h.shape[1], c, n, stream_ptr(h.device)), "train_head_logits_dw")
+        return chain_backward(blocks, dz)
 
     def _predictions(self, leaves):
         return {"score": leaves[0], "frame_R": leaves[1], "frame_t": leaves[2], "movable_logits": torch.sigmoid(leaves[3])}
@@ -305,24 +361,19 @@ class TrainEngine:
     # ------------------------------------------------------------------ backward
     def backward(self):
         """after ``total_loss.backward()`` filled the head leaves' gradients"""
-        d_point = None
-        for k, leaf in enumerate(self._head_leaves):
-            dz = self._head_backward(k, leaf)
-            d_point = dz.float() if d_point is None else d_point.add_(dz)
+        dzs = [self._head_backward(k, leaf) for k, leaf in enumerate(self._head_leaves)]
         self._head_leaves = self._point_feat = None
-        self._trunk_backward(d_point)
+        self._trunk_backward(_sum_rows(dzs))
 
-    def _trunk_backward(self, d_point):
-        dev = d_point.device
+    def _trunk_backward(self, d_out):
+        """d_out: gradient of the per-point features [B*N, C] bf16"""
+        dev = d_out.device
         # gradient buffers of the level features (fp32: they receive scatter-adds), index = level
         lv_grad = [None if s is None else torch.zeros(s, dtype=torch.float32, device=dev) for s in self._lv_shapes]
         n_fp = len(self.fp)
-        d_out = d_point.to(BF16)  # gradient of the current propagation level's OUTPUT rows
-        del d_point
+        # d_out = gradient of the current propagation level's OUTPUT rows
         for i in reversed(range(n_fp)):
-            dz = d_out
-            for blk in reversed(self.fp[i]):
-                dz = blk.backward(dz)
+            dz = chain_backward(self.fp[i], d_out)
             idx3, w, B, Nk, Nq, c2, c1 = self._fp_ctx[i]
             # dz rows = [d interpolated (c2) | d dense skip (c1)]
             if c1:
@@ -339,8 +390,7 @@ class TrainEngine:
             nbr, B, N, M, K, cf = self._sa_ctx[i]
             dz = lv_grad[i + 1].to(BF16)  # pooled gradient [B*M, cout]
             lv_grad[i + 1] = None
-            for j in reversed(range(len(blocks))):
-                dz = blocks[j].backward(dz, need_dx=(j > 0 or cf > 0))
+            dz = chain_backward(blocks, dz, need_dx=cf > 0)
             if cf > 0:
                 check(lib.s4g_train_group_rows_bwd(ptr(dz), dz.stride(0), ptr(nbr), B, N, M, K, cf, ptr(lv_grad[i]),
                                                    stream_ptr(dev)), "train_group_rows_bwd")
@@ -372,7 +422,7 @@ class TrainEngine:
             B, n = self._batch, self._n_points
             zeros = [torch.zeros((B, logit.weight.shape[0], n), dtype=torch.float32, device=points.device)
                      for _, logit in self.heads]
-            losses, d_point = {}, None
+            losses, dzs = {}, []
             for k in range(4):
                 with torch.no_grad():
                     leaf = self._head_forward(k, point_feat)
@@ -382,9 +432,10 @@ class TrainEngine:
                     term.backward()
                 losses[self.LOSS_KEYS[k]] = term.detach()
                 with torch.no_grad():
-                    dz = self._head_backward(k, leaf)
-                    d_point = dz.float() if d_point is None else d_point.add_(dz)
-                del leaf, dz
+                    dzs.append(self._head_backward(k, leaf))  # (bf16 [B*N, C]: 0.4 GB each at 32 scenes)
+                del leaf
             with torch.no_grad():
-                self._trunk_backward(d_point)
+                d_out = _sum_rows(dzs)
+                del dzs
+                self._trunk_backward(d_out)
         return losses

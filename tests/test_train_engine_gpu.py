@@ -74,6 +74,200 @@ def test_gemm_weight_stationary_schedule_is_bit_identical(P, N, K):
     assert (c1.double() - want).abs().max().item() <= 1e-2 * max(1.0, want.abs().max().item())
 
 
+@pytest.mark.parametrize("P,N,K", [(148 * 2 * 128 + 77, 128, 128), (70001, 256, 40), (333, 72, 264), (20000, 1024, 128),
+                                   (40000, 512, 1024)])
+def test_gemm_epilogue_groups_are_bit_identical(P, N, K):
+    """one or two groups of epilogue warps (tile parity -> group): same stored bits, same fused statistics up to
+    summation order — on the weight-stationary and on the streaming schedule"""
+    from s4g_release_b200._lib import lib
+    from s4g_release_b200.train_engine import gemm
+    g = torch.Generator().manual_seed(P % 1000 + N + K)
+    a = torch.randn(P, K, generator=g).cuda().to(BF)
+    b = (torch.randn(N, K, generator=g) / np.sqrt(K)).cuda().to(BF)
+    prev = lib.s4g_gemm_bf16_set_epilogue_groups(1)
+    try:
+        c1, s1 = gemm(a, b, stats=True)
+        p1 = gemm(a, b)
+        lib.s4g_gemm_bf16_set_epilogue_groups(2)
+        c2, s2 = gemm(a, b, stats=True)
+        p2 = gemm(a, b)
+    finally:
+        lib.s4g_gemm_bf16_set_epilogue_groups(prev)
+    torch.cuda.synchronize()
+    assert torch.equal(c1, c2) and torch.equal(p1, p2) and torch.equal(c1, p1)
+    np.testing.assert_allclose(s1.cpu().numpy(), s2.cpu().numpy(), rtol=1e-5, atol=1e-2)
+    want = a.double() @ b.double().t()
+    assert (c2.double() - want).abs().max().item() <= 1e-2 * max(1.0, want.abs().max().item())
+
+
+@pytest.mark.parametrize("groups", [1, 2])
+@pytest.mark.parametrize("P,N,K,drop", [(148 * 2 * 128 + 77, 128, 128, 0.0), (70001, 256, 40, 0.5), (333, 72, 264, 0.0),
+                                        (20000, 512, 1024, 0.3), (5000, 8, 128, 0.0)])
+def test_gemm_bwd_epilogue_masks_and_reduces(P, N, K, drop, groups):
+    """s4g_gemm_bf16_bwd = plain GEMM, then the ReLU' / dropout mask of the previous block, then the two column sums of
+    the BatchNorm backward — against the plain GEMM + torch masking, and against s4g_train_bn_bwd_reduce_bf16 run on the
+    UNMASKED result (the path it replaces)"""
+    from s4g_release_b200._lib import check, lib, ptr, stream_ptr
+    from s4g_release_b200.train_engine import gemm, gemm_bwd
+    g = torch.Generator().manual_seed(P % 1000 + N + K)
+    a = torch.randn(P, K, generator=g).cuda().to(BF)
+    b = (torch.randn(N, K, generator=g) / np.sqrt(K)).cuda().to(BF)
+    y = torch.randn(P, N, generator=g).cuda().to(BF)
+    scale = (torch.rand(N, generator=g) + 0.5).cuda()
+    shift = (torch.randn(N, generator=g) * 0.3).cuda()
+    seed = 4242
+    prev = lib.s4g_gemm_bf16_set_epilogue_groups(groups)
+    try:
+        c, sums = gemm_bwd(a, b, y, scale, shift, relu=True, seed=seed, drop_p=drop)
+        plain = gemm(a, b)
+    finally:
+        lib.s4g_gemm_bf16_set_epilogue_groups(prev)
+    plain = plain.contiguous()
+    # the path it replaces: reduce over the unmasked gradient (the kernel masks on the fly)
+    old = torch.empty(2 * N, dtype=torch.float64, device="cuda")
+    check(lib.s4g_train_bn_bwd_reduce_bf16(ptr(plain), None, 0, ptr(y), ptr(scale), ptr(shift), P, N, 1, seed, drop, ptr(old),
+                                           stream_ptr(plain.device)), "reduce")
+    torch.cuda.synchronize()
+    mask = (y.float() * scale + shift) > 0
+    if drop == 0.0:
+        want = torch.where(mask, plain, torch.zeros_like(plain))
+        assert torch.equal(c, want)
+    else:
+        # kept elements are scaled by 1 / (1 - p) BEFORE the bf16 rounding; dropped / masked ones are exactly zero
+        keep = c != 0
+        assert not (keep & ~mask).any()
+        frac = keep.float().sum().item() / max(mask.float().sum().item(), 1.0)
+        assert abs(frac - (1.0 - drop)) < 0.02, frac
+        ratio = (c.float()[keep] / plain.float()[keep])
+        assert (ratio - 1.0 / (1.0 - drop)).abs().max().item() <= 3e-2
+    s_g = c.double().sum(0)
+    s_gy = (c.double() * y.double()).sum(0)
+    np.testing.assert_allclose(sums[:N].cpu().numpy(), s_g.cpu().numpy(), rtol=1e-4, atol=2e-2)
+    np.testing.assert_allclose(sums[N:].cpu().numpy(), s_gy.cpu().numpy(), rtol=1e-4, atol=2e-2)
+    tol = 2e-2 * max(1.0, old.abs().max().item()) if drop else 2e-2
+    np.testing.assert_allclose(sums.cpu().numpy(), old.cpu().numpy(), rtol=1e-3 if drop == 0 else 2e-2, atol=tol)
+
+
+@pytest.mark.parametrize("P,C,drop", [(70001, 136, 0.0), (100, 1024, 0.0), (5000, 8, 0.0), (300000, 128, 0.4), (4097, 520, 0.0),
+                                      (1, 64, 0.0)])
+def test_bn_bwd_reduce_dense_against_torch(P, C, drop):
+    """the (copy-engine staged) first pass of the BatchNorm backward: sum g, sum g*y with g = dz * relu' * dropout"""
+    from s4g_release_b200._lib import check, lib, ptr, stream_ptr
+    g = torch.Generator().manual_seed(P + C)
+    dz = torch.randn(P, C, generator=g).cuda().to(BF)
+    y = torch.randn(P, C, generator=g).cuda().to(BF)
+    scale = (torch.rand(C, generator=g) + 0.5).cuda()
+    shift = (torch.randn(C, generator=g) * 0.3).cuda()
+    sums = torch.empty(2 * C, dtype=torch.float64, device="cuda")
+    st = stream_ptr(dz.device)
+    check(lib.s4g_train_bn_bwd_reduce_bf16(ptr(dz), None, 0, ptr(y), ptr(scale), ptr(shift), P, C, 1, 77, drop, ptr(sums), st), "r")
+    torch.cuda.synchronize()
+    gm = torch.where((y.float() * scale + shift) > 0, dz.float(), torch.zeros(()).cuda()).double()
+    if drop == 0.0:
+        np.testing.assert_allclose(sums[:C].cpu().numpy(), gm.sum(0).cpu().numpy(), rtol=1e-4, atol=2e-2)
+        np.testing.assert_allclose(sums[C:].cpu().numpy(), (gm * y.double()).sum(0).cpu().numpy(), rtol=1e-4, atol=2e-2)
+    else:
+        # the mask is the one bn_act applied in the forward: rebuild it from the forward kernel's zeros
+        z = torch.empty_like(y)
+        check(lib.s4g_train_bn_act_bf16(ptr(y), ptr(scale), ptr(shift), ptr(z), P, C, 1, 77, drop, st), "act")
+        torch.cuda.synchronize()
+        kept = (z != 0) | ~((y.float() * scale + shift) > 0)  # dropped = positive pre-activation that came out as 0
+        gk = torch.where(kept, gm / (1.0 - drop), torch.zeros((), dtype=torch.float64).cuda())
+        np.testing.assert_allclose(sums[:C].cpu().numpy(), gk.sum(0).cpu().numpy(), rtol=1e-3, atol=5e-2)
+        np.testing.assert_allclose(sums[C:].cpu().numpy(), (gk * y.double()).sum(0).cpu().numpy(), rtol=1e-3, atol=5e-2)
+
+
+@pytest.mark.parametrize("P,C,K,drop", [(70001, 136, 0, 0.0), (96, 1024, 0, 0.0), (5000, 8, 0, 0.0), (300000, 128, 0, 0.4),
+                                        (4097 * 16, 264, 16, 0.0), (64 * 1000, 128, 64, 0.0), (1, 64, 0, 0.0)])
+def test_bn_bwd_apply_against_torch(P, C, K, drop):
+    """the (copy-engine staged) second pass: dy = ka * g + kb * y + kc, g = dz * relu' * dropout, dense or routed through
+    the arg-max of a pooled block"""
+    from s4g_release_b200._lib import check, lib, ptr, stream_ptr
+    g = torch.Generator().manual_seed(P + C)
+    y = torch.randn(P, C, generator=g).cuda().to(BF)
+    scale = (torch.rand(C, generator=g) + 0.5).cuda()
+    shift = (torch.randn(C, generator=g) * 0.3).cuda()
+    ka, kb, kc = [(torch.randn(C, generator=g) * 0.5).cuda() for _ in range(3)]
+    st = stream_ptr(y.device)
+    pos = (y.float() * scale + shift) > 0
+    if K:
+        G = P // K
+        dz = torch.randn(G, C, generator=g).cuda().to(BF)
+        arg = torch.randint(0, K, (G, C), generator=g, dtype=torch.uint8).cuda()
+        routed = torch.zeros(G, K, C, device="cuda")
+        routed.scatter_(1, arg.long().unsqueeze(1), dz.float().unsqueeze(1))
+        gm = torch.where(pos, routed.reshape(P, C), torch.zeros(()).cuda())
+    else:
+        dz = torch.randn(P, C, generator=g).cuda().to(BF)
+        arg = None
+        gm = torch.where(pos, dz.float(), torch.zeros(()).cuda())
+    if drop:
+        z = torch.empty_like(y)
+        check(lib.s4g_train_bn_act_bf16(ptr(y), ptr(scale), ptr(shift), ptr(z), P, C, 1, 77, drop, st), "act")
+        gm = torch.where((z != 0) | ~pos, gm / (1.0 - drop), torch.zeros(()).cuda())
+    dy = torch.empty(P, C, dtype=BF, device="cuda")
+    check(lib.s4g_train_bn_bwd_apply_bf16(ptr(dz), ptr(arg) if K else None, K, ptr(y), ptr(scale), ptr(shift), ptr(ka), ptr(kb),
+                                          ptr(kc), P, C, 1, 77, drop, ptr(dy), st), "apply")
+    torch.cuda.synchronize()
+    want = ka * gm + kb * y.float() + kc
+    assert (dy.float() - want).abs().max().item() <= 2 ** -7 * max(1.0, want.abs().max().item())
+
+
+def test_pooled_reduce_over_the_arg_max_rows():
+    """BatchNorm-backward sums of a pooled block from the G arg-max rows (y kept by bn_act_maxpool) = the dense kernel
+    that routes the pooled gradient over all G * K rows"""
+    from s4g_release_b200._lib import check, lib, ptr, stream_ptr
+    G, K, C = 3000, 16, 136
+    g = torch.Generator().manual_seed(11)
+    y = torch.randn(G * K, C, generator=g).cuda().to(BF)
+    scale = (torch.rand(C, generator=g) + 0.5).cuda()
+    shift = (torch.randn(C, generator=g) * 0.3).cuda()
+    z = torch.empty(G, C, dtype=BF, device="cuda")
+    arg = torch.empty(G, C, dtype=torch.uint8, device="cuda")
+    ymax = torch.empty(G, C, dtype=BF, device="cuda")
+    st = stream_ptr(y.device)
+    check(lib.s4g_train_bn_act_maxpool_bf16(ptr(y), ptr(scale), ptr(shift), ptr(z), ptr(arg), ptr(ymax), G, K, C, 1, st), "pool")
+    torch.cuda.synchronize()
+    picked = torch.gather(y.reshape(G, K, C), 1, arg.long().unsqueeze(1))[:, 0]
+    assert torch.equal(ymax, picked)
+    dz = torch.randn(G, C, generator=g).cuda().to(BF)
+    dense = torch.empty(2 * C, dtype=torch.float64, device="cuda")
+    sparse = torch.empty(2 * C, dtype=torch.float64, device="cuda")
+    check(lib.s4g_train_bn_bwd_reduce_bf16(ptr(dz), ptr(arg), K, ptr(y), ptr(scale), ptr(shift), G * K, C, 1, 0, 0.0, ptr(dense), st), "dense")
+    check(lib.s4g_train_bn_bwd_reduce_bf16(ptr(dz), None, 0, ptr(ymax), ptr(scale), ptr(shift), G, C, 1, 0, 0.0, ptr(sparse), st), "sparse")
+    torch.cuda.synchronize()
+    np.testing.assert_allclose(sparse.cpu().numpy(), dense.cpu().numpy(), rtol=1e-5, atol=1e-3)
+
+
+def test_fused_and_separate_backward_reduce_agree():
+    """a 4-block chain with dropout, backward with the reduce fused into the input-gradient GEMMs vs the separate pass"""
+    from s4g_release_b200 import train_engine as te
+    dims = [64, 128, 64, 72, 32]
+    P = 5000
+    x = torch.randn(P, dims[0], generator=torch.Generator().manual_seed(9)).cuda().to(BF)
+    dz = torch.randn(P, dims[-1], generator=torch.Generator().manual_seed(10)).cuda().to(BF)
+    grads = []
+    for fused in (False, True):
+        blocks = [_block(dims[i], dims[i + 1], seed=20 + i) for i in range(4)]
+        chain = [te.Block(b, drop_p=0.3 if i in (1, 2) else 0.0) for i, b in enumerate(blocks)]
+        h = x
+        for j, f in enumerate(chain):
+            h = f.forward(h, seed=100 + j)
+        prev = te.FUSED_BWD_REDUCE
+        te.FUSED_BWD_REDUCE = fused
+        try:
+            dx = te.chain_backward(chain, dz)
+        finally:
+            te.FUSED_BWD_REDUCE = prev
+        torch.cuda.synchronize()
+        grads.append([dx.float()] + [b.conv.weight.grad.clone() for b in blocks] + [b.bn.weight.grad.clone() for b in blocks]
+                     + [b.bn.bias.grad.clone() for b in blocks])
+    for a, b in zip(*grads):
+        rel = (a - b).norm().item() / max(b.norm().item(), 1e-12)
+        assert rel <= 1e-2, rel  # (only the place of one bf16 rounding differs: g * 1/(1-p) is rounded when stored)
+
+
+
 def test_gemm_bf16_strided_operands():
     """A with a row stride larger than K (a column slice of a wider matrix), B^T made contiguous by the caller"""
     from s4g_release_b200.train_engine import gemm
@@ -179,6 +373,25 @@ def test_head_logits_kernels(k):
     check(lib.s4g_train_head_logits_bwd(ptr(dl), ptr(w), ptr(dh), B * n, C, k, n, stream_ptr(h.device)), "b")
     want_dh = dl.permute(0, 2, 1).reshape(B * n, k) @ w
     assert (dh.float() - want_dh).abs().max().item() <= 1e-2 * want_dh.abs().max().item()
+    # parameter gradients: accumulated INTO the buffers
+    dw = torch.full((k, C), 0.5, device="cuda")
+    db = torch.full((k,), -1.0, device="cuda")
+    check(lib.s4g_train_head_logits_dw(ptr(dl), ptr(h), ptr(dw), ptr(db), B * n, C, k, n, stream_ptr(h.device)), "dw")
+    rows = dl.permute(0, 2, 1).reshape(B * n, k).double()
+    want_dw = rows.t() @ h.double() + 0.5
+    want_db = rows.sum(0) - 1.0
+    assert (dw.double() - want_dw).abs().max().item() <= 1e-4 * max(1.0, want_dw.abs().max().item())
+    assert (db.double() - want_db).abs().max().item() <= 1e-4 * max(1.0, want_db.abs().max().item())
+
+
+@pytest.mark.parametrize("parts", [2, 3, 4])
+def test_sum_of_bf16_row_matrices(parts):
+    from s4g_release_b200.train_engine import _sum_rows
+    g = torch.Generator().manual_seed(parts)
+    xs = [torch.randn(1001, 136, generator=g).cuda().to(BF) for _ in range(parts)]
+    got = _sum_rows(xs)
+    want = sum(x.float() for x in xs).to(BF)
+    assert torch.equal(got, want) or (got.float() - want.float()).abs().max().item() <= 2 ** -7 * want.float().abs().max().item()
 
 
 def test_sequential_heads_equal_the_joint_step():
@@ -402,9 +615,8 @@ def test_four_block_chain_against_autograd():
     assert (h.float() - hr).abs().max().item() <= 5e-2 * max(1.0, hr.abs().max().item())
     dz = _bf(torch.randn(hr.shape, generator=torch.Generator().manual_seed(10))).cuda()
     hr.backward(dz)
-    d = dz.to(BF)
-    for f in reversed(fused):
-        d = f.backward(d)
+    from s4g_release_b200.train_engine import chain_backward
+    d = chain_backward(fused, dz.to(BF))
     torch.cuda.synchronize()
     rel = lambda got, want: (got.float() - want).norm().item() / max(want.norm().item(), 1e-12)
     assert rel(d, xr.grad) <= 5e-2, rel(d, xr.grad)
