@@ -75,6 +75,14 @@ FUSED_STATS = True
 # (the gradient is zero off the arg-max rows; the forward keeps y at the arg-max).  Both selectable for A/B measurements.
 FUSED_BWD_REDUCE = False  # (measured: 79.0 vs 78.6 ms per step — the fused epilogue is instruction-bound, see csrc/gemm_bf16.cu)
 SPARSE_POOL_REDUCE = True
+# A propagation level WITHOUT skip features (the finest one of PN2_CLS: 512 channels of 5 120 points onto 25 600 points)
+# starts with a linear layer on an interpolation whose weights sum to one: W (sum_k w_k f_k) = sum_k w_k (W f_k).  So the
+# conv runs on the SPARSE rows (5 x fewer), the 256-wide pre-activations are interpolated instead of the 512-wide
+# features (the concat input is never written), and the backward scatters 256-wide gradients; BatchNorm's statistics are
+# those of the interpolated rows, as in the reference order (PointNet2_tcls.py:120-128 -> modules.py FeatureInterpolator).
+# Measured at 32 scenes: 74.7-75.9 ms with, 75.6 ms without (the saved GEMM / scatter work is paid back by the separate
+# statistics pass and the extra casts), 0.6 GB less memory — no gain in training, unlike inference; off by default.
+FP_LINEAR_SPLIT = False
 
 
 def colstats_raw(y):
@@ -120,15 +128,25 @@ class Block:
 
     def forward(self, x, pool_k=0, seed=0):
         """x [P, Kp] bf16 -> z [P, cout] bf16, or (pooled [P / pool_k, cout], arg) when pool_k > 0."""
-        bn = self.bn
-        P = x.shape[0]
         wb = self._weight_rows()
         if FUSED_STATS:
             y, sums = gemm(x, wb, stats=True)  # conv + the BatchNorm batch statistics of its (stored) output
         else:
             y = gemm(x, wb)
             sums = colstats_raw(y)
-        dev = x.device
+        return self._normalise(x, y, sums, wb, pool_k, seed)
+
+    def forward_pre(self, y, x_rows, wb):
+        """the block from its PRE-activations y [P, cout] bf16 (computed elsewhere: FP_LINEAR_SPLIT); x_rows / wb = the rows
+        and weights they came from, kept for the caller's backward (backward returns d y, not d x, for such a block)"""
+        z = self._normalise(x_rows, y, colstats_raw(y), wb, 0, 0)
+        self.saved = self.saved + (True,)
+        return z
+
+    def _normalise(self, x, y, sums, wb, pool_k, seed):
+        bn = self.bn
+        P = y.shape[0]
+        dev = y.device
         C = self.cout
         stat = torch.empty(4 * C, dtype=torch.float32, device=dev)  # [mean | rstd | scale | shift]
         track = bn.track_running_stats and bn.running_mean is not None
@@ -140,7 +158,6 @@ class Block:
         if track:
             bn.num_batches_tracked += 1
         mean_rstd, scale, shift = stat[:2 * C], stat[2 * C:3 * C], stat[3 * C:]
-        dev = x.device
         if pool_k:
             G = P // pool_k
             z = torch.empty((G, self.cout), dtype=BF16, device=dev)
@@ -162,7 +179,8 @@ class Block:
         gradients; returns dx [P, Kp or Cf] bf16 (None when not needed).
         ``pre``: dz is already masked and these are its sums (it came out of gemm_bwd).  ``prev``: the block that produced
         this block's input — dx is then returned as (masked dx, sums) for prev.backward(..., pre=sums)."""
-        x, y, wb, mean_rstd, scale, shift, arg, pool_k, seed, ymax = self.saved
+        x, y, wb, mean_rstd, scale, shift, arg, pool_k, seed, ymax = self.saved[:10]
+        split = len(self.saved) > 10
         self.saved = None
         P, C = y.shape
         dev = y.device
@@ -188,6 +206,8 @@ class Block:
         check(lib.s4g_train_bn_bwd_apply_bf16(ptr(dz), ptr(arg) if pool_k else None, pool_k, ptr(y), ptr(scale), ptr(shift),
                                               ptr(coef), ptr(coef[C:]), ptr(coef[2 * C:]), P, C, relu, seed, drop, ptr(dy),
                                               stream_ptr(dev)), "train_bn_bwd_apply")
+        if split:
+            return dy, x, wb  # the caller owns the conv (it ran on other rows)
         # dW = dY^T X: a plain library GEMM (bf16 operands, fp32 result)
         dwb = torch.mm(dy.t(), x, out_dtype=torch.float32)
         if self.cf is None:
@@ -214,7 +234,7 @@ def chain_backward(blocks, dz, need_dx=True):
         prev = blocks[j - 1] if (j > 0 and FUSED_BWD_REDUCE) else None
         out = blocks[j].backward(dz, need_dx=(j > 0 or need_dx), prev=prev, pre=pre)
         dz, pre = out if prev is not None else (out, None)
-    return dz
+    return dz  # ((d y, x rows, weights) when the first block was built from pre-activations: Block.forward_pre)
 
 
 def _sum_rows(parts):
@@ -307,10 +327,17 @@ class TrainEngine:
             dense_xyz, dense = lv_xyz[-2 - i], lv_feat[-2 - i]
             idx3, w = E.three_nn_weights(dense_xyz, sparse_xyz)
             Nk, Nq = sparse_xyz.shape[2], dense_xyz.shape[2]
-            x = E.interp_concat(sparse, idx3, w, dense, B, Nk, Nq)
-            self._fp_ctx.append((idx3, w, B, Nk, Nq, sparse.shape[1], 0 if dense is None else dense.shape[1]))
-            h = x
-            for blk in blocks:
+            split = FP_LINEAR_SPLIT and dense is None
+            self._fp_ctx.append((idx3, w, B, Nk, Nq, sparse.shape[1], 0 if dense is None else dense.shape[1], split))
+            if split:
+                wb = blocks[0]._weight_rows()
+                y = E.interp_concat(gemm(sparse, wb), idx3, w, None, B, Nk, Nq)
+                h = blocks[0].forward_pre(y, sparse, wb)
+                rest = blocks[1:]
+            else:
+                h = E.interp_concat(sparse, idx3, w, dense, B, Nk, Nq)
+                rest = blocks
+            for blk in rest:
                 h = blk.forward(h)
             sparse_xyz, sparse = dense_xyz, h
         self._lv_shapes = [None if f is None else tuple(f.shape) for f in lv_feat]
@@ -373,8 +400,24 @@ class TrainEngine:
         n_fp = len(self.fp)
         # d_out = gradient of the current propagation level's OUTPUT rows
         for i in reversed(range(n_fp)):
+            idx3, w, B, Nk, Nq, c2, c1, split = self._fp_ctx[i]
+            if split:
+                blk0 = self.fp[i][0]
+                dy, x_sparse, wb = chain_backward(self.fp[i], d_out)  # d(pre-activations) of the first block, dense rows
+                d_ys = torch.zeros((B * Nk, blk0.cout), dtype=torch.float32, device=dev)
+                check(lib.s4g_train_interp_rows_bwd(ptr(dy), dy.stride(0), ptr(idx3), ptr(w), B, Nk, Nq, blk0.cout, ptr(d_ys),
+                                                    stream_ptr(dev)), "train_interp_rows_bwd")
+                del dy
+                d_ys = d_ys.to(BF16)
+                _accumulate(blk0.conv.weight, torch.mm(d_ys.t(), x_sparse, out_dtype=torch.float32)[:, :blk0.cin]
+                            .reshape(blk0.conv.weight.shape))
+                d_feat = gemm(d_ys, wb[:, :c2].t().contiguous())  # gradient of the sparse level's features [B*Nk, c2]
+                if i == 0:
+                    lv_grad[-1].add_(d_feat)
+                else:
+                    d_out = d_feat
+                continue
             dz = chain_backward(self.fp[i], d_out)
-            idx3, w, B, Nk, Nq, c2, c1 = self._fp_ctx[i]
             # dz rows = [d interpolated (c2) | d dense skip (c1)]
             if c1:
                 lv_grad[-2 - i].add_(dz[:, c2:c2 + c1])
