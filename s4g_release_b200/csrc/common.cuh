@@ -55,4 +55,15 @@ inline int num_sms() {
   return cache[dev];
 }
 
+// true the first time it is called for (flags, CURRENT device): per-device one-time set-up such as
+// cudaFuncSetAttribute (function attributes are per device; a process may drive several GPUs)
+inline bool first_use_on_device(bool (&flags)[64]) {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 64) dev = 0;
+  if (flags[dev]) return false;
+  flags[dev] = true;
+  return true;
+}
+
 }  // namespace s4g

@@ -499,15 +499,14 @@ static int gemm_launch(const void* a, long long lda, const void* b, long long ld
   }
   const size_t smem = 1024 + (size_t)(groups + (mode == kBwd ? 2 : 0)) * kStagingBytes + table_bytes +
                       (ws ? (size_t)(n_slabs + n_stages) * kOperandBytes : (size_t)n_stages * kStageBytes);
-  static bool attr_set = false;
-  if (!attr_set) {
+  static bool attr_set[64] = {};
+  if (s4g::first_use_on_device(attr_set)) {
     S4G_CUDA(cudaFuncSetAttribute(gemm_bf16_kernel<kPlain, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
     S4G_CUDA(cudaFuncSetAttribute(gemm_bf16_kernel<kPlain, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
     S4G_CUDA(cudaFuncSetAttribute(gemm_bf16_kernel<kStats, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
     S4G_CUDA(cudaFuncSetAttribute(gemm_bf16_kernel<kStats, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
     S4G_CUDA(cudaFuncSetAttribute(gemm_bf16_kernel<kBwd, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
     S4G_CUDA(cudaFuncSetAttribute(gemm_bf16_kernel<kBwd, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
-    attr_set = true;
   }
   const long long tiles = tiles_m * tiles_n;
   int grid = (int)(tiles < sms ? tiles : sms);

@@ -119,12 +119,11 @@ extern "C" int s4g_group_points_forward_f32(const float* input, const int64_t* i
     while (slots > 2048 && (long long)((MK + slots - 1) / slots) * c_groups * B < want) slots >>= 1;
     const long long ctas = (long long)((MK + slots - 1) / slots) * c_groups * B;
     if (ctas >= s4g::num_sms() && c_groups <= 65535 && B <= 65535) {
-      static bool attr_set = false;
-      if (!attr_set) {
+      static bool attr_set[64] = {};
+      if (s4g::first_use_on_device(attr_set)) {
         S4G_CUDA(cudaFuncSetAttribute(s4g::group_forward_staged_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       s4g::kStageSmemBytes));
-        attr_set = true;
-      }
+          }
       dim3 grid((MK + slots - 1) / slots, c_groups, B);
       s4g::group_forward_staged_kernel<<<grid, 256, (size_t)planes * plane_bytes, (cudaStream_t)stream>>>(
           input, index, C, N, MK, planes, slots, out);

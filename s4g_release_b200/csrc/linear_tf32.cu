@@ -220,10 +220,9 @@ extern "C" int s4g_linear_tf32(const float* x, long long ldx, const float* w, lo
   if (rc != S4G_OK) return rc;
   rc = encode_f32_map(&mw, w, K, ldw, N);
   if (rc != S4G_OK) return rc;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static bool attr_set[64] = {};
+  if (s4g::first_use_on_device(attr_set)) {
     S4G_CUDA(cudaFuncSetAttribute(linear_tf32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
-    attr_set = true;
   }
   dim3 grid((unsigned)((P + kTile - 1) / kTile), (unsigned)((N + kTile - 1) / kTile));
   S4G_CHECK_ARG(grid.y <= 65535, "linear_tf32: too many output channels");

@@ -1046,10 +1046,9 @@ namespace s4g {
 template <bool PROF, bool XYZ_MLP, int OUT, bool GATHER, bool TMA_IN = false>
 static int launch_chain(const ChainParams& p, int grid, size_t smem, cudaStream_t stream) {
   auto kern = mlp_chain_kernel<PROF, XYZ_MLP, OUT, GATHER, TMA_IN>;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static bool attr_set[64] = {};
+  if (s4g::first_use_on_device(attr_set)) {
     S4G_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    attr_set = true;
   }
   kern<<<grid, kChainThreads, smem, stream>>>(p);
   return S4G_OK;

@@ -243,10 +243,9 @@ extern "C" int s4g_farthest_point_sample_f64(const double* points, int B, int N,
   int block = 16, L = 4;  // the reference's block size for this N (sampling_kernel.cu:34-42,150-167)
   while (block < N && block < 512) { block <<= 1; ++L; }
   const size_t smem = need == 0 ? sizeof(double) * (size_t)N : 0;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static bool attr_set[64] = {};
+  if (s4g::first_use_on_device(attr_set)) {
     S4G_CUDA(cudaFuncSetAttribute(s4g::fps64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    attr_set = true;
   }
   s4g::fps64_kernel<<<B, s4g::kFps64Threads, smem, (cudaStream_t)stream>>>(points, N, M, L, (double*)workspace,
                                                                           need == 0 ? 1 : 0, index);

@@ -859,10 +859,9 @@ extern "C" int s4g_train_bn_bwd_reduce_bf16(const void* dz, const uint8_t* arg, 
     const int R = kStgRowsPerLane * lanes_s;
     const size_t tile_bytes = (size_t)R * C * 2;
     const size_t smem = kStgStages * 2 * tile_bytes;  // (>= the 32 KB the final reduction needs)
-    static bool attr = false;
-    if (!attr) {
+    static bool attr[64] = {};
+    if (s4g::first_use_on_device(attr)) {
       S4G_CUDA(cudaFuncSetAttribute(bn_bwd_reduce_staged_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-      attr = true;
     }
     const long long n_tiles = (P + R - 1) / R;
     const int sms = s4g::num_sms();
@@ -895,10 +894,9 @@ extern "C" int s4g_train_bn_bwd_apply_bf16(const void* dz, const uint8_t* arg, i
     const int pieces = C >> 3, lanes_s = kCons / pieces;
     const int R = kRpl * lanes_s;
     const size_t smem = (size_t)kStages * 2 * R * C * 2;
-    static bool attr = false;
-    if (!attr) {
+    static bool attr[64] = {};
+    if (s4g::first_use_on_device(attr)) {
       S4G_CUDA(cudaFuncSetAttribute(bn_bwd_apply_staged_kernel<kRpl, kStages, kCons>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-      attr = true;
     }
     const long long n_tiles = (P + R - 1) / R;
     const int sms = s4g::num_sms();
