@@ -153,13 +153,22 @@ bn_act_maxpool_kernel(const __nv_bfloat16* __restrict__ y, const float* __restri
 #pragma unroll
   for (int e = 0; e < 8; ++e) { best.v[e] = -3.4e38f; raw.v[e] = 0.f; bi[e] = 0; }
   const uint4* src = reinterpret_cast<const uint4*>(y + g * K * C) + piece;
-  for (int k = 0; k < K; ++k) {
-    const F8 v = unpack8(__ldg(src + (size_t)k * pieces));
+  for (int k0 = 0; k0 < K; k0 += 4) {  // four rows in flight
+    uint4 rawv[4];
 #pragma unroll
-    for (int e = 0; e < 8; ++e) {
-      float t = fmaf(v.v[e], a.v[e], b.v[e]);
-      if (relu) t = fmaxf(t, 0.f);
-      if (t > best.v[e]) { best.v[e] = t; raw.v[e] = v.v[e]; bi[e] = k; }  // first maximum wins, like torch.max
+    for (int u = 0; u < 4; ++u)
+      if (k0 + u < K) rawv[u] = __ldg(src + (size_t)(k0 + u) * pieces);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int k = k0 + u;
+      if (k >= K) break;
+      const F8 v = unpack8(rawv[u]);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        float t = fmaf(v.v[e], a.v[e], b.v[e]);
+        if (relu) t = fmaxf(t, 0.f);
+        if (t > best.v[e]) { best.v[e] = t; raw.v[e] = v.v[e]; bi[e] = k; }  // first maximum wins, like torch.max
+      }
     }
   }
   reinterpret_cast<uint4*>(out + g * C)[piece] = pack8(best);
@@ -176,7 +185,13 @@ struct Upstream {
   const __nv_bfloat16* dz;   // dense: [P][C];   pooled: [G][C]
   const uint8_t* arg;        // pooled only: [G][C]
   int K;                     // 0 = dense
+  int kshift;                // log2 K when K is a power of two (every shipped configuration), else -1
 };
+static Upstream make_upstream(const void* dz, const uint8_t* arg, int K) {
+  int sh = -1;
+  if (K > 0 && (K & (K - 1)) == 0) { sh = 0; while ((1 << sh) < K) ++sh; }
+  return Upstream{reinterpret_cast<const __nv_bfloat16*>(dz), arg, K, sh};
+}
 struct UpRaw { uint4 d; uint2 a; int k; };
 // load now (raw, 16 B + 8 B), route later: keeps the loads of several rows in flight without holding converted values
 __device__ __forceinline__ UpRaw upstream_load(const Upstream& u, long long row, int piece, int C) {
@@ -186,23 +201,32 @@ __device__ __forceinline__ UpRaw upstream_load(const Upstream& u, long long row,
     r.a = make_uint2(0u, 0u);
     r.k = -1;
   } else {
-    const long long g = row / u.K;
-    r.k = (int)(row - g * u.K);
+    long long g;
+    if (u.kshift >= 0) {  // (a 64-bit division per row and thread was a visible part of the pooled pass: ncu, 59-63 % issue)
+      g = row >> u.kshift;
+      r.k = (int)(row & (long long)(u.K - 1));
+    } else {
+      g = row / u.K;
+      r.k = (int)(row - g * u.K);
+    }
     r.d = __ldg(reinterpret_cast<const uint4*>(u.dz + g * C) + piece);
     r.a = __ldg(reinterpret_cast<const uint2*>(u.arg + g * C) + piece);
   }
   return r;
 }
+// pooled: keep the gradient of the channels whose arg-max is this row — byte-wise compare of the 8 packed indices, the
+// 8-bit masks widened to the 16-bit bf16 lanes by byte permutes (10 instructions instead of a select per channel)
 __device__ __forceinline__ F8 upstream_route(const UpRaw& r) {
-  F8 d = unpack8(r.d);
+  uint4 d = r.d;
   if (r.k >= 0) {
-#pragma unroll
-    for (int e = 0; e < 8; ++e) {
-      const unsigned idx = ((e < 4 ? r.a.x : r.a.y) >> (8 * (e & 3))) & 0xffu;
-      if ((int)idx != r.k) d.v[e] = 0.f;
-    }
+    const unsigned kk = (unsigned)r.k * 0x01010101u;
+    const unsigned m0 = __vcmpeq4(r.a.x, kk), m1 = __vcmpeq4(r.a.y, kk);
+    d.x &= __byte_perm(m0, 0u, 0x1100);
+    d.y &= __byte_perm(m0, 0u, 0x3322);
+    d.z &= __byte_perm(m1, 0u, 0x1100);
+    d.w &= __byte_perm(m1, 0u, 0x3322);
   }
-  return d;
+  return unpack8(d);
 }
 
 // sums = [sum_r g | sum_r g * y]; the caller turns the second into sum g * xhat = rstd * (sum g y - mean * sum g) in fp64
@@ -848,7 +872,7 @@ extern "C" int s4g_train_bn_bwd_reduce_bf16(const void* dz, const uint8_t* arg, 
   const int pieces = C >> 3, lanes = kStatThreads / pieces;
   S4G_CHECK_ARG(lanes >= 1, "train_bn_bwd_reduce: too many channels");
   const unsigned thresh = drop_p > 0.f ? (unsigned)((double)drop_p * 4294967296.0) : 0u;
-  const Upstream up{reinterpret_cast<const bf16*>(dz), arg, K};
+  const Upstream up = make_upstream(dz, arg, K);
   // S4G_BWD_REDUCE_VARIANT (A/B measurements): 0 (default) = rows staged by the copy engine for dense upstream gradients,
   // 1 = registers, 2 rows in flight x 3 blocks per SM, 2 = registers, 4 x 2
   static int variant = -1;
@@ -886,7 +910,7 @@ extern "C" int s4g_train_bn_bwd_apply_bf16(const void* dz, const uint8_t* arg, i
                 "train_bn_bwd_apply: bad arguments");
   TRN_CHECK_C(C);
   const unsigned thresh = drop_p > 0.f ? (unsigned)((double)drop_p * 4294967296.0) : 0u;
-  const Upstream up{reinterpret_cast<const bf16*>(dz), arg, K};
+  const Upstream up = make_upstream(dz, arg, K);
   static int variant = -1;  // S4G_BWD_APPLY_VARIANT (A/B measurements): 0 (default) = rows staged by the copy engine, 1 = registers
   if (variant < 0) { const char* e = getenv("S4G_BWD_APPLY_VARIANT"); variant = e ? atoi(e) : 0; }
   if (variant == 0 && (((uintptr_t)dz | (uintptr_t)y | (uintptr_t)dy) & 15) == 0) {

@@ -178,7 +178,7 @@ def test_bn_bwd_reduce_dense_against_torch(P, C, drop):
 
 
 @pytest.mark.parametrize("P,C,K,drop", [(70001, 136, 0, 0.0), (96, 1024, 0, 0.0), (5000, 8, 0, 0.0), (300000, 128, 0, 0.4),
-                                        (4097 * 16, 264, 16, 0.0), (64 * 1000, 128, 64, 0.0), (1, 64, 0, 0.0)])
+                                        (4097 * 16, 264, 16, 0.0), (64 * 1000, 128, 64, 0.0), (12 * 777, 72, 12, 0.0), (1, 64, 0, 0.0)])
 def test_bn_bwd_apply_against_torch(P, C, K, drop):
     """the (copy-engine staged) second pass: dy = ka * g + kb * y + kc, g = dz * relu' * dropout, dense or routed through
     the arg-max of a pooled block"""
