@@ -146,6 +146,9 @@ int s4g_gemm_bf16_set_weight_stationary(int on);
 /* A/B switch (measurements): number of epilogue warp groups, 1 or 2 (one group per TMEM accumulator / tile parity, a
  * staging tile each), 0 (default) = chosen per launch (2 when K <= 128).  Returns the previous setting.  Same bits. */
 int s4g_gemm_bf16_set_epilogue_groups(int groups);
+/* A/B switch (measurements): output columns per tile, 128 or 256 (one N = 256 MMA per K step, two epilogue groups splitting
+ * the tile; streaming schedule), 0 (default) = chosen per launch.  Returns the previous setting.  Same bits. */
+int s4g_gemm_bf16_set_tile_n(int bn);
 /* Input-gradient GEMM whose RESULT is the upstream gradient of the block that produced y_prev (its rows [P][N] before
  * BatchNorm; scale / shift = its folded BatchNorm; relu / seed / drop_p = its activation and dropout):
  *   c = (a · b^T) * relu'(y_prev * scale + shift) * dropout mask     (stored MASKED, bf16)

@@ -38,7 +38,9 @@ def timed(fn, reps=5):
 
 
 def main():
-    print("%-28s %10s %10s %10s %10s   (ms; fraction of %.0f GB/s)" % ("rows x K -> N", "plain g1", "plain g2", "fused g1", "fused g2", PEAK))
+    tiles = os.environ.get("S4G_GEMM_LAYERS_TILES") == "1"  # compare 128- with 256-column tiles instead of epilogue groups
+    print("%-28s %10s %10s %10s %10s   (ms; fraction of %.0f GB/s)" % (("rows x K -> N", "plain n128", "plain n256", "fused n128", "fused n256", PEAK)
+          if tiles else ("rows x K -> N", "plain g1", "plain g2", "fused g1", "fused g2", PEAK)))
     for kind, shapes in (("fwd+stats", FWD), ("dX+reduce", BWD)):
         for P, K, N in shapes:
             a = torch.randn(P, K, device="cuda").to(BF)
@@ -51,7 +53,10 @@ def main():
             cells = []
             for fused in (False, True):
                 for groups in (1, 2):
-                    lib.s4g_gemm_bf16_set_epilogue_groups(groups)
+                    if tiles:
+                        lib.s4g_gemm_bf16_set_tile_n(128 * groups)
+                    else:
+                        lib.s4g_gemm_bf16_set_epilogue_groups(groups)
                     if not fused:
                         ms = timed(lambda: gemm(a, b))
                     elif y is None:
@@ -60,7 +65,8 @@ def main():
                         ms = timed(lambda: gemm_bwd(a, b, y, sc, sh))
                     by = bytes_fused if fused else bytes_plain
                     cells.append("%.3f/%.2f" % (ms, by / (ms * 1e-3) / 1e9 / PEAK))
-            lib.s4g_gemm_bf16_set_epilogue_groups(2)
+            lib.s4g_gemm_bf16_set_epilogue_groups(0)
+            lib.s4g_gemm_bf16_set_tile_n(0)
             print("%-9s %9d x %4d -> %4d %10s %10s %10s %10s" % ((kind, P, K, N) + tuple(cells)))
             del a, b, y
 

@@ -49,7 +49,7 @@
 namespace s4g {
 namespace gemm {
 
-constexpr int kMaxThreads = 64 + 2 * 128;         // producer warp, MMA warp, 1 or 2 epilogue groups of 4 warps
+constexpr int kMaxThreads = 64 + 2 * 128 + 32;    // producer warp, MMA warp, 1 or 2 epilogue groups of 4 warps, second producer warp
 constexpr int kStages = 5;                         // streaming mode: at most this many stages of A + B slabs (32 KB)
 constexpr int kMaxStagesA = 6;                     // weight-stationary mode: stages of A slabs (16 KB)
 constexpr int kMaxSlabsWS = 8;                     // K <= 512
@@ -156,14 +156,20 @@ template <int MODE, bool WS>
 __global__ void __launch_bounds__(kMaxThreads, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                  const __grid_constant__ CUtensorMap map_c, const __grid_constant__ CUtensorMap map_y, int P, int N, int K,
-                 int n_stages, int groups, double* __restrict__ stats, const BwdEpilogue bw) {
+                 int n_stages, int groups, int bn, double* __restrict__ stats, const BwdEpilogue bw) {
   constexpr bool STATS = MODE != kPlain;  // per-column sums collected in shared memory, fp64 global atomics at the end
   const int kThreads = (int)blockDim.x;
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t full[kMaxStagesA], empty[kMaxStagesA], acc_full[2], acc_empty[2], w_full, y_full[2], y_empty[2];
   __shared__ uint32_t tmem_slot;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int tiles_n = (N + kTile - 1) / kTile;
+  // bn = output columns per tile: 128, or 256 (streaming schedule only): ONE N = 256 MMA per K step instead of two N = 128
+  // ones — the MMA-issuing thread, not the tensor pipe or the loads, paces the K >= 256 layers (~190 cycles per MMA
+  // whatever its N: profiles/r02/gemm_layers_v3.txt, gemm_layers_v4_two_producers.txt; profiles/r01/mma_loop.txt).  The two
+  // epilogue groups then split every tile by columns instead of alternating tiles.
+  const bool split = bn > kTile;
+  const int tiles_n = (N + bn - 1) / bn;
+  const int ncols = tiles_n * bn;  // width of the per-column tables
   const int tiles_m = (P + kTile - 1) / kTile;
   const int n_slabs = (K + kSlab - 1) / kSlab;
   // shared memory: [WS: B slice, n_slabs x 16 KB][ring][staging: groups x 32 KB][BWD: 2 y tiles of 32 KB]
@@ -171,7 +177,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
   uint8_t* base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);  // swizzle atoms are 1024-byte aligned
   uint8_t* wreg = base;
   uint8_t* ring = base + (WS ? (size_t)n_slabs * kOperandBytes : 0);
-  const int stage_bytes = WS ? kOperandBytes : kStageBytes;
+  const int stage_bytes = WS ? kOperandBytes : kOperandBytes + (bn / kTile) * kOperandBytes;
   uint8_t* staging_all = ring + (size_t)n_stages * stage_bytes;
   uint8_t* ytile = staging_all + (size_t)groups * kStagingBytes;
   float* s_stat = reinterpret_cast<float*>(ytile + (MODE == kBwd ? 2 * kStagingBytes : 0));
@@ -183,22 +189,22 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                       : (((int)blockIdx.x < tiles_m * tiles_n) ? (tiles_m * tiles_n - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0);
   auto tile_of = [&](int i, int& row0, int& col0) {
     if (WS) { row0 = (my_m0 + i * per_n) * kTile; col0 = my_n * kTile; }
-    else { const int t = (int)blockIdx.x + i * (int)gridDim.x; row0 = (t / tiles_n) * kTile; col0 = (t % tiles_n) * kTile; }
+    else { const int t = (int)blockIdx.x + i * (int)gridDim.x; row0 = (t / tiles_n) * kTile; col0 = (t % tiles_n) * bn; }
   };
 
   if constexpr (STATS) {
-    for (int i = threadIdx.x; i < 2 * tiles_n * kTile; i += kThreads) s_stat[i] = 0.f;
+    for (int i = threadIdx.x; i < 2 * ncols; i += kThreads) s_stat[i] = 0.f;
   }
   if (threadIdx.x == 0) {
-    for (int s = 0; s < kMaxStagesA; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    for (int s = 0; s < kMaxStagesA; ++s) { mbar_init(&full[s], WS ? 1 : 2); mbar_init(&empty[s], 1); }  // streaming: A and B producers
     mbar_init(&w_full, 1);
     for (int a = 0; a < 2; ++a) { mbar_init(&y_full[a], 1); mbar_init(&y_empty[a], 1); }
-    for (int a = 0; a < 2; ++a) { mbar_init(&acc_full[a], 1); mbar_init(&acc_empty[a], 4); }  // 4 epilogue warps
+    for (int a = 0; a < 2; ++a) { mbar_init(&acc_full[a], 1); mbar_init(&acc_empty[a], split ? 8 : 4); }  // epilogue warps per tile
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "r"(256u)
-                 : "memory");
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)),
+                 "r"(2u * (unsigned)bn) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -206,9 +212,16 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem = tmem_slot;
 
-  if (warp == 0) {
+  const int warp_p1 = 2 + 4 * groups;  // the second producer warp (the last one)
+  if (warp == 0 || warp == warp_p1) {
+    // Two producer lanes in two warps: ONE thread issues a bulk copy every ~0.26 us whatever its size
+    // (profiles/r01/tma_bw.txt); with 256-column tiles a K slab is an A box of 16 KB and a B box of 32 KB, and one lane
+    // issuing both paced the K = 512 layers at ~1 360 cycles per slab (gemm_layers_v5_tile256.txt).  Streaming: producer 0
+    // loads the A boxes, producer 1 the B boxes (each arms the stage's barrier with its own bytes).  Weight-stationary:
+    // they alternate slabs; producer 1 also loads the resident B slice and, in BWD mode, the y tiles.
+    const int who = warp == 0 ? 0 : 1;
     if (elect_one() && n_my > 0) {
-      if (WS) {  // the CTA's B slice, once
+      if (WS && who == 1) {  // the CTA's B slice, once
         mbar_expect_tx(&w_full, (unsigned)n_slabs * kOperandBytes);
         for (int k = 0; k < n_slabs; ++k) tma_load_2d(wreg + (size_t)k * kOperandBytes, &map_b, k * kSlab, my_n * kTile, &w_full);
       }
@@ -217,28 +230,35 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         int row0, col0;
         tile_of(i, row0, col0);
         for (int k = 0; k < n_slabs; ++k, ++g) {
+          if (WS && (int)(g & 1u) != who) continue;
           const unsigned s = g % (unsigned)n_stages, use = g / (unsigned)n_stages;
           if (use > 0) mbar_wait(&empty[s], (use - 1) & 1u);
-          mbar_expect_tx(&full[s], (unsigned)stage_bytes);  // zero-filled out-of-range elements count as transferred bytes
-          tma_load_2d(ring + (size_t)s * stage_bytes, &map_a, k * kSlab, row0, &full[s]);
-          if (!WS) tma_load_2d(ring + (size_t)s * stage_bytes + kOperandBytes, &map_b, k * kSlab, col0, &full[s]);
+          // (zero-filled out-of-range elements count as transferred bytes)
+          if (WS || who == 0) {
+            mbar_expect_tx(&full[s], (unsigned)kOperandBytes);
+            tma_load_2d(ring + (size_t)s * stage_bytes, &map_a, k * kSlab, row0, &full[s]);
+          } else {
+            mbar_expect_tx(&full[s], (unsigned)(stage_bytes - kOperandBytes));
+            tma_load_2d(ring + (size_t)s * stage_bytes + kOperandBytes, &map_b, k * kSlab, col0, &full[s]);
+          }
         }
         if constexpr (MODE == kBwd) {  // the previous block's pre-activation tile, for this tile's epilogue
-          // (two buffers: with one, the producer could not run more than a tile ahead of the epilogue — 8 150 cycles per
-          // tile, latency-bound, on the 128 -> 128 layer)
-          const int yb = i & 1;
-          if (i >= 2) mbar_wait(&y_empty[yb], (unsigned)((i >> 1) - 1) & 1u);
-          const bool two = col0 + 64 < N;
-          uint8_t* yt = ytile + (size_t)yb * kStagingBytes;
-          mbar_expect_tx(&y_full[yb], two ? (unsigned)kStagingBytes : (unsigned)kStagingBytes / 2);
-          tma_load_2d(yt, &map_y, col0, row0, &y_full[yb]);
-          if (two) tma_load_2d(yt + kStagingBytes / 2, &map_y, col0 + 64, row0, &y_full[yb]);
+          if (who == 1) {
+            // (two buffers: with one, the producer could not run more than a tile ahead of the epilogue)
+            const int yb = i & 1;
+            if (i >= 2) mbar_wait(&y_empty[yb], (unsigned)((i >> 1) - 1) & 1u);
+            const bool two = col0 + 64 < N;
+            uint8_t* yt = ytile + (size_t)yb * kStagingBytes;
+            mbar_expect_tx(&y_full[yb], two ? (unsigned)kStagingBytes : (unsigned)kStagingBytes / 2);
+            tma_load_2d(yt, &map_y, col0, row0, &y_full[yb]);
+            if (two) tma_load_2d(yt + kStagingBytes / 2, &map_y, col0 + 64, row0, &y_full[yb]);
+          }
         }
       }
     }
   } else if (warp == 1) {
     // instruction descriptor, kind::f16: D = f32 (bit 4), A = B = bf16 (1 at bits 7, 10), both K-major, N at 17, M at 24
-    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(kTile >> 3) << 17) | ((uint32_t)(kTile >> 4) << 24);
+    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(bn >> 3) << 17) | ((uint32_t)(kTile >> 4) << 24);
     // shared-memory descriptor of a 128-byte-swizzled K-major tile: SBO = 1024 B (8 rows), version 1, layout 2; LBO unused
     const uint64_t desc_hi = (uint64_t)((1024u >> 4) | (1u << 14) | (2u << 29)) << 32;
     unsigned g = 0;
@@ -247,7 +267,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
       const unsigned a = (unsigned)i & 1u, ause = (unsigned)i >> 1;
       if (ause > 0) mbar_wait(&acc_empty[a], (ause - 1) & 1u);  // the epilogue has drained this accumulator's previous tile
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      const uint32_t d_addr = tmem + a * (uint32_t)kTile;
+      const uint32_t d_addr = tmem + a * (uint32_t)bn;
       for (int k = 0; k < n_slabs; ++k, ++g) {
         const unsigned s = g % (unsigned)n_stages;
         mbar_wait(&full[s], (g / (unsigned)n_stages) & 1u);
@@ -265,23 +285,31 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         __syncwarp();
       }
     }
-  } else {
+  } else if (warp < warp_p1) {
     const int qd = warp & 3;  // the TMEM lane quadrant a warp may read is fixed by warp id % 4
     const int r = qd * 32 + lane;  // this thread's row of the tile (= TMEM lane)
-    const int grp = (warp - 2) >> 2;  // epilogue group: tiles i = grp, grp + groups, ...
+    const int grp = (warp - 2) >> 2;  // epilogue group: tiles i = grp, grp + groups, ... — or, split, its 128 columns of every tile
     const int bar_id = 1 + grp;
     const bool issuer = (((warp - 2) & 3) == 0 && lane == 0);
     uint8_t* staging = staging_all + (size_t)grp * kStagingBytes;
-    for (int i = grp; i < n_my; i += groups) {
+    const int coff = split ? grp * kTile : 0;
+    for (int i = split ? 0 : grp; i < n_my; i += split ? 1 : groups) {
       const unsigned a = (unsigned)i & 1u;
       int row0, col0;
       tile_of(i, row0, col0);
+      col0 += coff;
       mbar_wait(&acc_full[a], ((unsigned)i >> 1) & 1u);
+      if (col0 >= N) {  // (split, ragged N: this group's half of the tile does not exist)
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&acc_empty[a]);
+        continue;
+      }
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       // the group's previous tile's stores must have finished READING the staging tile before it is overwritten
       if (issuer) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
       epi_barrier(bar_id);
-      const uint32_t t_addr = tmem + ((uint32_t)(qd * 32) << 16) + a * (uint32_t)kTile;
+      const uint32_t t_addr = tmem + ((uint32_t)(qd * 32) << 16) + a * (uint32_t)bn + (uint32_t)coff;
 #pragma unroll 1
       for (int cc = 0; cc < kTile; cc += 32) {
         float v[32];
@@ -362,8 +390,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         float* dst = s_stat + col0 + h * 64 + 2 * w;
         atomicAdd(dst, s0);
         atomicAdd(dst + 1, s1);
-        atomicAdd(dst + tiles_n * kTile, q0);
-        atomicAdd(dst + tiles_n * kTile + 1, q1);
+        atomicAdd(dst + ncols, q0);
+        atomicAdd(dst + ncols + 1, q1);
       }
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // staging writes -> visible to the copy engine
       epi_barrier(bar_id);
@@ -387,26 +415,26 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         float* dst = s_stat + col0 + h * 64 + 2 * w;
         atomicAdd(dst, s0);
         atomicAdd(dst + 1, s1);
-        atomicAdd(dst + tiles_n * kTile, q0);
-        atomicAdd(dst + tiles_n * kTile + 1, q1);
+        atomicAdd(dst + ncols, q0);
+        atomicAdd(dst + ncols + 1, q1);
       }
     }
     if (issuer) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
-  if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(256u) : "memory");
+  if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(2u * (unsigned)bn) : "memory");
   if constexpr (STATS) {
     if (n_my > 0) {
-      for (int i = threadIdx.x; i < 2 * tiles_n * kTile; i += kThreads) {
-        const int half = i / (tiles_n * kTile), col = i - half * tiles_n * kTile;
+      for (int i = threadIdx.x; i < 2 * ncols; i += kThreads) {
+        const int half = i / ncols, col = i - half * ncols;
         if (col < N) atomicAdd(stats + (size_t)half * N + col, (double)s_stat[i]);
       }
     }
   }
 }
 
-static int encode_bf16_map(CUtensorMap* map, const void* base, long long width, long long ld, long long rows) {
+static int encode_bf16_map(CUtensorMap* map, const void* base, long long width, long long ld, long long rows, int box_rows = kTile) {
   typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -420,7 +448,7 @@ static int encode_bf16_map(CUtensorMap* map, const void* base, long long width, 
   }
   const cuuint64_t dims[2] = {(cuuint64_t)width, (cuuint64_t)rows};
   const cuuint64_t strides[1] = {(cuuint64_t)ld * 2u};
-  const cuuint32_t box[2] = {(cuuint32_t)kSlab, (cuuint32_t)kTile};
+  const cuuint32_t box[2] = {(cuuint32_t)kSlab, (cuuint32_t)box_rows};
   const cuuint32_t estr[2] = {1u, 1u};
   const CUresult r = encode(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
                             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -434,6 +462,7 @@ static int encode_bf16_map(CUtensorMap* map, const void* base, long long width, 
 
 static bool g_gemm_ws = true;
 static int g_epi_groups = 0;
+static int g_tile_n = 0;
 // A/B switches for measurements.  weight_stationary: 0 = always stream B through the ring, 1 = weight-stationary where it
 // applies (default).  epilogue_groups: 1 or 2 groups of 4 epilogue warps, 0 (default) = chosen per launch.  Both return
 // the previous value.
@@ -448,6 +477,13 @@ extern "C" int s4g_gemm_bf16_set_epilogue_groups(int groups) {
   return prev;
 }
 
+// A/B switch for measurements: output columns per tile, 128 or 256, 0 (default) = chosen per launch.  Returns the previous value.
+extern "C" int s4g_gemm_bf16_set_tile_n(int bn) {
+  const int prev = g_tile_n;
+  if (bn == 0 || bn == 128 || bn == 256) g_tile_n = bn;
+  return prev;
+}
+
 static int gemm_launch(const void* a, long long lda, const void* b, long long ldb, void* c, long long ldc, long long P, int N,
                        int K, int mode, double* stats, const s4g::gemm::BwdEpilogue& bw, void* stream) {
   using namespace s4g::gemm;
@@ -458,17 +494,26 @@ static int gemm_launch(const void* a, long long lda, const void* b, long long ld
                     ((uintptr_t)c & 15) == 0,
                 "gemm_bf16: rows must be 16-byte aligned (leading dimensions multiples of 8 bf16)");
   if (P == 0) return S4G_OK;
+  const int n_slabs = (K + kSlab - 1) / kSlab;
+  const long long tiles_m = (P + kTile - 1) / kTile;
+  // 256-column tiles (streaming schedule, two epilogue groups splitting the tile): where the MMA-issuing thread sets the
+  // pace, i.e. many K slabs per tile and at least 256 output columns.  Measured per shape (profiles/r02/gemm_layers_v6.txt):
+  // 10-25 % faster for K >= 256 (512 -> 1024 on 0.5 M rows 0.72 -> 0.58 ms, 1024 -> 512 0.72 -> 0.54), except K = 264 (a fifth
+  // slab of 8 columns costs a whole 48 KB stage here but 16 KB on the weight-stationary schedule: 0.58 vs 0.70 ms)
+  int bn = kTile;
+  if (mode != kBwd && N > kTile) {
+    if (g_tile_n == 256) bn = 256;
+    else if (g_tile_n == 0 && n_slabs >= 4 && (K % kSlab == 0 || n_slabs >= 8)) bn = 256;
+  }
   CUtensorMap ma, mb;
   int rc = encode_bf16_map(&ma, a, K, lda, P);
   if (rc != S4G_OK) return rc;
-  rc = encode_bf16_map(&mb, b, K, ldb, N);
+  rc = encode_bf16_map(&mb, b, K, ldb, N, bn);
   if (rc != S4G_OK) return rc;
   CUtensorMap mc;
   rc = encode_bf16_map(&mc, c, N, ldc, P);
   if (rc != S4G_OK) return rc;
-  const int tiles_n = (N + kTile - 1) / kTile;
-  const long long tiles_m = (P + kTile - 1) / kTile;
-  const int n_slabs = (K + kSlab - 1) / kSlab;
+  const int tiles_n = (N + bn - 1) / bn;
   CUtensorMap my = mc;
   if (mode == kBwd) {
     rc = encode_bf16_map(&my, bw.y, N, bw.ldy, P);
@@ -477,28 +522,29 @@ static int gemm_launch(const void* a, long long lda, const void* b, long long ld
   // epilogue groups: two pay where the epilogue, not HBM or the tensor pipe, sets the pace — short K (<= 2 slabs: measured
   // 3 -> 128 on 10.5 M rows 0.82 -> 0.55 ms, 128 -> 256 1.63 -> 1.28 ms); with more slabs per tile the second staging tile
   // only costs ring stages (264 -> 256 on 2.1 M rows 0.49 -> 0.64 ms: it loses the weight-stationary schedule).  The BWD
-  // epilogue has one group (its y tile takes the second staging tile's place).
-  const int groups = mode == kBwd ? 1 : g_epi_groups ? g_epi_groups : (n_slabs <= 2 ? 2 : 1);
+  // epilogue has one group (its y tiles take the second staging tile's place); 256-column tiles always have two.
+  const int groups = bn == 256 ? 2 : mode == kBwd ? 1 : g_epi_groups ? g_epi_groups : (n_slabs <= 2 ? 2 : 1);
   // per-column sums in shared memory
-  const size_t table_bytes = sizeof(float) * (size_t)tiles_n * kTile * (mode == kPlain ? 0 : 2);
+  const size_t table_bytes = sizeof(float) * (size_t)tiles_n * bn * (mode == kPlain ? 0 : 2);
   constexpr int kMaxDynSmem = 226 * 1024;  // (the kernel also has ~170 bytes of static shared memory; the limit is 227 KB)
   const long long room = (long long)kMaxDynSmem - 1024 - (long long)(groups + (mode == kBwd ? 2 : 0)) * kStagingBytes -
                          (long long)table_bytes;
-  S4G_CHECK_ARG(room >= 2LL * kStageBytes, "gemm_bf16: too many output columns for the fused statistics");
+  const int stage_bytes = kOperandBytes + (bn / kTile) * kOperandBytes;
+  S4G_CHECK_ARG(room >= 2LL * stage_bytes, "gemm_bf16: too many output columns for the fused statistics");
   // weight-stationary when the B slice fits beside >= 5 A stages and every CTA gets >= 2 m-tiles
   // (K = 512 with 3 A stages beside its 128 KB slice: measured 20-30 % SLOWER than streaming)
   const int sms = s4g::num_sms();
-  int n_stages = (int)(room / kStageBytes);
+  int n_stages = (int)(room / stage_bytes);
   if (n_stages > kStages) n_stages = kStages;
   bool ws = false;
-  if (g_gemm_ws && n_slabs <= kMaxSlabsWS && tiles_n <= sms) {
+  if (bn == kTile && g_gemm_ws && n_slabs <= kMaxSlabsWS && tiles_n <= sms) {
     int stages_a = (int)(room / kOperandBytes) - n_slabs;
     if (stages_a > kMaxStagesA) stages_a = kMaxStagesA;
     ws = stages_a >= 5 && tiles_m >= 2LL * (sms / tiles_n);
     if (ws) n_stages = stages_a;
   }
   const size_t smem = 1024 + (size_t)(groups + (mode == kBwd ? 2 : 0)) * kStagingBytes + table_bytes +
-                      (ws ? (size_t)(n_slabs + n_stages) * kOperandBytes : (size_t)n_stages * kStageBytes);
+                      (ws ? (size_t)(n_slabs + n_stages) * kOperandBytes : (size_t)n_stages * stage_bytes);
   static bool attr_set[64] = {};
   if (s4g::first_use_on_device(attr_set)) {
     S4G_CUDA(cudaFuncSetAttribute(gemm_bf16_kernel<kPlain, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
@@ -511,11 +557,11 @@ static int gemm_launch(const void* a, long long lda, const void* b, long long ld
   const long long tiles = tiles_m * tiles_n;
   int grid = (int)(tiles < sms ? tiles : sms);
   if (ws) grid = (sms / tiles_n) * tiles_n;  // every n-tile gets the same number of CTAs
-  const int threads = 64 + 128 * groups;
+  const int threads = 64 + 128 * groups + 32;
   cudaStream_t st = (cudaStream_t)stream;
   if (stats) S4G_CUDA(cudaMemsetAsync(stats, 0, sizeof(double) * 2 * N, st));
 #define S4G_GEMM_GO(MODE_, WS_) \
-  gemm_bf16_kernel<MODE_, WS_><<<grid, threads, smem, st>>>(ma, mb, mc, my, (int)P, N, K, n_stages, groups, stats, bw)
+  gemm_bf16_kernel<MODE_, WS_><<<grid, threads, smem, st>>>(ma, mb, mc, my, (int)P, N, K, n_stages, groups, bn, stats, bw)
   if (mode == kBwd) { if (ws) S4G_GEMM_GO(kBwd, true); else S4G_GEMM_GO(kBwd, false); }
   else if (mode == kStats) { if (ws) S4G_GEMM_GO(kStats, true); else S4G_GEMM_GO(kStats, false); }
   else { if (ws) S4G_GEMM_GO(kPlain, true); else S4G_GEMM_GO(kPlain, false); }

@@ -100,6 +100,32 @@ def test_gemm_epilogue_groups_are_bit_identical(P, N, K):
     assert (c2.double() - want).abs().max().item() <= 1e-2 * max(1.0, want.abs().max().item())
 
 
+@pytest.mark.parametrize("P,N,K", [(148 * 2 * 128 + 77, 256, 256), (70001, 264, 40), (3333, 520, 264), (20000, 1024, 512),
+                                   (40000, 136, 1024), (129, 512, 520)])
+def test_gemm_256_column_tiles_are_bit_identical(P, N, K):
+    """128 x 256 tiles (one N = 256 MMA per K step, the two epilogue groups splitting the tile) against 128 x 128 tiles:
+    same stored bits, same fused statistics up to summation order — including ragged N (a group's half tile missing)"""
+    from s4g_release_b200._lib import lib
+    from s4g_release_b200.train_engine import gemm
+    g = torch.Generator().manual_seed(P % 1000 + N + K)
+    a = torch.randn(P, K, generator=g).cuda().to(BF)
+    b = (torch.randn(N, K, generator=g) / np.sqrt(K)).cuda().to(BF)
+    prev = lib.s4g_gemm_bf16_set_tile_n(128)
+    try:
+        c1, s1 = gemm(a, b, stats=True)
+        p1 = gemm(a, b)
+        lib.s4g_gemm_bf16_set_tile_n(256)
+        c2, s2 = gemm(a, b, stats=True)
+        p2 = gemm(a, b)
+    finally:
+        lib.s4g_gemm_bf16_set_tile_n(prev)
+    torch.cuda.synchronize()
+    assert torch.equal(c1, c2) and torch.equal(p1, p2) and torch.equal(c1, p1)
+    np.testing.assert_allclose(s1.cpu().numpy(), s2.cpu().numpy(), rtol=1e-5, atol=1e-2)
+    want = a.double() @ b.double().t()
+    assert (c2.double() - want).abs().max().item() <= 1e-2 * max(1.0, want.abs().max().item())
+
+
 @pytest.mark.parametrize("groups", [1, 2])
 @pytest.mark.parametrize("P,N,K,drop", [(148 * 2 * 128 + 77, 128, 128, 0.0), (70001, 256, 40, 0.5), (333, 72, 264, 0.0),
                                         (20000, 512, 1024, 0.3), (5000, 8, 128, 0.0)])
