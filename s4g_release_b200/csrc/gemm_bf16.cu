@@ -6,22 +6,27 @@
 // path, one GEMM over channel-last bf16 rows followed by small fused element-wise kernels (csrc/train_ops.cu); this
 // kernel is that GEMM — forward (Y = X W^T) and input gradient (dX = dY W, with W^T handed in as B).
 //
-//   * one persistent CTA per SM walks 128 x 128 output tiles, n-tile fastest (the CTAs that run side by side share the
-//     A rows through L2);
-//   * warp 0: TMA producer — per K-slab of 64 bf16 (= one 128-byte swizzle row) one A box and one B box {64, 128} into a
-//     5-stage ring; rows / channels out of range are zero-filled by the copy engine, so P, N, K need no padding;
-//   * warp 1: tcgen05.mma kind::f16 (M = 128, N = 128, K = 16), 4 per slab, into one of TWO TMEM accumulators;
-//     tcgen05.commit frees the stage / publishes the accumulator;
-//   * warps 2-5: epilogue — drain the other accumulator (tcgen05.ld, bf16 pack) into a 128-byte-swizzled staging tile in
-//     shared memory and hand it to the copy engine (cp.async.bulk.tensor store, two {64, 128} boxes; rows >= P and
+//   * one persistent CTA per SM walks 128 x 128 — or, for the K >= 256 layers, 128 x 256 — output tiles, n-tile fastest
+//     (the CTAs that run side by side share the A rows through L2);
+//   * warp 0 and the LAST warp: TMA producers — per K-slab of 64 bf16 (= one 128-byte swizzle row) one A box {64, 128}
+//     and one B box {64, 128 or 256} into a 3-5-stage ring (producer 0 issues the A boxes, producer 1 the B boxes: one
+//     thread issues a bulk copy every ~0.26 us whatever its size); rows / channels out of range are zero-filled by the
+//     copy engine, so P, N, K need no padding;
+//   * warp 1: tcgen05.mma kind::f16 (M = 128, N = 128 or 256, K = 16), 4 per slab, into one of TWO TMEM accumulators;
+//     tcgen05.commit frees the stage / publishes the accumulator.  The issuing thread costs ~130-190 cycles per MMA
+//     whatever N (profiles/r01/mma_loop.txt), hence N = 256 where there are many K steps per tile;
+//   * warps 2-5 (and 6-9): epilogue — drain the other accumulator (tcgen05.ld, bf16 pack) into a 128-byte-swizzled staging
+//     tile in shared memory and hand it to the copy engine (cp.async.bulk.tensor store, two {64, 128} boxes; rows >= P and
 //     columns >= N are clipped by the tensor map) while the tensor pipe fills the next accumulator.  (First version:
 //     every thread stored its own row with 16-byte st.global — 32 half-filled sectors per warp instruction; the store
 //     path, not HBM, bounded the memory-bound layers: 25.8 ms of GEMM per training step against ~14 ms of traffic.)
-//
-//   * the epilogue comes in TWO groups of 4 warps (tile parity = accumulator = group, one staging tile each): with one
-//     group every layer of this model ran at the epilogue's pace — ncu (profiles/r02/ncu_training.txt): 128 -> 128 and
-//     128 -> 256 on 10.5 M rows both at 34.3 % issue-active and ~3 000 cycles per tile, i.e. 75 % resp. 58 % of the DRAM
-//     peak although the tile's traffic differs by 1.35 x.
+//   * the epilogue comes in one or TWO groups of 4 warps, a staging tile each: with 128-column tiles the groups alternate
+//     tiles (tile parity = accumulator = group) — with one group the K <= 128 layers ran at the epilogue's pace (ncu,
+//     profiles/r02/ncu_training.txt: 128 -> 128 and 128 -> 256 on 10.5 M rows both at ~3 000 cycles per tile, 75 % resp.
+//     58 % of the DRAM peak although the tile's traffic differs by 1.35 x); with 256-column tiles they split every tile.
+//   What bounds a layer (profiles/r02/gemm_layers_v6.txt): HBM for the 10.5 M-row layers (0.9-1.0 of the copy bandwidth);
+//   for K, N >= 512 the operand traffic L2 -> SM (~40 B per cycle and SM, 11 TB/s in all: 384 KB per 128 x 256 x 512
+//   tile) — a cluster multicast of the shared operand is the next step there.
 //
 // BWD (input-gradient GEMM of block l, dX = dY W): the output tile IS the upstream gradient of block l-1, so the epilogue
 // also does what the first pass of that block's BatchNorm backward would do: the producer warp fetches the matching
@@ -29,13 +34,15 @@
 // accumulator is staged, the epilogue threads walk the tile COLUMN-wise (2 columns x 64 rows per thread, conflict-free),
 // mask the staged gradient with ReLU' / dropout of block l-1 in place, and accumulate sum g and sum g*y per column;
 // the MASKED tile goes out through the TMA store — s4g_train_bn_bwd_reduce never runs for a block whose gradient comes
-// out of a GEMM.  One epilogue group, two y tiles (so that the producer can run two tiles ahead).  First version, measured and replaced (profiles/r02/
-// gemm_layers_v1.txt): every thread read its own ROW of y from global memory and the column sums were a register
+// out of a GEMM.  One epilogue group, two y tiles (so that the producer can run two tiles ahead).  Measured: the column
+// walk is ~2 800 instructions per epilogue warp and tile at 0.36 IPC (one warp per scheduler) — 7 700 cycles per tile
+// against 3 700 of HBM time, slower than the plain GEMM + the staged separate pass; kept as an opt-in
+// (train_engine.FUSED_BWD_REDUCE).  A first version (profiles/r02/gemm_layers_v1.txt) was slower still: every thread read its own ROW of y from global memory and the column sums were a register
 // transpose-reduce over the warp (31 shuffles per 32 columns and quantity) — ~2 300 instructions per thread and tile,
 // 2.6 ms for the 128 -> 128 layer on 10.5 M rows against 0.87 ms for the plain GEMM + 0.9 ms for the separate pass.
 //
-// WS (weight-stationary, K <= 384: the slice must leave room for >= 5 A stages): a CTA keeps ONE n-tile for all its m-tiles and loads that [128][K] slice of B into
-// shared memory once; the ring then only carries A slabs (16 KB each, up to 6 in flight).  Without it every 128 x 128
+// WS (weight-stationary, 128-column tiles, K <= 384: the slice must leave room for >= 5 A stages): a CTA keeps ONE n-tile
+// for all its m-tiles and loads that [128][K] slice of B into shared memory once; the ring then only carries A slabs (16 KB each, up to 6 in flight).  Without it every 128 x 128
 // tile re-reads its B slice from L2 — ncu on the 264 -> 256 layer of the second set-abstraction level (2.1 M rows):
 // 30 % of the DRAM peak, tensor pipe 22 %, stalls `long_scoreboard`, 6.3 TB/s of L2 -> SM traffic, i.e. L2-bound
 // (profiles/r02/ncu_training.txt).  Measured per launch (profiles/r02/train_kernels_v5.txt): 3 -> 128 layer on 10.5 M rows
