@@ -42,6 +42,7 @@ def main():
                          "GPU (SURVEY.md §8a6); fp32 = IEEE")
     ap.add_argument("--fused-bwd-reduce", action="store_true", help="A/B: BatchNorm-backward sums in the dX GEMM's epilogue")
     ap.add_argument("--fp-split", action="store_true", help="A/B: finest propagation level with its conv on the sparse rows")
+    ap.add_argument("--interp-bwd-scatter", action="store_true", help="A/B: interpolation gradient by atomic scatter")
     ap.add_argument("--no-sparse-pool-reduce", action="store_true", help="A/B: pooled blocks reduce over all G*K rows")
     ap.add_argument("--epilogue-groups", type=int, default=0, choices=[0, 1, 2], help="A/B: GEMM epilogue warp groups")
     args = ap.parse_args()
@@ -69,6 +70,7 @@ def main():
     train_engine.FUSED_BWD_REDUCE = args.fused_bwd_reduce
     train_engine.SPARSE_POOL_REDUCE = not args.no_sparse_pool_reduce
     train_engine.FP_LINEAR_SPLIT = args.fp_split
+    train_engine.INTERP_BWD_GATHER = not args.interp_bwd_scatter
     if args.epilogue_groups:
         _lib.lib.s4g_gemm_bf16_set_epilogue_groups(args.epilogue_groups)
     B = args.batch

@@ -614,6 +614,82 @@ interp_rows_bwd_kernel(const __nv_bfloat16* __restrict__ dx, long long ld, const
   }
 }
 
+// ---- the same gradient as a GATHER over the inverse of the 3-NN index -------------------------------------------------
+// The scatter above issues 3 x rows x C2 fp32 atomic adds (1.26 G element-adds for 819 200 rows of 512 channels: 1.6 ms).
+// The 3-NN index is geometry (fixed for the step), so it is inverted once — count, exclusive scan (caller), fill — into
+// per-sparse-point lists of entries e = row * 3 + k, and every sparse row then SUMS its own list: dx rows are read three
+// times in all, the result is written once (fp32 or bf16), no atomics on the gradient.
+__global__ void __launch_bounds__(256)
+interp_inverse_count_kernel(const int* __restrict__ index, int Nk, long long per_b, long long entries, int* __restrict__ count) {
+  const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= entries) return;
+  const long long b = e / per_b;  // per_b = Nq * 3
+  atomicAdd(count + b * Nk + __ldg(index + e), 1);
+}
+__global__ void __launch_bounds__(256)
+interp_inverse_fill_kernel(const int* __restrict__ index, int Nk, long long per_b, long long entries, int* __restrict__ cursor,
+                           int* __restrict__ list) {
+  const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= entries) return;
+  const long long b = e / per_b;
+  list[atomicAdd(cursor + b * Nk + __ldg(index + e), 1)] = (int)e;
+}
+// thread = (16-byte piece, sparse-row lane); out row j = sum over its list of weight[e] * dx[e / 3]
+__global__ void __launch_bounds__(256)
+interp_rows_bwd_gather_kernel(const __nv_bfloat16* __restrict__ dx, long long ld, const int* __restrict__ list,
+                              const int* __restrict__ end, const int* __restrict__ count, const float* __restrict__ weight,
+                              long long sparse_rows, int C2, float* __restrict__ out_f32, __nv_bfloat16* __restrict__ out_bf16) {
+  const int pieces = C2 >> 3;
+  const int lanes = 256 / pieces;
+  const int piece = threadIdx.x % pieces, rl = threadIdx.x / pieces;
+  const long long j = (long long)blockIdx.x * lanes + rl;
+  if (rl >= lanes || j >= sparse_rows) return;
+  const int n = __ldg(count + j);
+  const int* src = list + (__ldg(end + j) - n);  // end = inclusive scan of count
+  F8 acc{};
+  int t = 0;
+  for (; t + 1 < n; t += 2) {  // two entries in flight
+    const int e0 = __ldg(src + t), e1 = __ldg(src + t + 1);
+    const float w0 = __ldg(weight + e0), w1 = __ldg(weight + e1);
+    const F8 v0 = unpack8(__ldg(reinterpret_cast<const uint4*>(dx + (long long)(e0 / 3) * ld) + piece));
+    const F8 v1 = unpack8(__ldg(reinterpret_cast<const uint4*>(dx + (long long)(e1 / 3) * ld) + piece));
+#pragma unroll
+    for (int c = 0; c < 8; ++c) acc.v[c] = fmaf(w0, v0.v[c], fmaf(w1, v1.v[c], acc.v[c]));
+  }
+  if (t < n) {
+    const int e0 = __ldg(src + t);
+    const float w0 = __ldg(weight + e0);
+    const F8 v0 = unpack8(__ldg(reinterpret_cast<const uint4*>(dx + (long long)(e0 / 3) * ld) + piece));
+#pragma unroll
+    for (int c = 0; c < 8; ++c) acc.v[c] = fmaf(w0, v0.v[c], acc.v[c]);
+  }
+  if (out_f32) {
+    float4* o = reinterpret_cast<float4*>(out_f32 + j * C2 + piece * 8);
+    o[0] = make_float4(acc.v[0], acc.v[1], acc.v[2], acc.v[3]);
+    o[1] = make_float4(acc.v[4], acc.v[5], acc.v[6], acc.v[7]);
+  }
+  if (out_bf16) reinterpret_cast<uint4*>(out_bf16 + j * C2)[piece] = pack8(acc);
+}
+
+// g = dz where relu'(y * scale + shift) else 0, rows [P][C] — the pooled gradient of a max-pooled block masked ONCE on its
+// G rows (y = the pre-activation at the arg-max, kept by bn_act_maxpool), so that the two passes over the G x K rows
+// run without the ReLU test
+__global__ void __launch_bounds__(256)
+relu_mask_rows_kernel(const __nv_bfloat16* __restrict__ dz, const __nv_bfloat16* __restrict__ y, const float* __restrict__ scale,
+                      const float* __restrict__ shift, long long P, int C, __nv_bfloat16* __restrict__ out) {
+  const int pieces = C >> 3;
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= P * pieces) return;
+  const int piece = (int)(i % pieces);
+  const F8 a = load_f8(scale + piece * 8), b = load_f8(shift + piece * 8);
+  const F8 v = unpack8(__ldg(reinterpret_cast<const uint4*>(y) + i));
+  F8 d = unpack8(__ldg(reinterpret_cast<const uint4*>(dz) + i));
+#pragma unroll
+  for (int e = 0; e < 8; ++e)
+    if (!(fmaf(v.v[e], a.v[e], b.v[e]) > 0.f)) d.v[e] = 0.f;
+  reinterpret_cast<uint4*>(out)[i] = pack8(d);
+}
+
 // fp32 [rows][C] -> bf16 (gradient buffers accumulated with atomics -> the next kernel's bf16 operand)
 __global__ void __launch_bounds__(256)
 f32_to_bf16_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ y, long long n8) {
@@ -1042,5 +1118,51 @@ extern "C" int s4g_train_head_logits_dw(const float* dlogits, const void* h, flo
   else if (k <= 9) head_logits_dw_kernel<9><<<grid, 256, smem, st>>>(dlogits, hh, dw, dbias, P, C, k, n_points);
   else head_logits_dw_kernel<kMaxLogits><<<grid, 256, smem, st>>>(dlogits, hh, dw, dbias, P, C, k, n_points);
   S4G_LAUNCH_CHECK("train_head_logits_dw");
+  return S4G_OK;
+}
+
+// inverse of the 3-NN index (B, Nq, 3) -> per sparse point (b, j) the list of entries e = (b * Nq + q) * 3 + k with
+// index[e] == j.  Step 1: count[B * Nk] (zeroed here).  The caller turns it into `end` = inclusive scan (int32).
+extern "C" int s4g_train_interp_inverse_count(const int* index, int B, int Nk, int Nq, int* count, void* stream) {
+  S4G_CHECK_ARG(index && count && B > 0 && Nk > 0 && Nq > 0 && (long long)B * Nq * 3 < (1ll << 31), "train_interp_inverse_count: bad arguments");
+  cudaStream_t st = (cudaStream_t)stream;
+  S4G_CUDA(cudaMemsetAsync(count, 0, sizeof(int) * (size_t)B * Nk, st));
+  const long long entries = (long long)B * Nq * 3;
+  interp_inverse_count_kernel<<<grid_for(entries, 256), 256, 0, st>>>(index, Nk, (long long)Nq * 3, entries, count);
+  S4G_LAUNCH_CHECK("train_interp_inverse_count");
+  return S4G_OK;
+}
+// Step 2: cursor[B * Nk] = the lists' start offsets (end - count) on entry, advanced to their ends; list[B * Nq * 3].
+extern "C" int s4g_train_interp_inverse_fill(const int* index, int B, int Nk, int Nq, int* cursor, int* list, void* stream) {
+  S4G_CHECK_ARG(index && cursor && list && B > 0 && Nk > 0 && Nq > 0, "train_interp_inverse_fill: bad arguments");
+  const long long entries = (long long)B * Nq * 3;
+  interp_inverse_fill_kernel<<<grid_for(entries, 256), 256, 0, (cudaStream_t)stream>>>(index, Nk, (long long)Nq * 3, entries, cursor, list);
+  S4G_LAUNCH_CHECK("train_interp_inverse_fill");
+  return S4G_OK;
+}
+// InterpolateBackward as a gather: out[b * Nk + j][c] = sum over the list of (b, j) of weight[e] * dx[e / 3][c]; written
+// (not accumulated) as fp32 and / or bf16 rows [B * Nk][C2] (either may be NULL).  The order inside a list is the fill's
+// (atomic cursor): the fp32 sum may differ in its last bits between runs, like the scatter's.
+extern "C" int s4g_train_interp_rows_bwd_gather(const void* dx, long long ld, const int* list, const int* end, const int* count,
+                                                const float* weight, int B, int Nk, int C2, float* out_f32, void* out_bf16,
+                                                void* stream) {
+  S4G_CHECK_ARG(dx && list && end && count && weight && (out_f32 || out_bf16) && B > 0 && Nk > 0 && C2 > 0 && C2 % 8 == 0 &&
+                    C2 <= 2048 && ld >= C2 && ld % 8 == 0,
+                "train_interp_rows_bwd_gather: bad arguments");
+  const long long sparse_rows = (long long)B * Nk;
+  const int lanes = 256 / (C2 >> 3);
+  interp_rows_bwd_gather_kernel<<<grid_for(sparse_rows, lanes), 256, 0, (cudaStream_t)stream>>>(
+      reinterpret_cast<const bf16*>(dx), ld, list, end, count, weight, sparse_rows, C2, out_f32, reinterpret_cast<bf16*>(out_bf16));
+  S4G_LAUNCH_CHECK("train_interp_rows_bwd_gather");
+  return S4G_OK;
+}
+
+extern "C" int s4g_train_relu_mask_rows_bf16(const void* dz, const void* y, const float* scale, const float* shift, long long P,
+                                             int C, void* out, void* stream) {
+  S4G_CHECK_ARG(dz && y && scale && shift && out && P > 0, "train_relu_mask_rows: bad arguments");
+  TRN_CHECK_C(C);
+  relu_mask_rows_kernel<<<grid_for(P * (C >> 3), 256), 256, 0, (cudaStream_t)stream>>>(
+      reinterpret_cast<const bf16*>(dz), reinterpret_cast<const bf16*>(y), scale, shift, P, C, reinterpret_cast<bf16*>(out));
+  S4G_LAUNCH_CHECK("train_relu_mask_rows");
   return S4G_OK;
 }

@@ -191,7 +191,12 @@ class Block:
         else:
             sums = torch.empty(2 * C, dtype=torch.float64, device=dev)
             if pool_k and ymax is not None:  # the G arg-max rows carry the whole gradient
-                check(lib.s4g_train_bn_bwd_reduce_bf16(ptr(dz), None, 0, ptr(ymax), ptr(scale), ptr(shift), P // pool_k, C, 1,
+                # ReLU' applied ONCE on the G pooled rows (y at the arg-max is ymax); both passes then skip the test
+                dzm = torch.empty_like(dz)
+                check(lib.s4g_train_relu_mask_rows_bf16(ptr(dz), ptr(ymax), ptr(scale), ptr(shift), P // pool_k, C, ptr(dzm),
+                                                        stream_ptr(dev)), "train_relu_mask_rows")
+                dz, relu = dzm, 0
+                check(lib.s4g_train_bn_bwd_reduce_bf16(ptr(dz), None, 0, ptr(ymax), ptr(scale), ptr(shift), P // pool_k, C, 0,
                                                        seed, 0.0, ptr(sums), stream_ptr(dev)), "train_bn_bwd_reduce")
             else:
                 check(lib.s4g_train_bn_bwd_reduce_bf16(ptr(dz), ptr(arg) if pool_k else None, pool_k, ptr(y), ptr(scale),
@@ -243,6 +248,33 @@ def _sum_rows(parts):
     out = torch.empty_like(parts[0])
     q = [ptr(p) for p in parts] + [None] * (4 - len(parts))
     check(lib.s4g_train_sum_bf16(q[0], q[1], q[2], q[3], ptr(out), out.numel(), stream_ptr(out.device)), "train_sum_bf16")
+    return out
+
+
+# gradient of the interpolation as a gather over the inverted 3-NN index (no atomics, written once) or as the scatter
+INTERP_BWD_GATHER = True
+
+
+def interp_rows_backward(dz, idx3, w, B, Nk, Nq, c2, want_f32):
+    """d(sparse features) [B*Nk, c2] of out[q] = sum_k w[q,k] * sparse[idx3[q,k]] from dz [B*Nq, >= c2] bf16 (its first c2
+    columns); fp32 when ``want_f32`` (it is added to another gradient), else bf16 (it feeds the next block's backward)."""
+    dev = dz.device
+    st = stream_ptr(dev)
+    if not INTERP_BWD_GATHER:
+        d_sparse = torch.zeros((B * Nk, c2), dtype=torch.float32, device=dev)
+        check(lib.s4g_train_interp_rows_bwd(ptr(dz), dz.stride(0), ptr(idx3), ptr(w), B, Nk, Nq, c2, ptr(d_sparse), st),
+              "train_interp_rows_bwd")
+        return d_sparse if want_f32 else d_sparse.to(BF16)
+    count = torch.empty(B * Nk, dtype=torch.int32, device=dev)
+    check(lib.s4g_train_interp_inverse_count(ptr(idx3), B, Nk, Nq, ptr(count), st), "train_interp_inverse_count")
+    end = torch.cumsum(count, 0, dtype=torch.int32)
+    cursor = end - count
+    lst = torch.empty(B * Nq * 3, dtype=torch.int32, device=dev)
+    check(lib.s4g_train_interp_inverse_fill(ptr(idx3), B, Nk, Nq, ptr(cursor), ptr(lst), st), "train_interp_inverse_fill")
+    out = torch.empty((B * Nk, c2), dtype=torch.float32 if want_f32 else BF16, device=dev)
+    check(lib.s4g_train_interp_rows_bwd_gather(ptr(dz), dz.stride(0), ptr(lst), ptr(end), ptr(count), ptr(w), B, Nk, c2,
+                                               ptr(out) if want_f32 else None, None if want_f32 else ptr(out), st),
+          "train_interp_rows_bwd_gather")
     return out
 
 
@@ -404,11 +436,8 @@ class TrainEngine:
             if split:
                 blk0 = self.fp[i][0]
                 dy, x_sparse, wb = chain_backward(self.fp[i], d_out)  # d(pre-activations) of the first block, dense rows
-                d_ys = torch.zeros((B * Nk, blk0.cout), dtype=torch.float32, device=dev)
-                check(lib.s4g_train_interp_rows_bwd(ptr(dy), dy.stride(0), ptr(idx3), ptr(w), B, Nk, Nq, blk0.cout, ptr(d_ys),
-                                                    stream_ptr(dev)), "train_interp_rows_bwd")
+                d_ys = interp_rows_backward(dy, idx3, w, B, Nk, Nq, blk0.cout, want_f32=False)
                 del dy
-                d_ys = d_ys.to(BF16)
                 _accumulate(blk0.conv.weight, torch.mm(d_ys.t(), x_sparse, out_dtype=torch.float32)[:, :blk0.cin]
                             .reshape(blk0.conv.weight.shape))
                 d_feat = gemm(d_ys, wb[:, :c2].t().contiguous())  # gradient of the sparse level's features [B*Nk, c2]
@@ -421,13 +450,11 @@ class TrainEngine:
             # dz rows = [d interpolated (c2) | d dense skip (c1)]
             if c1:
                 lv_grad[-2 - i].add_(dz[:, c2:c2 + c1])
-            d_sparse = torch.zeros((B * Nk, c2), dtype=torch.float32, device=dev)
-            check(lib.s4g_train_interp_rows_bwd(ptr(dz), dz.stride(0), ptr(idx3), ptr(w), B, Nk, Nq, c2, ptr(d_sparse),
-                                                stream_ptr(dev)), "train_interp_rows_bwd")
+            d_sparse = interp_rows_backward(dz, idx3, w, B, Nk, Nq, c2, want_f32=(i == 0))
             if i == 0:
                 lv_grad[-1].add_(d_sparse)  # the coarsest propagation level interpolates the last SA level's features
             else:
-                d_out = d_sparse.to(BF16)
+                d_out = d_sparse
         for i in reversed(range(len(self.sa))):
             blocks = self.sa[i]
             nbr, B, N, M, K, cf = self._sa_ctx[i]

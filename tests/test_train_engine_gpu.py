@@ -480,6 +480,26 @@ def test_interp_rows_backward():
     for k in range(3):
         want.scatter_add_(1, idx[:, :, k].long().unsqueeze(-1).expand(-1, -1, C), d * w[:, :, k:k + 1])
     assert torch.allclose(ds, want.reshape(-1, C), atol=1e-4, rtol=1e-5)
+    # the gather over the inverted index (what the engine uses): fp32 and bf16 outputs, points nobody references stay zero
+    from s4g_release_b200 import train_engine as te
+    idx[:, :, :] = torch.where(idx == 7, idx + 1, idx)  # sparse point 7 has an empty list
+    want = torch.zeros(B, Nk, C, device="cuda")
+    for k in range(3):
+        want.scatter_add_(1, idx[:, :, k].long().unsqueeze(-1).expand(-1, -1, C), d * w[:, :, k:k + 1])
+    for f32 in (True, False):
+        got = te.interp_rows_backward(dx, idx, w, B, Nk, Nq, C, want_f32=f32)
+        torch.cuda.synchronize()
+        assert got.dtype == (torch.float32 if f32 else BF)
+        tol = 1e-4 if f32 else 2 ** -7 * want.abs().max().item()
+        assert (got.float() - want.reshape(-1, C)).abs().max().item() <= tol
+        assert (got.float().reshape(B, Nk, C)[:, 7] == 0).all()
+    prev = te.INTERP_BWD_GATHER
+    te.INTERP_BWD_GATHER = False
+    try:
+        old = te.interp_rows_backward(dx, idx, w, B, Nk, Nq, C, want_f32=True)
+    finally:
+        te.INTERP_BWD_GATHER = prev
+    assert torch.allclose(old, want.reshape(-1, C), atol=1e-4, rtol=1e-5)
 
 
 CFG = dict(score_classes=3, num_centroids=(256, 64, 16), radius=(0.1, 0.2, 0.4), num_neighbours=(16, 16, 8),
