@@ -206,13 +206,17 @@ int s4g_train_group_rows_bwd(const void* dx, long long ld, const int* nbr, int B
 /* InterpolateBackward (interpolate_kernel.cu:243-286) in the row layout: dsparse[b*Nk + idx_k][c] += w_k * dx[(b,q)][c]. */
 int s4g_train_interp_rows_bwd(const void* dx, long long ld, const int* index, const float* weight, int B, int Nk, int Nq,
                               int C2, float* dsparse, void* stream);
-/* The same gradient as a GATHER over the inverse of the 3-NN index (geometry, fixed for the step): count -> (caller:
- * inclusive scan `end`, start = end - count) -> fill -> every sparse row sums its own list; no atomics on the gradient,
- * dx rows read three times, the result written once as fp32 and / or bf16 (either may be NULL).  entries e = (b*Nq+q)*3+k. */
-int s4g_train_interp_inverse_count(const int* index, int B, int Nk, int Nq, int* count, void* stream);
-int s4g_train_interp_inverse_fill(const int* index, int B, int Nk, int Nq, int* cursor, int* list, void* stream);
-int s4g_train_interp_rows_bwd_gather(const void* dx, long long ld, const int* list, const int* end, const int* count,
-                                     const float* weight, int B, int Nk, int C2, float* out_f32, void* out_bf16, void* stream);
+/* The scatter-add gradients (InterpolateBackward, GroupPointsBackward) as a GATHER over the INVERSE of their index
+ * tensor (geometry, fixed for the step).  index (B, E) with values in [0, T): the 3-NN index (E = Nq * 3, T = Nk) or the
+ * neighbour index (E = M * K, T = N).  count -> (caller: inclusive scan `end`, start = end - count) -> fill -> every target
+ * row sums its own list of entries e = b * E + i:  out[b*T + j][c] (+)= sum weight[e] * dx[e / div][c]  (div = 3 with the
+ * interpolation weights; div = 1, weight NULL for the grouping).  No atomics on the gradient; written once as fp32
+ * and / or bf16 (either may be NULL); accumulate != 0 adds into out_f32. */
+int s4g_train_index_inverse_count(const int* index, int B, int T, long long E, int* count, void* stream);
+int s4g_train_index_inverse_fill(const int* index, int B, int T, long long E, int* cursor, int* list, void* stream);
+int s4g_train_rows_bwd_gather(const void* dx, long long ld, const int* list, const int* end, const int* count,
+                              const float* weight, int div, long long targets, int C, int accumulate, float* out_f32,
+                              void* out_bf16, void* stream);
 /* out = dz where y * scale + shift > 0, else 0 (rows [P][C], contiguous): the pooled gradient of a max-pooled block masked
  * once on its G rows (y = ymax of s4g_train_bn_act_maxpool_bf16); the two BatchNorm-backward passes then run with relu = 0. */
 int s4g_train_relu_mask_rows_bf16(const void* dz, const void* y, const float* scale, const float* shift, long long P, int C,

@@ -77,9 +77,9 @@ _SIGNATURES = {
     "s4g_train_group_rows_bwd": ([_vp, _ll, _vp, _i, _i, _i, _i, _i, _vp, _vp], _i),
     "s4g_train_interp_rows_bwd": ([_vp, _ll, _vp, _vp, _i, _i, _i, _i, _vp, _vp], _i),
     "s4g_train_relu_mask_rows_bf16": ([_vp, _vp, _vp, _vp, _ll, _i, _vp, _vp], _i),
-    "s4g_train_interp_inverse_count": ([_vp, _i, _i, _i, _vp, _vp], _i),
-    "s4g_train_interp_inverse_fill": ([_vp, _i, _i, _i, _vp, _vp, _vp], _i),
-    "s4g_train_interp_rows_bwd_gather": ([_vp, _ll, _vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp], _i),
+    "s4g_train_index_inverse_count": ([_vp, _i, _i, _ll, _vp, _vp], _i),
+    "s4g_train_index_inverse_fill": ([_vp, _i, _i, _ll, _vp, _vp, _vp], _i),
+    "s4g_train_rows_bwd_gather": ([_vp, _ll, _vp, _vp, _vp, _vp, _i, _ll, _i, _i, _vp, _vp, _vp], _i),
     "s4g_train_f32_to_bf16": ([_vp, _vp, _ll, _vp], _i),
     "s4g_train_head_logits_fwd": ([_vp, _vp, _vp, _vp, _ll, _i, _i, _i, _vp], _i),
     "s4g_train_head_logits_bwd": ([_vp, _vp, _vp, _ll, _i, _i, _i, _vp], _i),

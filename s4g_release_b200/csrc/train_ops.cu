@@ -634,11 +634,14 @@ interp_inverse_fill_kernel(const int* __restrict__ index, int Nk, long long per_
   const long long b = e / per_b;
   list[atomicAdd(cursor + b * Nk + __ldg(index + e), 1)] = (int)e;
 }
-// thread = (16-byte piece, sparse-row lane); out row j = sum over its list of weight[e] * dx[e / 3]
+// thread = (16-byte piece, target-row lane); out row j (+)= sum over its list of weight[e] * dx[e / DIV]
+// (DIV = 3, weights: interpolation;  DIV = 1, no weights: grouping — entry e IS the gathered row (b, m, k))
+template <int DIV>
 __global__ void __launch_bounds__(256)
-interp_rows_bwd_gather_kernel(const __nv_bfloat16* __restrict__ dx, long long ld, const int* __restrict__ list,
-                              const int* __restrict__ end, const int* __restrict__ count, const float* __restrict__ weight,
-                              long long sparse_rows, int C2, float* __restrict__ out_f32, __nv_bfloat16* __restrict__ out_bf16) {
+rows_bwd_gather_kernel(const __nv_bfloat16* __restrict__ dx, long long ld, const int* __restrict__ list,
+                       const int* __restrict__ end, const int* __restrict__ count, const float* __restrict__ weight,
+                       long long sparse_rows, int C2, int accumulate, float* __restrict__ out_f32,
+                       __nv_bfloat16* __restrict__ out_bf16) {
   const int pieces = C2 >> 3;
   const int lanes = 256 / pieces;
   const int piece = threadIdx.x % pieces, rl = threadIdx.x / pieces;
@@ -650,21 +653,26 @@ interp_rows_bwd_gather_kernel(const __nv_bfloat16* __restrict__ dx, long long ld
   int t = 0;
   for (; t + 1 < n; t += 2) {  // two entries in flight
     const int e0 = __ldg(src + t), e1 = __ldg(src + t + 1);
-    const float w0 = __ldg(weight + e0), w1 = __ldg(weight + e1);
-    const F8 v0 = unpack8(__ldg(reinterpret_cast<const uint4*>(dx + (long long)(e0 / 3) * ld) + piece));
-    const F8 v1 = unpack8(__ldg(reinterpret_cast<const uint4*>(dx + (long long)(e1 / 3) * ld) + piece));
+    const float w0 = weight ? __ldg(weight + e0) : 1.f, w1 = weight ? __ldg(weight + e1) : 1.f;
+    const F8 v0 = unpack8(__ldg(reinterpret_cast<const uint4*>(dx + (long long)(e0 / DIV) * ld) + piece));
+    const F8 v1 = unpack8(__ldg(reinterpret_cast<const uint4*>(dx + (long long)(e1 / DIV) * ld) + piece));
 #pragma unroll
     for (int c = 0; c < 8; ++c) acc.v[c] = fmaf(w0, v0.v[c], fmaf(w1, v1.v[c], acc.v[c]));
   }
   if (t < n) {
     const int e0 = __ldg(src + t);
-    const float w0 = __ldg(weight + e0);
-    const F8 v0 = unpack8(__ldg(reinterpret_cast<const uint4*>(dx + (long long)(e0 / 3) * ld) + piece));
+    const float w0 = weight ? __ldg(weight + e0) : 1.f;
+    const F8 v0 = unpack8(__ldg(reinterpret_cast<const uint4*>(dx + (long long)(e0 / DIV) * ld) + piece));
 #pragma unroll
     for (int c = 0; c < 8; ++c) acc.v[c] = fmaf(w0, v0.v[c], acc.v[c]);
   }
   if (out_f32) {
     float4* o = reinterpret_cast<float4*>(out_f32 + j * C2 + piece * 8);
+    if (accumulate) {  // (the row is this thread's alone: a plain read-modify-write)
+      const float4 p0 = o[0], p1 = o[1];
+      acc.v[0] += p0.x; acc.v[1] += p0.y; acc.v[2] += p0.z; acc.v[3] += p0.w;
+      acc.v[4] += p1.x; acc.v[5] += p1.y; acc.v[6] += p1.z; acc.v[7] += p1.w;
+    }
     o[0] = make_float4(acc.v[0], acc.v[1], acc.v[2], acc.v[3]);
     o[1] = make_float4(acc.v[4], acc.v[5], acc.v[6], acc.v[7]);
   }
@@ -745,61 +753,98 @@ __global__ void bn_bwd_finalize_kernel(const double* __restrict__ sums, long lon
 // per row; the k x C weight matrix lives in shared memory (broadcast reads).
 constexpr int kMaxLogits = 16;
 
+// Tiles of kHeadRows rows.  (First versions: one thread per row walking its 256-byte row piece by piece — every warp load
+// and store touched 32 different rows, 0.11 / 0.15 ms per head for 0.03 ms of traffic.)
+constexpr int kHeadRows = 128;
+
+// forward: the h tile is staged in shared memory with coalesced 16-byte loads (row stride 2 C + 16 bytes: conflict-free
+// 16-byte reads by row); thread = (row, half of the k outputs); the stores of one output j are consecutive in n
 __global__ void __launch_bounds__(256)
 head_logits_fwd_kernel(const __nv_bfloat16* __restrict__ h, const float* __restrict__ w, const float* __restrict__ bias,
-                       float* __restrict__ out, long long P, int C, int k, int n_points) {
-  extern __shared__ float s_w[];  // [k][C]
-  for (int i = threadIdx.x; i < k * C; i += blockDim.x) s_w[i] = w[i];
+                       float* __restrict__ out, int P, int C, int k, int n_points) {
+  extern __shared__ __align__(16) uint8_t s_raw[];
+  float* s_w = reinterpret_cast<float*>(s_raw);                 // [k][C]
+  uint8_t* s_h = s_raw + sizeof(float) * (size_t)k * C;         // [kHeadRows][2 C + 16]
+  const int pieces = C >> 3, stride = 2 * C + 16;
+  for (int i = threadIdx.x; i < k * C; i += 256) s_w[i] = w[i];
+  const int row0 = blockIdx.x * kHeadRows;
+  const int rows = min(kHeadRows, P - row0);
+  for (int i = threadIdx.x; i < rows * pieces; i += 256) {
+    const int r = i / pieces, pc = i - r * pieces;
+    *reinterpret_cast<uint4*>(s_h + (size_t)r * stride + pc * 16) = __ldg(reinterpret_cast<const uint4*>(h + (size_t)(row0 + r) * C) + pc);
+  }
   __syncthreads();
-  const long long row = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (row >= P) return;
-  float acc[kMaxLogits];
+  const int r = threadIdx.x & (kHeadRows - 1), half = threadIdx.x >> 7;  // outputs j = half, half + 2, ...
+  if (r >= rows) return;
+  float acc[kMaxLogits / 2];
 #pragma unroll
-  for (int j = 0; j < kMaxLogits; ++j) acc[j] = j < k ? __ldg(bias + j) : 0.f;
-  const uint4* src = reinterpret_cast<const uint4*>(h + row * C);
-  for (int p = 0; p < (C >> 3); ++p) {
-    const F8 v = unpack8(__ldg(src + p));
+  for (int q = 0; q < kMaxLogits / 2; ++q) acc[q] = (2 * q + half) < k ? __ldg(bias + 2 * q + half) : 0.f;
+  for (int pc = 0; pc < pieces; ++pc) {
+    const F8 v = unpack8(*reinterpret_cast<const uint4*>(s_h + (size_t)r * stride + pc * 16));
 #pragma unroll
-    for (int j = 0; j < kMaxLogits; ++j) {
+    for (int q = 0; q < kMaxLogits / 2; ++q) {
+      const int j = 2 * q + half;
       if (j < k) {
-        const float* wj = s_w + j * C + p * 8;
-#pragma unroll
-        for (int e = 0; e < 8; ++e) acc[j] = fmaf(v.v[e], wj[e], acc[j]);
+        const float4* wj = reinterpret_cast<const float4*>(s_w + j * C + pc * 8);  // warp-uniform: broadcast
+        const float4 w0 = wj[0], w1 = wj[1];
+        acc[q] = fmaf(v.v[0], w0.x, fmaf(v.v[1], w0.y, fmaf(v.v[2], w0.z, fmaf(v.v[3], w0.w, acc[q]))));
+        acc[q] = fmaf(v.v[4], w1.x, fmaf(v.v[5], w1.y, fmaf(v.v[6], w1.z, fmaf(v.v[7], w1.w, acc[q]))));
       }
     }
   }
-  const long long b = row / n_points, n = row - b * n_points;
-  float* o = out + (b * k) * n_points + n;
+  const int row = row0 + r;
+  const int b = row / n_points, n = row - b * n_points;
+  float* o = out + ((size_t)b * k) * n_points + n;
 #pragma unroll
-  for (int j = 0; j < kMaxLogits; ++j)
-    if (j < k) o[(long long)j * n_points] = acc[j];
+  for (int q = 0; q < kMaxLogits / 2; ++q)
+    if (2 * q + half < k) o[(size_t)(2 * q + half) * n_points] = acc[q];
 }
 
-// dh[row][c] = sum_j dlogits[b][j][n] * w[j][c]   (bf16 rows out)
+// dh[row][c] = sum_j dlogits[b][j][n] * w[j][c]   (bf16 rows out): the tile's k x rows gradients are staged in shared
+// memory (coalesced), thread = (16-byte piece of the row, row lane) keeps its k x 8 weights in registers and stores
+// 16-byte pieces next to its neighbours'
+template <int KT>
 __global__ void __launch_bounds__(256)
-head_logits_bwd_kernel(const float* __restrict__ dl, const float* __restrict__ w, __nv_bfloat16* __restrict__ dh, long long P,
+head_logits_bwd_kernel(const float* __restrict__ dl, const float* __restrict__ w, __nv_bfloat16* __restrict__ dh, int P,
                        int C, int k, int n_points) {
-  extern __shared__ float s_w[];  // [k][C]
-  for (int i = threadIdx.x; i < k * C; i += blockDim.x) s_w[i] = w[i];
-  __syncthreads();
-  const long long row = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (row >= P) return;
-  const long long b = row / n_points, n = row - b * n_points;
-  float g[kMaxLogits];
+  __shared__ float s_g[KT][kHeadRows];
+  const int pieces = C >> 3, lanes = 256 / pieces;
+  const int row0 = blockIdx.x * kHeadRows;
+  const int rows = min(kHeadRows, P - row0);
+  for (int i = threadIdx.x; i < k * kHeadRows; i += 256) {
+    const int j = i / kHeadRows, r = i - j * kHeadRows;
+    float g = 0.f;
+    if (r < rows) {
+      const int row = row0 + r;
+      const int b = row / n_points, n = row - b * n_points;
+      g = __ldg(dl + ((size_t)b * k + j) * n_points + n);
+    }
+    s_g[j][r] = g;
+  }
+  const int piece = threadIdx.x % pieces, rl = threadIdx.x / pieces;
+  float wr[KT][8];
 #pragma unroll
-  for (int j = 0; j < kMaxLogits; ++j) g[j] = j < k ? __ldg(dl + (b * k + j) * n_points + n) : 0.f;
-  uint4* dst = reinterpret_cast<uint4*>(dh + row * C);
-  for (int p = 0; p < (C >> 3); ++p) {
+  for (int j = 0; j < KT; ++j) {
+    if (j < k && rl < lanes) {
+      const F8 t = load_f8(w + (size_t)j * C + piece * 8);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) wr[j][e] = t.v[e];
+    } else {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) wr[j][e] = 0.f;
+    }
+  }
+  __syncthreads();
+  if (rl >= lanes) return;
+  for (int r = rl; r < rows; r += lanes) {
     F8 o{};
 #pragma unroll
-    for (int j = 0; j < kMaxLogits; ++j) {
-      if (j < k) {
-        const float* wj = s_w + j * C + p * 8;
+    for (int j = 0; j < KT; ++j) {
+      const float g = s_g[j][r];  // (zero for j >= k)
 #pragma unroll
-        for (int e = 0; e < 8; ++e) o.v[e] = fmaf(g[j], wj[e], o.v[e]);
-      }
+      for (int e = 0; e < 8; ++e) o.v[e] = fmaf(g, wr[j][e], o.v[e]);
     }
-    dst[p] = pack8(o);
+    reinterpret_cast<uint4*>(dh + (size_t)(row0 + r) * C)[piece] = pack8(o);
   }
 }
 
@@ -819,74 +864,80 @@ sum_bf16_kernel(const uint4* __restrict__ a, const uint4* __restrict__ b, const 
 }
 
 // dw[j][c] += sum_row dlogits[b][j][n] * h[row][c],  dbias[j] += sum_row dlogits[b][j][n]   (fp32 atomics, k <= KT)
-// thread = (16-byte piece of h, row lane); a block walks kDwRows rows, reduces over its row lanes in shared memory
-constexpr int kDwRows = 512;  // (2048: 400 blocks on 296 slots, one latency-bound row at a time -> 0.5 ms per head)
+// thread = (16-byte piece of h, row lane); a block walks kDwTiles tiles of kHeadRows rows — the tile's k x rows gradients
+// staged in shared memory (coalesced loads, broadcast reads), two rows of h in flight per thread — and reduces over its
+// row lanes in shared memory at the end.  (First version: k scalar global loads per row and thread, 152 registers, one
+// block per SM: 0.22 ms per head for 0.03 ms of traffic.)
+constexpr int kDwTiles = 4;
 template <int KT>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, KT > 9 ? 1 : 2)
 head_logits_dw_kernel(const float* __restrict__ dl, const __nv_bfloat16* __restrict__ h, float* __restrict__ dw,
-                      float* __restrict__ dbias, long long P, int C, int k, int n_points) {
+                      float* __restrict__ dbias, int P, int C, int k, int n_points) {
   extern __shared__ float s_red[];  // [lanes][C]
-  __shared__ float s_b[256];
+  __shared__ float s_g[KT][kHeadRows];
   const int pieces = C >> 3;
   const int lanes = 256 / pieces;
   const int piece = threadIdx.x % pieces, rl = threadIdx.x / pieces;
-  const long long r0 = (long long)blockIdx.x * kDwRows, r1 = min(P, r0 + kDwRows);
   float acc[KT][8];
-  float accb[KT];
+  float accb = 0.f;  // thread j < k: the bias gradient of output j
 #pragma unroll
   for (int j = 0; j < KT; ++j) {
-    accb[j] = 0.f;
 #pragma unroll
     for (int e = 0; e < 8; ++e) acc[j][e] = 0.f;
   }
-  if (rl < lanes) {
-    for (long long r = r0 + rl; r < r1; r += 2LL * lanes) {  // two rows in flight
-      const long long rb = r + lanes;
-      const bool two = rb < r1;
-      const uint4 raw0 = __ldg(reinterpret_cast<const uint4*>(h + r * C) + piece);
-      const uint4 raw1 = two ? __ldg(reinterpret_cast<const uint4*>(h + rb * C) + piece) : make_uint4(0u, 0u, 0u, 0u);
-      const long long b0 = r / n_points, n0 = r - b0 * n_points;
-      const long long b1 = two ? rb / n_points : b0, n1 = two ? rb - b1 * n_points : n0;
-      const float* g0 = dl + (b0 * k) * n_points + n0;
-      const float* g1 = dl + (b1 * k) * n_points + n1;
-      float gj0[KT], gj1[KT];
-#pragma unroll
-      for (int j = 0; j < KT; ++j) {
-        gj0[j] = j < k ? __ldg(g0 + (long long)j * n_points) : 0.f;
-        gj1[j] = (j < k && two) ? __ldg(g1 + (long long)j * n_points) : 0.f;
+  for (int tile = 0; tile < kDwTiles; ++tile) {
+    const int row0 = (blockIdx.x * kDwTiles + tile) * kHeadRows;
+    if (row0 >= P) break;  // (block-uniform)
+    const int rows = min(kHeadRows, P - row0);
+    __syncthreads();  // the previous tile's gradients have been consumed
+    for (int i = threadIdx.x; i < k * kHeadRows; i += 256) {
+      const int j = i / kHeadRows, r = i - j * kHeadRows;
+      float g = 0.f;
+      if (r < rows) {
+        const int row = row0 + r;
+        const int b = row / n_points, n = row - b * n_points;
+        g = __ldg(dl + ((size_t)b * k + j) * n_points + n);
       }
-      const F8 v0 = unpack8(raw0), v1 = unpack8(raw1);
+      s_g[j][r] = g;
+    }
+    __syncthreads();
+    if (threadIdx.x < k) {
+      float t = 0.f;
+      for (int r = 0; r < rows; ++r) t += s_g[threadIdx.x][r];
+      accb += t;
+    }
+    if (rl < lanes) {
+      for (int r = rl; r < rows; r += 2 * lanes) {
+        const int r1 = r + lanes;
+        const bool two = r1 < rows;
+        const uint4 raw0 = __ldg(reinterpret_cast<const uint4*>(h + (size_t)(row0 + r) * C) + piece);
+        const uint4 raw1 = two ? __ldg(reinterpret_cast<const uint4*>(h + (size_t)(row0 + r1) * C) + piece) : make_uint4(0u, 0u, 0u, 0u);
+        const F8 v0 = unpack8(raw0), v1 = unpack8(raw1);
 #pragma unroll
-      for (int j = 0; j < KT; ++j) {
-        if (j < k) {
-          accb[j] += gj0[j] + gj1[j];
+        for (int j = 0; j < KT; ++j) {
+          const float g0 = s_g[j][r], g1 = two ? s_g[j][r1] : 0.f;  // (rows j >= k hold stale or zero values: never reduced)
 #pragma unroll
-          for (int e = 0; e < 8; ++e) acc[j][e] = fmaf(gj0[j], v0.v[e], fmaf(gj1[j], v1.v[e], acc[j][e]));
+          for (int e = 0; e < 8; ++e) acc[j][e] = fmaf(g0, v0.v[e], fmaf(g1, v1.v[e], acc[j][e]));
         }
       }
     }
   }
+  if (threadIdx.x < k) atomicAdd(dbias + threadIdx.x, accb);
 #pragma unroll
   for (int j = 0; j < KT; ++j) {
     if (j < k) {  // (k is block-uniform: the barriers below are reached by every thread)
+      __syncthreads();
       if (rl < lanes) {
         float* dst = s_red + (size_t)rl * C + piece * 8;
 #pragma unroll
         for (int e = 0; e < 8; ++e) dst[e] = acc[j][e];
       }
-      if (piece == 0 && rl < lanes) s_b[rl] = accb[j];
       __syncthreads();
       for (int c = threadIdx.x; c < C; c += 256) {
         float t = 0.f;
         for (int l = 0; l < lanes; ++l) t += s_red[(size_t)l * C + c];
         atomicAdd(dw + (size_t)j * C + c, t);
       }
-      if (threadIdx.x == 0) {
-        float t = 0.f;
-        for (int l = 0; l < lanes; ++l) t += s_b[l];
-        atomicAdd(dbias + j, t);
-      }
-      __syncthreads();
     }
   }
 }
@@ -1077,8 +1128,13 @@ extern "C" int s4g_train_head_logits_fwd(const void* h, const float* w, const fl
   S4G_CHECK_ARG(h && w && bias && out && P > 0 && k > 0 && k <= kMaxLogits && n_points > 0 && P % n_points == 0,
                 "train_head_logits_fwd: bad arguments");
   TRN_CHECK_C(C);
-  head_logits_fwd_kernel<<<grid_for(P, 256), 256, sizeof(float) * k * C, (cudaStream_t)stream>>>(
-      reinterpret_cast<const bf16*>(h), w, bias, out, P, C, k, n_points);
+  S4G_CHECK_ARG(P < (1ll << 31) && C <= 512, "train_head_logits_fwd: at most 512 channels");
+  const size_t smem = sizeof(float) * (size_t)k * C + (size_t)kHeadRows * (2 * C + 16);
+  static bool attr[64] = {};
+  if (s4g::first_use_on_device(attr))
+    S4G_CUDA(cudaFuncSetAttribute(head_logits_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  head_logits_fwd_kernel<<<grid_for(P, kHeadRows), 256, smem, (cudaStream_t)stream>>>(
+      reinterpret_cast<const bf16*>(h), w, bias, out, (int)P, C, k, n_points);
   S4G_LAUNCH_CHECK("train_head_logits_fwd");
   return S4G_OK;
 }
@@ -1088,8 +1144,13 @@ extern "C" int s4g_train_head_logits_bwd(const float* dlogits, const float* w, v
   S4G_CHECK_ARG(dlogits && w && dh && P > 0 && k > 0 && k <= kMaxLogits && n_points > 0 && P % n_points == 0,
                 "train_head_logits_bwd: bad arguments");
   TRN_CHECK_C(C);
-  head_logits_bwd_kernel<<<grid_for(P, 256), 256, sizeof(float) * k * C, (cudaStream_t)stream>>>(
-      dlogits, w, reinterpret_cast<bf16*>(dh), P, C, k, n_points);
+  S4G_CHECK_ARG(P < (1ll << 31), "train_head_logits_bwd: too many rows");
+  const unsigned grid = grid_for(P, kHeadRows);
+  cudaStream_t st = (cudaStream_t)stream;
+  bf16* out = reinterpret_cast<bf16*>(dh);
+  if (k <= 4) head_logits_bwd_kernel<4><<<grid, 256, 0, st>>>(dlogits, w, out, (int)P, C, k, n_points);
+  else if (k <= 9) head_logits_bwd_kernel<9><<<grid, 256, 0, st>>>(dlogits, w, out, (int)P, C, k, n_points);
+  else head_logits_bwd_kernel<kMaxLogits><<<grid, 256, 0, st>>>(dlogits, w, out, (int)P, C, k, n_points);
   S4G_LAUNCH_CHECK("train_head_logits_bwd");
   return S4G_OK;
 }
@@ -1110,50 +1171,58 @@ extern "C" int s4g_train_head_logits_dw(const float* dlogits, const void* h, flo
   S4G_CHECK_ARG(dlogits && h && dw && dbias && P > 0 && k > 0 && k <= kMaxLogits && n_points > 0 && P % n_points == 0,
                 "train_head_logits_dw: bad arguments");
   TRN_CHECK_C(C);
+  S4G_CHECK_ARG(P < (1ll << 31), "train_head_logits_dw: too many rows");
   const size_t smem = sizeof(float) * 2048;  // lanes * C = (256 / pieces) * pieces * 8 <= 2048
-  const unsigned grid = grid_for(P, kDwRows);
+  const unsigned grid = grid_for(P, kDwTiles * kHeadRows);
   cudaStream_t st = (cudaStream_t)stream;
   const bf16* hh = reinterpret_cast<const bf16*>(h);
-  if (k <= 4) head_logits_dw_kernel<4><<<grid, 256, smem, st>>>(dlogits, hh, dw, dbias, P, C, k, n_points);
-  else if (k <= 9) head_logits_dw_kernel<9><<<grid, 256, smem, st>>>(dlogits, hh, dw, dbias, P, C, k, n_points);
-  else head_logits_dw_kernel<kMaxLogits><<<grid, 256, smem, st>>>(dlogits, hh, dw, dbias, P, C, k, n_points);
+  if (k <= 4) head_logits_dw_kernel<4><<<grid, 256, smem, st>>>(dlogits, hh, dw, dbias, (int)P, C, k, n_points);
+  else if (k <= 9) head_logits_dw_kernel<9><<<grid, 256, smem, st>>>(dlogits, hh, dw, dbias, (int)P, C, k, n_points);
+  else head_logits_dw_kernel<kMaxLogits><<<grid, 256, smem, st>>>(dlogits, hh, dw, dbias, (int)P, C, k, n_points);
   S4G_LAUNCH_CHECK("train_head_logits_dw");
   return S4G_OK;
 }
 
-// inverse of the 3-NN index (B, Nq, 3) -> per sparse point (b, j) the list of entries e = (b * Nq + q) * 3 + k with
-// index[e] == j.  Step 1: count[B * Nk] (zeroed here).  The caller turns it into `end` = inclusive scan (int32).
-extern "C" int s4g_train_interp_inverse_count(const int* index, int B, int Nk, int Nq, int* count, void* stream) {
-  S4G_CHECK_ARG(index && count && B > 0 && Nk > 0 && Nq > 0 && (long long)B * Nq * 3 < (1ll << 31), "train_interp_inverse_count: bad arguments");
+// Inverse of an index tensor (B, E) with values in [0, T) — the 3-NN index (E = Nq * 3, T = Nk) or the ball-query
+// neighbour index (E = M * K, T = N): per target (b, j) the list of entries e = b * E + i with index[e] == j.
+// Step 1: count[B * T] (zeroed here).  The caller turns it into `end` = inclusive scan (int32).
+extern "C" int s4g_train_index_inverse_count(const int* index, int B, int T, long long E, int* count, void* stream) {
+  S4G_CHECK_ARG(index && count && B > 0 && T > 0 && E > 0 && (long long)B * E < (1ll << 31), "train_index_inverse_count: bad arguments");
   cudaStream_t st = (cudaStream_t)stream;
-  S4G_CUDA(cudaMemsetAsync(count, 0, sizeof(int) * (size_t)B * Nk, st));
-  const long long entries = (long long)B * Nq * 3;
-  interp_inverse_count_kernel<<<grid_for(entries, 256), 256, 0, st>>>(index, Nk, (long long)Nq * 3, entries, count);
-  S4G_LAUNCH_CHECK("train_interp_inverse_count");
+  S4G_CUDA(cudaMemsetAsync(count, 0, sizeof(int) * (size_t)B * T, st));
+  const long long entries = (long long)B * E;
+  interp_inverse_count_kernel<<<grid_for(entries, 256), 256, 0, st>>>(index, T, E, entries, count);
+  S4G_LAUNCH_CHECK("train_index_inverse_count");
   return S4G_OK;
 }
-// Step 2: cursor[B * Nk] = the lists' start offsets (end - count) on entry, advanced to their ends; list[B * Nq * 3].
-extern "C" int s4g_train_interp_inverse_fill(const int* index, int B, int Nk, int Nq, int* cursor, int* list, void* stream) {
-  S4G_CHECK_ARG(index && cursor && list && B > 0 && Nk > 0 && Nq > 0, "train_interp_inverse_fill: bad arguments");
-  const long long entries = (long long)B * Nq * 3;
-  interp_inverse_fill_kernel<<<grid_for(entries, 256), 256, 0, (cudaStream_t)stream>>>(index, Nk, (long long)Nq * 3, entries, cursor, list);
-  S4G_LAUNCH_CHECK("train_interp_inverse_fill");
+// Step 2: cursor[B * T] = the lists' start offsets (end - count) on entry, advanced to their ends; list[B * E].
+extern "C" int s4g_train_index_inverse_fill(const int* index, int B, int T, long long E, int* cursor, int* list, void* stream) {
+  S4G_CHECK_ARG(index && cursor && list && B > 0 && T > 0 && E > 0, "train_index_inverse_fill: bad arguments");
+  const long long entries = (long long)B * E;
+  interp_inverse_fill_kernel<<<grid_for(entries, 256), 256, 0, (cudaStream_t)stream>>>(index, T, E, entries, cursor, list);
+  S4G_LAUNCH_CHECK("train_index_inverse_fill");
   return S4G_OK;
 }
-// InterpolateBackward as a gather: out[b * Nk + j][c] = sum over the list of (b, j) of weight[e] * dx[e / 3][c]; written
-// (not accumulated) as fp32 and / or bf16 rows [B * Nk][C2] (either may be NULL).  The order inside a list is the fill's
-// (atomic cursor): the fp32 sum may differ in its last bits between runs, like the scatter's.
-extern "C" int s4g_train_interp_rows_bwd_gather(const void* dx, long long ld, const int* list, const int* end, const int* count,
-                                                const float* weight, int B, int Nk, int C2, float* out_f32, void* out_bf16,
-                                                void* stream) {
-  S4G_CHECK_ARG(dx && list && end && count && weight && (out_f32 || out_bf16) && B > 0 && Nk > 0 && C2 > 0 && C2 % 8 == 0 &&
-                    C2 <= 2048 && ld >= C2 && ld % 8 == 0,
-                "train_interp_rows_bwd_gather: bad arguments");
-  const long long sparse_rows = (long long)B * Nk;
-  const int lanes = 256 / (C2 >> 3);
-  interp_rows_bwd_gather_kernel<<<grid_for(sparse_rows, lanes), 256, 0, (cudaStream_t)stream>>>(
-      reinterpret_cast<const bf16*>(dx), ld, list, end, count, weight, sparse_rows, C2, out_f32, reinterpret_cast<bf16*>(out_bf16));
-  S4G_LAUNCH_CHECK("train_interp_rows_bwd_gather");
+// The scatter-add gradients as a gather: out[b * T + j][c] (+)= sum over the list of (b, j) of weight[e] * dx[e / div][c]
+// (div = 3 with weights: InterpolateBackward;  div = 1, weight NULL: GroupPointsBackward).  fp32 and / or bf16 rows
+// [B * T][C] (either may be NULL); accumulate != 0 adds into out_f32 (bf16 output then holds the sum as well).  The order
+// inside a list is the fill's (atomic cursor): the fp32 sum may differ in its last bits between runs, like the scatter's.
+extern "C" int s4g_train_rows_bwd_gather(const void* dx, long long ld, const int* list, const int* end, const int* count,
+                                         const float* weight, int div, long long targets, int C, int accumulate,
+                                         float* out_f32, void* out_bf16, void* stream) {
+  S4G_CHECK_ARG(dx && list && end && count && (out_f32 || out_bf16) && targets > 0 && C > 0 && C % 8 == 0 && C <= 2048 &&
+                    ld >= C && ld % 8 == 0 && (div == 1 || div == 3) && (!accumulate || out_f32),
+                "train_rows_bwd_gather: bad arguments");
+  const int lanes = 256 / (C >> 3);
+  const unsigned grid = grid_for(targets, lanes);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (div == 3)
+    rows_bwd_gather_kernel<3><<<grid, 256, 0, st>>>(reinterpret_cast<const bf16*>(dx), ld, list, end, count, weight, targets, C,
+                                                    accumulate, out_f32, reinterpret_cast<bf16*>(out_bf16));
+  else
+    rows_bwd_gather_kernel<1><<<grid, 256, 0, st>>>(reinterpret_cast<const bf16*>(dx), ld, list, end, count, weight, targets, C,
+                                                    accumulate, out_f32, reinterpret_cast<bf16*>(out_bf16));
+  S4G_LAUNCH_CHECK("train_rows_bwd_gather");
   return S4G_OK;
 }
 

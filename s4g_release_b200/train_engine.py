@@ -251,7 +251,7 @@ def _sum_rows(parts):
     return out
 
 
-# gradient of the interpolation as a gather over the inverted 3-NN index (no atomics, written once) or as the scatter
+# gradients of the interpolation and of the grouping as gathers over the inverted index (no atomics) or as scatters
 INTERP_BWD_GATHER = True
 
 
@@ -265,17 +265,37 @@ def interp_rows_backward(dz, idx3, w, B, Nk, Nq, c2, want_f32):
         check(lib.s4g_train_interp_rows_bwd(ptr(dz), dz.stride(0), ptr(idx3), ptr(w), B, Nk, Nq, c2, ptr(d_sparse), st),
               "train_interp_rows_bwd")
         return d_sparse if want_f32 else d_sparse.to(BF16)
-    count = torch.empty(B * Nk, dtype=torch.int32, device=dev)
-    check(lib.s4g_train_interp_inverse_count(ptr(idx3), B, Nk, Nq, ptr(count), st), "train_interp_inverse_count")
+    lst, end, count = _inverse_index(idx3, B, Nk, Nq * 3)
+    out = torch.empty((B * Nk, c2), dtype=torch.float32 if want_f32 else BF16, device=dev)
+    check(lib.s4g_train_rows_bwd_gather(ptr(dz), dz.stride(0), ptr(lst), ptr(end), ptr(count), ptr(w), 3, B * Nk, c2, 0,
+                                        ptr(out) if want_f32 else None, None if want_f32 else ptr(out), st),
+          "train_rows_bwd_gather")
+    return out
+
+
+def _inverse_index(index, B, T, E):
+    """index (B, E) int32 with values in [0, T) -> (list [B*E], end [B*T], count [B*T]): per target its entries"""
+    dev = index.device
+    st = stream_ptr(dev)
+    count = torch.empty(B * T, dtype=torch.int32, device=dev)
+    check(lib.s4g_train_index_inverse_count(ptr(index), B, T, E, ptr(count), st), "train_index_inverse_count")
     end = torch.cumsum(count, 0, dtype=torch.int32)
     cursor = end - count
-    lst = torch.empty(B * Nq * 3, dtype=torch.int32, device=dev)
-    check(lib.s4g_train_interp_inverse_fill(ptr(idx3), B, Nk, Nq, ptr(cursor), ptr(lst), st), "train_interp_inverse_fill")
-    out = torch.empty((B * Nk, c2), dtype=torch.float32 if want_f32 else BF16, device=dev)
-    check(lib.s4g_train_interp_rows_bwd_gather(ptr(dz), dz.stride(0), ptr(lst), ptr(end), ptr(count), ptr(w), B, Nk, c2,
-                                               ptr(out) if want_f32 else None, None if want_f32 else ptr(out), st),
-          "train_interp_rows_bwd_gather")
-    return out
+    lst = torch.empty(B * E, dtype=torch.int32, device=dev)
+    check(lib.s4g_train_index_inverse_fill(ptr(index), B, T, E, ptr(cursor), ptr(lst), st), "train_index_inverse_fill")
+    return lst, end, count
+
+
+def group_rows_backward(dz, nbr, B, N, M, K, cf, dfeat):
+    """dfeat[b*N + nbr[b,m,k]] += dz[(b,m,k)][:cf]  (dfeat fp32 [B*N, cf], may already hold the skip connection's gradient)"""
+    dev = dz.device
+    if not INTERP_BWD_GATHER:
+        check(lib.s4g_train_group_rows_bwd(ptr(dz), dz.stride(0), ptr(nbr), B, N, M, K, cf, ptr(dfeat), stream_ptr(dev)),
+              "train_group_rows_bwd")
+        return
+    lst, end, count = _inverse_index(nbr, B, N, M * K)
+    check(lib.s4g_train_rows_bwd_gather(ptr(dz), dz.stride(0), ptr(lst), ptr(end), ptr(count), None, 1, B * N, cf, 1,
+                                        ptr(dfeat), None, stream_ptr(dev)), "train_rows_bwd_gather")
 
 
 def _grad_buffer(param):
@@ -462,8 +482,7 @@ class TrainEngine:
             lv_grad[i + 1] = None
             dz = chain_backward(blocks, dz, need_dx=cf > 0)
             if cf > 0:
-                check(lib.s4g_train_group_rows_bwd(ptr(dz), dz.stride(0), ptr(nbr), B, N, M, K, cf, ptr(lv_grad[i]),
-                                                   stream_ptr(dev)), "train_group_rows_bwd")
+                group_rows_backward(dz, nbr, B, N, M, K, cf, lv_grad[i])
         self._sa_ctx = self._fp_ctx = None
 
     def _separable(self):

@@ -382,7 +382,7 @@ def test_dropout_mask_is_reproduced_in_backward():
     assert torch.isfinite(dx.float()).all()
 
 
-@pytest.mark.parametrize("k", [3, 9, 5])
+@pytest.mark.parametrize("k", [3, 9, 5, 16, 1])
 def test_head_logits_kernels(k):
     from s4g_release_b200._lib import check, lib, ptr, stream_ptr
     B, n, C = 3, 1000, 128
@@ -464,6 +464,13 @@ def test_group_rows_and_scatter_backward():
     want = torch.zeros(B, N, Cf, device="cuda").scatter_add_(1, idx.unsqueeze(-1).expand(-1, -1, Cf),
                                                              dx[:, :Cf].float().reshape(B, M * K, Cf)).reshape(-1, Cf)
     assert torch.allclose(dfeat, want, atol=1e-4, rtol=1e-5)
+    # the gather over the inverted neighbour index (what the engine uses) ADDS into a buffer that already holds a gradient
+    from s4g_release_b200 import train_engine as te
+    base = torch.randn(B * N, Cf, generator=g).cuda()
+    acc = base.clone()
+    te.group_rows_backward(dx, nbr, B, N, M, K, Cf, acc)
+    torch.cuda.synchronize()
+    assert torch.allclose(acc, base + want, atol=1e-4, rtol=1e-5)
 
 
 def test_interp_rows_backward():
