@@ -451,7 +451,9 @@ bn_bwd_apply_kernel(Upstream up, const __nv_bfloat16* __restrict__ y, const floa
 // upstream gradient is G x C, K times smaller than y, and stays on the read-only path); dy leaves with 16-byte stores
 // (RPL rows per thread and tile, STAGES tiles in flight, CONS consumer threads: 15 consumer warps + the producer warp = 512
 // threads get 128 registers each; with 16 + 1 warps ptxas allots 96 and the five per-channel parameter vectors spill)
-template <int RPL, int STAGES, int CONS>
+// DENSE / DROP are compile-time: the pooled pass (G x K rows, no dropout) carries neither the dropout hash nor the dense
+// branch, the dense pass not the routing
+template <int RPL, int STAGES, int CONS, bool DENSE, bool DROP>
 __global__ void __launch_bounds__(CONS + 32, 1)
 bn_bwd_apply_staged_kernel(Upstream up, const __nv_bfloat16* __restrict__ y, const float* __restrict__ scale,
                            const float* __restrict__ shift, const float* __restrict__ ka, const float* __restrict__ kb,
@@ -465,7 +467,7 @@ bn_bwd_apply_staged_kernel(Upstream up, const __nv_bfloat16* __restrict__ y, con
   const unsigned tile_bytes = (unsigned)R * (unsigned)C * 2u;
   const long long n_tiles = (P + R - 1) / R;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const bool dense = up.K == 0;
+  constexpr bool dense = DENSE;
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) {
       asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(stg_u32(&full[s])));
@@ -532,7 +534,7 @@ bn_bwd_apply_staged_kernel(Upstream up, const __nv_bfloat16* __restrict__ y, con
         for (int e = 0; e < 8; ++e) {
           float g = d.v[e];
           if (relu && !(fmaf(v.v[e], a.v[e], b.v[e]) > 0.f)) g = 0.f;
-          if (thresh) g = keep_elem(seed, row0 + rr, piece * 8 + e, C, thresh) ? g * keep_scale : 0.f;
+          if (DROP) g = keep_elem(seed, row0 + rr, piece * 8 + e, C, thresh) ? g * keep_scale : 0.f;
           o.v[e] = fmaf(A.v[e], g, fmaf(Bc.v[e], v.v[e], Cc.v[e]));
         }
         reinterpret_cast<uint4*>(dy + (row0 + rr) * C)[piece] = pack8(o);
@@ -1047,13 +1049,22 @@ extern "C" int s4g_train_bn_bwd_apply_bf16(const void* dz, const uint8_t* arg, i
     const size_t smem = (size_t)kStages * 2 * R * C * 2;
     static bool attr[64] = {};
     if (s4g::first_use_on_device(attr)) {
-      S4G_CUDA(cudaFuncSetAttribute(bn_bwd_apply_staged_kernel<kRpl, kStages, kCons>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+      S4G_CUDA(cudaFuncSetAttribute(bn_bwd_apply_staged_kernel<kRpl, kStages, kCons, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+      S4G_CUDA(cudaFuncSetAttribute(bn_bwd_apply_staged_kernel<kRpl, kStages, kCons, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+      S4G_CUDA(cudaFuncSetAttribute(bn_bwd_apply_staged_kernel<kRpl, kStages, kCons, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+      S4G_CUDA(cudaFuncSetAttribute(bn_bwd_apply_staged_kernel<kRpl, kStages, kCons, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     }
     const long long n_tiles = (P + R - 1) / R;
     const int sms = s4g::num_sms();
-    bn_bwd_apply_staged_kernel<kRpl, kStages, kCons><<<(unsigned)(n_tiles < sms ? n_tiles : sms), kCons + 32, smem, (cudaStream_t)stream>>>(
-        up, reinterpret_cast<const bf16*>(y), scale, shift, ka, kb, kc, P, C, relu, seed, thresh, 1.f / (1.f - drop_p),
-        reinterpret_cast<bf16*>(dy));
+    const unsigned grid = (unsigned)(n_tiles < sms ? n_tiles : sms);
+    cudaStream_t st = (cudaStream_t)stream;
+    const float ks = 1.f / (1.f - drop_p);
+#define S4G_APPLY_GO(DENSE_, DROP_)                                                                                        \
+  bn_bwd_apply_staged_kernel<kRpl, kStages, kCons, DENSE_, DROP_><<<grid, kCons + 32, smem, st>>>(                          \
+      up, reinterpret_cast<const bf16*>(y), scale, shift, ka, kb, kc, P, C, relu, seed, thresh, ks, reinterpret_cast<bf16*>(dy))
+    if (K == 0) { if (thresh) S4G_APPLY_GO(true, true); else S4G_APPLY_GO(true, false); }
+    else { if (thresh) S4G_APPLY_GO(false, true); else S4G_APPLY_GO(false, false); }
+#undef S4G_APPLY_GO
   } else {
     bn_bwd_apply_kernel<<<grid_for(P, kEltRows), 256, 0, (cudaStream_t)stream>>>(
         up, reinterpret_cast<const bf16*>(y), scale, shift, ka, kb, kc, P, C, relu, seed, thresh, 1.f / (1.f - drop_p),
