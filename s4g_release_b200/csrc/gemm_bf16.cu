@@ -25,8 +25,9 @@
 //     profiles/r02/ncu_training.txt: 128 -> 128 and 128 -> 256 on 10.5 M rows both at ~3 000 cycles per tile, 75 % resp.
 //     58 % of the DRAM peak although the tile's traffic differs by 1.35 x); with 256-column tiles they split every tile.
 //   What bounds a layer (profiles/r02/gemm_layers_v6.txt): HBM for the 10.5 M-row layers (0.9-1.0 of the copy bandwidth);
-//   for K, N >= 512 the operand traffic L2 -> SM (~40 B per cycle and SM, 11 TB/s in all: 384 KB per 128 x 256 x 512
-//   tile) — a cluster multicast of the shared operand is the next step there.
+//   for K, N >= 512 latency x bytes in flight (ncu, profiles/r02/ncu_gemm_tile256.txt: tensor pipe 47 %, L2 35 %, DRAM
+//   33 % of their peaks, stalls on the operand loads; the 144 KB ring turns over once per ~2 us and the shared memory is
+//   full) — sharing the weight slab in a CTA pair / cluster multicast is the next step there.
 //
 // BWD (input-gradient GEMM of block l, dX = dY W): the output tile IS the upstream gradient of block l-1, so the epilogue
 // also does what the first pass of that block's BatchNorm backward would do: the producer warp fetches the matching
