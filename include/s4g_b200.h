@@ -149,6 +149,10 @@ int s4g_gemm_bf16_set_epilogue_groups(int groups);
 /* A/B switch (measurements): output columns per tile, 128 or 256 (one N = 256 MMA per K step, two epilogue groups splitting
  * the tile; streaming schedule), 0 (default) = chosen per launch.  Returns the previous setting.  Same bits. */
 int s4g_gemm_bf16_set_tile_n(int bn);
+/* The launch the three GEMM entry points (mode 0 = s4g_gemm_bf16, 1 = _stats, 2 = _bwd) would make for a shape on a GPU with
+ * `sms` SMs (0 = the current device): out7 = {tile columns, epilogue groups, weight-stationary, ring stages, grid, threads,
+ * dynamic shared memory bytes}.  Host arithmetic only (the CPU tests check the shared-memory budget with it). */
+int s4g_gemm_bf16_plan(long long P, int N, int K, int mode, int sms, long long* out7);
 /* Input-gradient GEMM whose RESULT is the upstream gradient of the block that produced y_prev (its rows [P][N] before
  * BatchNorm; scale / shift = its folded BatchNorm; relu / seed / drop_p = its activation and dropout):
  *   c = (a · b^T) * relu'(y_prev * scale + shift) * dropout mask     (stored MASKED, bf16)

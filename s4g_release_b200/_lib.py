@@ -64,6 +64,7 @@ _SIGNATURES = {
     "s4g_gemm_bf16_set_weight_stationary": ([_i], _i),
     "s4g_gemm_bf16_set_epilogue_groups": ([_i], _i),
     "s4g_gemm_bf16_set_tile_n": ([_i], _i),
+    "s4g_gemm_bf16_plan": ([_ll, _i, _i, _i, _i, _vp], _i),
     "s4g_gemm_bf16_bwd": ([_vp, _ll, _vp, _ll, _vp, _ll, _ll, _i, _i, _vp, _ll, _vp, _vp, _i, ctypes.c_uint, _f, _vp, _vp], _i),
     "s4g_gemm_bf16_stats": ([_vp, _ll, _vp, _ll, _vp, _ll, _ll, _i, _i, _vp, _vp], _i),
     "s4g_train_bn_finalize": ([_vp, _ll, _i, _vp, _vp, _f, _f, _vp, _vp, _vp, _vp], _i),

@@ -64,7 +64,6 @@ constexpr int kMaxSlabsWS = 8;                     // K <= 512
 constexpr int kTile = 128;
 constexpr int kSlab = 64;                          // K elements per stage: 64 bf16 = 128 B
 constexpr int kOperandBytes = kTile * kSlab * 2;   // 16 KB
-constexpr int kStageBytes = 2 * kOperandBytes;
 constexpr int kStagingBytes = kTile * kTile * 2;    // 32 KB: the bf16 output tile as two {64 columns, 128 rows} swizzled halves
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -492,16 +491,16 @@ extern "C" int s4g_gemm_bf16_set_tile_n(int bn) {
   return prev;
 }
 
-static int gemm_launch(const void* a, long long lda, const void* b, long long ldb, void* c, long long ldc, long long P, int N,
-                       int K, int mode, double* stats, const s4g::gemm::BwdEpilogue& bw, void* stream) {
+// How one launch is laid out: tile width, epilogue groups, schedule, ring depth, shared memory, grid.  Pure host arithmetic
+// (exported as s4g_gemm_bf16_plan so that the CPU tests can check the shared-memory budget of every shape of the model).
+struct GemmPlan {
+  int bn, groups, ws, n_stages, grid, threads;
+  long long smem;
+};
+constexpr int kMaxDynSmem = 226 * 1024;  // (the kernel also has ~170 bytes of static shared memory; the limit is 227 KB)
+
+static int plan_gemm(long long P, int N, int K, int mode, int sms, GemmPlan* out) {
   using namespace s4g::gemm;
-  S4G_CHECK_ARG(a && b && c, "gemm_bf16: null pointer");
-  S4G_CHECK_ARG(P >= 0 && P < (1ll << 31) - kTile && N > 0 && K > 0, "gemm_bf16: bad shape");
-  S4G_CHECK_ARG(lda >= K && ldb >= K && ldc >= N, "gemm_bf16: leading dimension smaller than the row");
-  S4G_CHECK_ARG(lda % 8 == 0 && ldb % 8 == 0 && ldc % 8 == 0 && ((uintptr_t)a & 15) == 0 && ((uintptr_t)b & 15) == 0 &&
-                    ((uintptr_t)c & 15) == 0,
-                "gemm_bf16: rows must be 16-byte aligned (leading dimensions multiples of 8 bf16)");
-  if (P == 0) return S4G_OK;
   const int n_slabs = (K + kSlab - 1) / kSlab;
   const long long tiles_m = (P + kTile - 1) / kTile;
   // 256-column tiles (streaming schedule, two epilogue groups splitting the tile): where the MMA-issuing thread sets the
@@ -513,20 +512,7 @@ static int gemm_launch(const void* a, long long lda, const void* b, long long ld
     if (g_tile_n == 256) bn = 256;
     else if (g_tile_n == 0 && n_slabs >= 4 && (K % kSlab == 0 || n_slabs >= 8)) bn = 256;
   }
-  CUtensorMap ma, mb;
-  int rc = encode_bf16_map(&ma, a, K, lda, P);
-  if (rc != S4G_OK) return rc;
-  rc = encode_bf16_map(&mb, b, K, ldb, N, bn);
-  if (rc != S4G_OK) return rc;
-  CUtensorMap mc;
-  rc = encode_bf16_map(&mc, c, N, ldc, P);
-  if (rc != S4G_OK) return rc;
   const int tiles_n = (N + bn - 1) / bn;
-  CUtensorMap my = mc;
-  if (mode == kBwd) {
-    rc = encode_bf16_map(&my, bw.y, N, bw.ldy, P);
-    if (rc != S4G_OK) return rc;
-  }
   // epilogue groups: two pay where the epilogue, not HBM or the tensor pipe, sets the pace — short K (<= 2 slabs: measured
   // 3 -> 128 on 10.5 M rows 0.82 -> 0.55 ms, 128 -> 256 1.63 -> 1.28 ms); with more slabs per tile the second staging tile
   // only costs ring stages (264 -> 256 on 2.1 M rows 0.49 -> 0.64 ms: it loses the weight-stationary schedule).  The BWD
@@ -534,14 +520,12 @@ static int gemm_launch(const void* a, long long lda, const void* b, long long ld
   const int groups = bn == 256 ? 2 : mode == kBwd ? 1 : g_epi_groups ? g_epi_groups : (n_slabs <= 2 ? 2 : 1);
   // per-column sums in shared memory
   const size_t table_bytes = sizeof(float) * (size_t)tiles_n * bn * (mode == kPlain ? 0 : 2);
-  constexpr int kMaxDynSmem = 226 * 1024;  // (the kernel also has ~170 bytes of static shared memory; the limit is 227 KB)
   const long long room = (long long)kMaxDynSmem - 1024 - (long long)(groups + (mode == kBwd ? 2 : 0)) * kStagingBytes -
                          (long long)table_bytes;
   const int stage_bytes = kOperandBytes + (bn / kTile) * kOperandBytes;
   S4G_CHECK_ARG(room >= 2LL * stage_bytes, "gemm_bf16: too many output columns for the fused statistics");
   // weight-stationary when the B slice fits beside >= 5 A stages and every CTA gets >= 2 m-tiles
   // (K = 512 with 3 A stages beside its 128 KB slice: measured 20-30 % SLOWER than streaming)
-  const int sms = s4g::num_sms();
   int n_stages = (int)(room / stage_bytes);
   if (n_stages > kStages) n_stages = kStages;
   bool ws = false;
@@ -553,6 +537,55 @@ static int gemm_launch(const void* a, long long lda, const void* b, long long ld
   }
   const size_t smem = 1024 + (size_t)(groups + (mode == kBwd ? 2 : 0)) * kStagingBytes + table_bytes +
                       (ws ? (size_t)(n_slabs + n_stages) * kOperandBytes : (size_t)n_stages * stage_bytes);
+  const long long tiles = tiles_m * tiles_n;
+  int grid = (int)(tiles < sms ? tiles : sms);
+  if (ws) grid = (sms / tiles_n) * tiles_n;  // every n-tile gets the same number of CTAs
+  *out = GemmPlan{bn, groups, ws ? 1 : 0, n_stages, grid, 64 + 128 * groups + 32, (long long)smem};
+  return S4G_OK;
+}
+
+// out7 = {tile columns, epilogue groups, weight-stationary, ring stages, grid, threads, dynamic shared memory bytes} of the
+// launch s4g_gemm_bf16 / _stats / _bwd (mode 0 / 1 / 2) would make for this shape on a GPU with `sms` SMs (0 = the current
+// device).  No GPU work.
+extern "C" int s4g_gemm_bf16_plan(long long P, int N, int K, int mode, int sms, long long* out7) {
+  S4G_CHECK_ARG(out7 && P > 0 && N > 0 && K > 0 && mode >= 0 && mode <= 2, "gemm_bf16_plan: bad arguments");
+  GemmPlan pl;
+  const int rc = plan_gemm(P, N, K, mode, sms > 0 ? sms : s4g::num_sms(), &pl);
+  if (rc != S4G_OK) return rc;
+  out7[0] = pl.bn; out7[1] = pl.groups; out7[2] = pl.ws; out7[3] = pl.n_stages; out7[4] = pl.grid; out7[5] = pl.threads;
+  out7[6] = pl.smem;
+  return S4G_OK;
+}
+
+static int gemm_launch(const void* a, long long lda, const void* b, long long ldb, void* c, long long ldc, long long P, int N,
+                       int K, int mode, double* stats, const s4g::gemm::BwdEpilogue& bw, void* stream) {
+  using namespace s4g::gemm;
+  S4G_CHECK_ARG(a && b && c, "gemm_bf16: null pointer");
+  S4G_CHECK_ARG(P >= 0 && P < (1ll << 31) - kTile && N > 0 && K > 0, "gemm_bf16: bad shape");
+  S4G_CHECK_ARG(lda >= K && ldb >= K && ldc >= N, "gemm_bf16: leading dimension smaller than the row");
+  S4G_CHECK_ARG(lda % 8 == 0 && ldb % 8 == 0 && ldc % 8 == 0 && ((uintptr_t)a & 15) == 0 && ((uintptr_t)b & 15) == 0 &&
+                    ((uintptr_t)c & 15) == 0,
+                "gemm_bf16: rows must be 16-byte aligned (leading dimensions multiples of 8 bf16)");
+  if (P == 0) return S4G_OK;
+  GemmPlan pl;
+  int rc = plan_gemm(P, N, K, mode, s4g::num_sms(), &pl);
+  if (rc != S4G_OK) return rc;
+  const int bn = pl.bn, groups = pl.groups, n_stages = pl.n_stages, grid = pl.grid, threads = pl.threads;
+  const bool ws = pl.ws != 0;
+  const size_t smem = (size_t)pl.smem;
+  CUtensorMap ma, mb;
+  rc = encode_bf16_map(&ma, a, K, lda, P);
+  if (rc != S4G_OK) return rc;
+  rc = encode_bf16_map(&mb, b, K, ldb, N, bn);
+  if (rc != S4G_OK) return rc;
+  CUtensorMap mc;
+  rc = encode_bf16_map(&mc, c, N, ldc, P);
+  if (rc != S4G_OK) return rc;
+  CUtensorMap my = mc;
+  if (mode == kBwd) {
+    rc = encode_bf16_map(&my, bw.y, N, bw.ldy, P);
+    if (rc != S4G_OK) return rc;
+  }
   static bool attr_set[64] = {};
   if (s4g::first_use_on_device(attr_set)) {
     S4G_CUDA(cudaFuncSetAttribute(gemm_bf16_kernel<kPlain, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
@@ -562,10 +595,6 @@ static int gemm_launch(const void* a, long long lda, const void* b, long long ld
     S4G_CUDA(cudaFuncSetAttribute(gemm_bf16_kernel<kBwd, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
     S4G_CUDA(cudaFuncSetAttribute(gemm_bf16_kernel<kBwd, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
   }
-  const long long tiles = tiles_m * tiles_n;
-  int grid = (int)(tiles < sms ? tiles : sms);
-  if (ws) grid = (sms / tiles_n) * tiles_n;  // every n-tile gets the same number of CTAs
-  const int threads = 64 + 128 * groups + 32;
   cudaStream_t st = (cudaStream_t)stream;
   if (stats) S4G_CUDA(cudaMemsetAsync(stats, 0, sizeof(double) * 2 * N, st));
 #define S4G_GEMM_GO(MODE_, WS_) \

@@ -100,3 +100,52 @@ def test_engine_refuses_a_model_without_a_fused_plan():
 
     with pytest.raises(RuntimeError):
         te.TrainEngine(_NoPlan(), None)
+
+
+# ---------------------------------------------------------------- the GEMM's launch planning (host arithmetic, no GPU)
+def _plan(P, N, K, mode, sms=148):
+    import ctypes
+    from s4g_release_b200._lib import check, lib
+    out = (ctypes.c_longlong * 7)()
+    check(lib.s4g_gemm_bf16_plan(P, N, K, mode, sms, ctypes.cast(out, ctypes.c_void_p)), "gemm_bf16_plan")
+    return dict(zip(("bn", "groups", "ws", "stages", "grid", "threads", "smem"), list(out)))
+
+
+def _model_gemm_shapes(scenes):
+    """(rows, K, N) of every conv of PN2_CLS at `scenes` scenes: set abstraction, propagation, heads"""
+    r0, r1, r2, rp = scenes * 5120 * 64, scenes * 1024 * 64, scenes * 256 * 64, scenes * 25600
+    fwd = [(r0, 8, 128), (r0, 128, 128), (r0, 128, 256), (r1, 264, 256), (r1, 256, 256), (r1, 256, 512), (r2, 520, 512),
+           (r2, 512, 512), (r2, 512, 1024), (scenes * 1024, 1536, 1024), (scenes * 1024, 1024, 512), (scenes * 5120, 768, 512),
+           (scenes * 5120, 512, 512), (rp, 512, 256), (rp, 256, 256), (rp, 256, 512), (rp, 512, 256), (rp, 256, 128)]
+    return fwd
+
+
+@pytest.mark.parametrize("scenes", [1, 2, 32, 64])
+def test_gemm_plans_fit_the_shared_memory_of_an_sm(scenes):
+    limit = 227 * 1024 - 256  # dynamic + ~176 B static
+    for rows, K, N in _model_gemm_shapes(scenes):
+        for mode, (k, n) in ((0, (K, N)), (1, (K, N)), (0, (N, K)), (2, (N, (K + 7) // 8 * 8))):  # forward, dX, dX + reduce
+            p = _plan(rows, n, k, mode)
+            assert 0 < p["smem"] <= limit, (rows, k, n, mode, p)
+            assert p["stages"] >= 2 and p["threads"] in (224, 352) and 1 <= p["grid"] <= 148, (rows, k, n, mode, p)
+            assert p["bn"] in (128, 256) and p["groups"] in (1, 2)
+            if p["bn"] == 256:
+                assert p["groups"] == 2 and p["ws"] == 0 and n > 128
+            if mode == 2:
+                assert p["bn"] == 128 and p["groups"] == 1
+
+
+def test_gemm_plan_rules_follow_the_measurements():
+    """the per-shape choices DESIGN.md §3 "Training" reports (profiles/r02/gemm_layers_v6.txt)"""
+    R0, R1, R2 = 32 * 5120 * 64, 32 * 1024 * 64, 32 * 256 * 64
+    p = _plan(R0, 128, 8, 1)        # one K slab: epilogue-bound -> two groups alternating tiles, weights resident
+    assert (p["bn"], p["groups"], p["ws"]) == (128, 2, 1)
+    p = _plan(R0, 256, 128, 1)
+    assert (p["bn"], p["groups"], p["ws"]) == (128, 2, 1)
+    p = _plan(R1, 256, 264, 1)      # a fifth slab of 8 columns: stays on the weight-stationary 128-column schedule
+    assert (p["bn"], p["groups"], p["ws"]) == (128, 1, 1)
+    for rows, K, N in ((R1, 256, 512), (R2, 512, 1024), (R2, 520, 512), (32 * 25600, 512, 256)):
+        p = _plan(rows, N, K, 1)    # many K steps per tile: one N = 256 MMA per step, the groups split the tile
+        assert (p["bn"], p["groups"], p["ws"], p["stages"]) == (256, 2, 0, 3), (rows, K, N, p)
+    p = _plan(100, 16, 128, 0)      # a tiny problem: one CTA per tile
+    assert p["grid"] == 1
